@@ -1,0 +1,258 @@
+/*
+ * swfr.h - C ABI of libswfr_b200.so, the B200-native (sm_100a) replacement for the shape -> pixels path
+ * of open-flash/swf-renderer.
+ *
+ * The boundary mirrors the reference Rust crate's public API (the crate keeps its traits; a Rust shim binds
+ * these entry points).  Every entry point cites the reference interface it replaces,
+ * paths relative to the reference repository:
+ *
+ *   swfr_create / swfr_destroy        HeadlessGfxRenderer::new / Drop         rs/src/headless_renderer.rs:60-64, 871-904
+ *                                     createRenderer / destroyRenderer        rs/src/wasm.rs:60-99
+ *   swfr_register_shape               ClientAssetStore::register_shape        rs/src/asset.rs:9-12
+ *                                     HeadlessGfxRenderer::define_shape       rs/src/headless_renderer.rs:229-231
+ *                                     decodeSwfShape (compile, cached)        ts/src/lib/shape/decode-swf-shape.ts:22-39
+ *   swfr_register_morph_shape         ClientAssetStore::register_morph_shape  rs/src/asset.rs:9-12
+ *                                     decodeSwfMorphShape                     ts/src/lib/shape/decode-swf-morph-shape.ts:21-41
+ *   swfr_register_bitmap[_xswfbmp]    Renderer.addBitmap(tag)                 ts/src/lib/renderer.ts:4-8
+ *                                     NodeCanvasBitmapService.addBitmap       ts/src/lib/renderers/node-canvas-bitmap-service.ts:14-37
+ *                                     decodeXSwfBmpSync                       ts/src/lib/decode-x-swf-bmp.ts:9-41
+ *   swfr_render                       SwfRenderer::render(stage)              rs/src/swf_renderer.rs:3-5
+ *                                     Renderer::set_stage + get_image         rs/src/renderer.rs:81-87, headless_renderer.rs:233-244
+ *                                     CanvasRenderer.render(stage)            ts/src/lib/renderers/canvas-renderer.ts:61-78
+ *   swfr_render_batch                 the same, N stages per launch (frame batches / morph-ratio sweeps)
+ *   swfr_read_image                   HeadlessGfxRenderer::download_image     rs/src/headless_renderer.rs:725-868
+ *                                     Image{meta{width,height,stride},data}   rs/src/renderer.rs:89-103
+ *                                     canvas.toBuffer("image/png") un-premultiply  ts/src/test/node-canvas-renderer.spec.ts:134-147
+ *   swfr_debug_*                      parity taps (no reference counterpart)
+ *
+ * Conventions: every function returns a swfr_status (0 = ok, negative = error; the reference's
+ * &'static str / panic / throw sites map to these codes).  Inputs are borrowed for the duration of the call
+ * only (as register_shape(&tag) borrows); outputs are caller-allocated.  A handle owns one CUDA device and one
+ * stream and is NOT thread-safe (the reference takes &mut self); different handles may be driven from different
+ * threads or processes (that is how frames are sharded over 8 GPUs).  There is no CPU fallback: without a CUDA
+ * device swfr_create fails with SWFR_ERR_CUDA.
+ */
+#ifndef SWFR_H
+#define SWFR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWFR_ABI_VERSION 1
+
+typedef enum swfr_status {
+  SWFR_OK = 0,
+  SWFR_ERR_INVALID_HANDLE = -1,
+  SWFR_ERR_INVALID_ID = -2,        /* unknown shape / morph shape / bitmap id (reference: panic, BitmapNotFound) */
+  SWFR_ERR_INVALID_FILL_ID = -3,   /* "Invalid fill ID" (decode-swf-shape.ts:418-420) */
+  SWFR_ERR_UNSUPPORTED_STYLE = -4, /* NotImplementedFillStyle / NotImplementedLineStyle / "Unknown fill type" */
+  SWFR_ERR_OOM = -5,
+  SWFR_ERR_CUDA = -6,
+  SWFR_ERR_INVALID_ARGUMENT = -7,
+  SWFR_ERR_MALFORMED = -8          /* e.g. morph move_to without morph_move_to, bad x-swf-bmp stream */
+} swfr_status;
+
+typedef struct swfr_renderer swfr_renderer; /* opaque */
+typedef struct swfr_batch swfr_batch;       /* opaque: a set of stages resident in HBM */
+
+/* ---- swf-tree 0.8.0 POD mirrors (a Rust shim converts #[repr(C)] field by field) ------------------- */
+
+typedef struct swfr_rgba8 { uint8_t r, g, b, a; } swfr_rgba8; /* swf_tree::StraightSRgba8 */
+
+/* swf_tree::Matrix: Sfixed16P16 epsilons + twips translation */
+typedef struct swfr_swf_matrix {
+  int32_t scale_x, scale_y, rotate_skew0, rotate_skew1;
+  int32_t translate_x, translate_y;
+} swfr_swf_matrix;
+
+typedef enum swfr_fill_type {
+  SWFR_FILL_SOLID = 0,
+  SWFR_FILL_LINEAR_GRADIENT = 1,
+  SWFR_FILL_RADIAL_GRADIENT = 2,
+  SWFR_FILL_FOCAL_GRADIENT = 3,
+  SWFR_FILL_BITMAP = 4
+} swfr_fill_type;
+
+typedef enum swfr_spread { SWFR_SPREAD_PAD = 0, SWFR_SPREAD_REFLECT = 1, SWFR_SPREAD_REPEAT = 2 } swfr_spread;
+typedef enum swfr_color_space { SWFR_COLOR_SRGB = 0, SWFR_COLOR_LINEAR_RGB = 1 } swfr_color_space;
+
+typedef struct swfr_color_stop {
+  uint8_t ratio;
+  swfr_rgba8 color;
+  swfr_rgba8 morph_color; /* morph shapes only */
+} swfr_color_stop;
+
+typedef struct swfr_gradient {
+  uint8_t spread;      /* swfr_spread */
+  uint8_t color_space; /* swfr_color_space */
+  uint16_t n_colors;
+  const swfr_color_stop *colors;
+} swfr_gradient;
+
+typedef struct swfr_fill_style {
+  uint32_t type; /* swfr_fill_type */
+  swfr_rgba8 color;
+  swfr_rgba8 morph_color; /* morph shapes only */
+  swfr_swf_matrix matrix;
+  swfr_gradient gradient;
+  int16_t focal_point; /* Sfixed8P8 epsilons */
+  uint16_t bitmap_id;
+  uint8_t repeating;
+  uint8_t smoothed; /* carried, ignored like the reference (canvas-renderer.ts:295-316) */
+} swfr_fill_style;
+
+typedef struct swfr_line_style {
+  uint16_t width;       /* twips */
+  uint16_t morph_width; /* morph shapes only */
+  swfr_fill_style fill;
+  /* caps / joins / scaling flags of LineStyle2 are not consulted by the reference renderer */
+} swfr_line_style;
+
+typedef struct swfr_styles {
+  uint32_t n_fill;
+  const swfr_fill_style *fill;
+  uint32_t n_line;
+  const swfr_line_style *line;
+} swfr_styles;
+
+typedef enum swfr_record_type { SWFR_RECORD_EDGE = 0, SWFR_RECORD_STYLE_CHANGE = 1 } swfr_record_type;
+
+/* swf_tree::ShapeRecord / MorphShapeRecord as a tagged POD */
+typedef struct swfr_shape_record {
+  uint32_t type; /* swfr_record_type */
+  /* edge */
+  int32_t delta_x, delta_y;
+  int32_t control_delta_x, control_delta_y;
+  int32_t morph_delta_x, morph_delta_y;
+  int32_t morph_control_delta_x, morph_control_delta_y;
+  uint8_t has_control_delta, has_morph_control_delta;
+  /* style change */
+  uint8_t has_move_to, has_morph_move_to, has_left_fill, has_right_fill, has_line_style, has_new_styles;
+  int32_t move_to_x, move_to_y;
+  int32_t morph_move_to_x, morph_move_to_y;
+  uint32_t left_fill, right_fill, line_style;
+  const swfr_styles *new_styles;
+} swfr_shape_record;
+
+/* swf_tree::tags::DefineShape / DefineMorphShape (fields the renderer reads) */
+typedef struct swfr_define_shape {
+  uint16_t id;
+  int32_t bounds[4];       /* x_min, x_max, y_min, y_max (twips) */
+  int32_t morph_bounds[4]; /* morph shapes only */
+  swfr_styles initial_styles;
+  uint32_t n_records;
+  const swfr_shape_record *records;
+} swfr_define_shape;
+
+/* ---- stage (rs/src/stage.rs:4-59) ------------------------------------------------------------------- */
+
+typedef enum swfr_primitive_kind { SWFR_PRIM_SHAPE = 0, SWFR_PRIM_MORPH_SHAPE = 1 } swfr_primitive_kind;
+
+/* DisplayPrimitive::{Shape(StoredShape), MorphShape(StoredMorphShape)} */
+typedef struct swfr_display_primitive {
+  uint32_t kind;   /* swfr_primitive_kind */
+  uint32_t id;     /* ShapeId / MorphShapeId returned by swfr_register_* */
+  float matrix[6]; /* Matrix2D: [scale_x, scale_y, rotate_skew0, rotate_skew1, translate_x, translate_y];
+                      x' = m0*x + m3*y + m4, y' = m2*x + m1*y + m5 (twips) */
+  uint16_t ratio;  /* MorphRatio: 0 = start, 65535 = end */
+  uint16_t reserved;
+} swfr_display_primitive;
+
+typedef struct swfr_stage {
+  swfr_rgba8 background_color; /* carried; the reference TS renderer ignores it (canvas-renderer.ts:70-72) */
+  uint32_t n_primitives;
+  const swfr_display_primitive *display_root;
+} swfr_stage;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+
+/* Creates a renderer with a width x height RGBA8 viewport on CUDA device `device`, with its own stream. */
+int swfr_create(int device, uint32_t width, uint32_t height, swfr_renderer **out);
+/* Same, but all work is enqueued on an existing CUDA stream (a cudaStream_t passed as void*). */
+int swfr_create_on_stream(int device, uint32_t width, uint32_t height, void *cuda_stream, swfr_renderer **out);
+void swfr_destroy(swfr_renderer *r);
+const char *swfr_last_error(const swfr_renderer *r);
+const char *swfr_status_string(int status);
+uint32_t swfr_abi_version(void);
+
+/* Options: SWFR_OPT_RETAIN_COMPILED (default 1) keeps the compiled paths of every definition on the host for
+ * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 4) bounds how many frames
+ * share one set of launches and one working set. */
+typedef enum swfr_option { SWFR_OPT_RETAIN_COMPILED = 1, SWFR_OPT_FRAMES_PER_PASS = 2 } swfr_option;
+int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value);
+
+/* ---- asset store ------------------------------------------------------------------------------------ */
+
+int swfr_register_shape(swfr_renderer *r, const swfr_define_shape *tag, uint32_t *out_shape_id);
+int swfr_register_morph_shape(swfr_renderer *r, const swfr_define_shape *tag, uint32_t *out_morph_shape_id);
+/* straight (non-premultiplied) RGBA8 rows, `stride` bytes apart */
+int swfr_register_bitmap(swfr_renderer *r, uint16_t bitmap_id, uint32_t width, uint32_t height, const uint8_t *rgba,
+                         size_t stride);
+/* DefineBitmap with media type image/x-swf-bmp (format 3: colormapped 8-bit + zlib) */
+int swfr_register_bitmap_xswfbmp(swfr_renderer *r, uint16_t bitmap_id, const uint8_t *data, size_t len);
+/* The decoder alone (host only): writes straight RGBA8 when `rgba` is non-NULL and cap is large enough. */
+int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t cap, uint32_t *width, uint32_t *height);
+
+/* ---- rendering -------------------------------------------------------------------------------------- */
+
+/* Renders one stage into frame 0.  Asynchronous on the renderer's stream. */
+int swfr_render(swfr_renderer *r, const swfr_stage *stage);
+/* Renders n stages into frames 0..n-1 with one set of launches. */
+int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n);
+
+/* Stages kept resident in HBM, for repeated rendering without host traffic. */
+int swfr_batch_create(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_batch **out);
+int swfr_batch_render(swfr_renderer *r, swfr_batch *batch);
+void swfr_batch_destroy(swfr_renderer *r, swfr_batch *batch);
+
+int swfr_sync(swfr_renderer *r);
+
+/* Copies frame `frame` of the last render to host memory: RGBA8, `stride` >= 4*width bytes per row.
+ * premultiplied != 0 returns the canvas' internal premultiplied pixels; 0 returns straight alpha with the
+ * PNG-export rounding of the reference test (c = (c*255 + a/2) / a).  Synchronises the stream. */
+int swfr_read_image(swfr_renderer *r, uint32_t frame, uint8_t *dst, size_t stride, int premultiplied);
+/* Copies frames [first, first+count) premultiplied and tightly packed (width*height*4 bytes each) into pinned
+ * or pageable host memory without synchronising; pair with swfr_sync. */
+int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uint8_t *dst);
+/* Device pointer of frame 0 of the last render (premultiplied RGBA8, frames width*height*4 bytes apart). */
+int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n_frames);
+
+/* ---- statistics of the last render (after swfr_sync) ------------------------------------------------ */
+
+typedef struct swfr_stats {
+  uint64_t n_primitives, n_path_instances, n_segments, n_edges, n_slots, n_records, n_tiles;
+  uint64_t algorithmic_bytes; /* B_seg + B_draw + 2*8*E_tile + 4*W*H per frame, summed */
+  uint32_t kernel_launches;   /* kernels launched by the last swfr_*render* call */
+  uint32_t retries;           /* re-runs caused by working-memory growth */
+} swfr_stats;
+int swfr_get_stats(swfr_renderer *r, swfr_stats *out);
+
+/* ---- parity taps ------------------------------------------------------------------------------------ */
+
+/* Compiled path commands of a registered definition, in the reference's CommandType encoding
+ * (LineTo=0, CurveTo=1, MoveTo=2; ts/src/lib/shape/path.ts:4-8).  Per command 1 + 8 doubles:
+ * type, then x/endX, y/endY, controlX, controlY for the start state and the same four for the end state.
+ * path_info per path: [n_commands, has_fill, has_line].  Pass NULL buffers to query sizes. */
+int swfr_debug_compiled(swfr_renderer *r, uint32_t kind, uint32_t id, double *commands, uint64_t commands_cap,
+                        uint64_t *n_commands, int32_t *path_info, uint64_t path_cap, uint64_t *n_paths);
+/* The compiler alone (host only, no CUDA device needed): same outputs as swfr_debug_compiled and
+ * swfr_debug_segments for a tag that is not registered anywhere. */
+int swfr_compile_debug(const swfr_define_shape *tag, int morph, double *commands, uint64_t commands_cap,
+                       uint64_t *n_commands, int32_t *path_info, uint64_t path_cap, uint64_t *n_paths, double *segs,
+                       uint64_t segs_cap, uint64_t *n_segs);
+/* Device segment store of a definition after implicit close + stroke expansion: per segment
+ * [is_curve, path, x0,y0,cx,cy,x1,y1 (start), same six (end)] as doubles. */
+int swfr_debug_segments(swfr_renderer *r, uint32_t kind, uint32_t id, double *segs, uint64_t cap, uint64_t *n);
+/* Flattened 24.8 edges (x0,y0,x1,y1) and their path-instance index for one frame of the last render. */
+int swfr_debug_edges(swfr_renderer *r, uint32_t frame, int32_t *edges, int32_t *edge_path, uint64_t cap, uint64_t *n);
+/* Binned records per 16x16 tile (row-major ceil(h/16) x ceil(w/16)) for one frame of the last render. */
+int swfr_debug_tile_counts(swfr_renderer *r, uint32_t frame, uint32_t *counts, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWFR_H */

@@ -1,0 +1,237 @@
+"""ctypes binding of include/swfr.h (libswfr_b200.so).
+
+The library is the product: it must be present (built in-tree by ``__graft_entry__.build()`` or
+``make -C swf_renderer_b200/csrc``) and there is no fallback of any kind when it is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libswfr_b200.so")
+
+OK = 0
+ERR_INVALID_HANDLE, ERR_INVALID_ID, ERR_INVALID_FILL_ID, ERR_UNSUPPORTED_STYLE = -1, -2, -3, -4
+ERR_OOM, ERR_CUDA, ERR_INVALID_ARGUMENT, ERR_MALFORMED = -5, -6, -7, -8
+
+FILL_SOLID, FILL_LINEAR_GRADIENT, FILL_RADIAL_GRADIENT, FILL_FOCAL_GRADIENT, FILL_BITMAP = 0, 1, 2, 3, 4
+SPREAD_PAD, SPREAD_REFLECT, SPREAD_REPEAT = 0, 1, 2
+COLOR_SRGB, COLOR_LINEAR_RGB = 0, 1
+RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
+PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
+OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS = 1, 2
+
+
+class Rgba8(C.Structure):
+    _fields_ = [("r", C.c_uint8), ("g", C.c_uint8), ("b", C.c_uint8), ("a", C.c_uint8)]
+
+
+class SwfMatrix(C.Structure):
+    _fields_ = [
+        ("scale_x", C.c_int32),
+        ("scale_y", C.c_int32),
+        ("rotate_skew0", C.c_int32),
+        ("rotate_skew1", C.c_int32),
+        ("translate_x", C.c_int32),
+        ("translate_y", C.c_int32),
+    ]
+
+
+class ColorStop(C.Structure):
+    _fields_ = [("ratio", C.c_uint8), ("color", Rgba8), ("morph_color", Rgba8)]
+
+
+class Gradient(C.Structure):
+    _fields_ = [
+        ("spread", C.c_uint8),
+        ("color_space", C.c_uint8),
+        ("n_colors", C.c_uint16),
+        ("colors", C.POINTER(ColorStop)),
+    ]
+
+
+class FillStyle(C.Structure):
+    _fields_ = [
+        ("type", C.c_uint32),
+        ("color", Rgba8),
+        ("morph_color", Rgba8),
+        ("matrix", SwfMatrix),
+        ("gradient", Gradient),
+        ("focal_point", C.c_int16),
+        ("bitmap_id", C.c_uint16),
+        ("repeating", C.c_uint8),
+        ("smoothed", C.c_uint8),
+    ]
+
+
+class LineStyle(C.Structure):
+    _fields_ = [("width", C.c_uint16), ("morph_width", C.c_uint16), ("fill", FillStyle)]
+
+
+class Styles(C.Structure):
+    _fields_ = [
+        ("n_fill", C.c_uint32),
+        ("fill", C.POINTER(FillStyle)),
+        ("n_line", C.c_uint32),
+        ("line", C.POINTER(LineStyle)),
+    ]
+
+
+class ShapeRecord(C.Structure):
+    _fields_ = [
+        ("type", C.c_uint32),
+        ("delta_x", C.c_int32),
+        ("delta_y", C.c_int32),
+        ("control_delta_x", C.c_int32),
+        ("control_delta_y", C.c_int32),
+        ("morph_delta_x", C.c_int32),
+        ("morph_delta_y", C.c_int32),
+        ("morph_control_delta_x", C.c_int32),
+        ("morph_control_delta_y", C.c_int32),
+        ("has_control_delta", C.c_uint8),
+        ("has_morph_control_delta", C.c_uint8),
+        ("has_move_to", C.c_uint8),
+        ("has_morph_move_to", C.c_uint8),
+        ("has_left_fill", C.c_uint8),
+        ("has_right_fill", C.c_uint8),
+        ("has_line_style", C.c_uint8),
+        ("has_new_styles", C.c_uint8),
+        ("move_to_x", C.c_int32),
+        ("move_to_y", C.c_int32),
+        ("morph_move_to_x", C.c_int32),
+        ("morph_move_to_y", C.c_int32),
+        ("left_fill", C.c_uint32),
+        ("right_fill", C.c_uint32),
+        ("line_style", C.c_uint32),
+        ("new_styles", C.POINTER(Styles)),
+    ]
+
+
+class DefineShape(C.Structure):
+    _fields_ = [
+        ("id", C.c_uint16),
+        ("bounds", C.c_int32 * 4),
+        ("morph_bounds", C.c_int32 * 4),
+        ("initial_styles", Styles),
+        ("n_records", C.c_uint32),
+        ("records", C.POINTER(ShapeRecord)),
+    ]
+
+
+class DisplayPrimitive(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32),
+        ("id", C.c_uint32),
+        ("matrix", C.c_float * 6),
+        ("ratio", C.c_uint16),
+        ("reserved", C.c_uint16),
+    ]
+
+
+class Stage(C.Structure):
+    _fields_ = [
+        ("background_color", Rgba8),
+        ("n_primitives", C.c_uint32),
+        ("display_root", C.POINTER(DisplayPrimitive)),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_primitives", C.c_uint64),
+        ("n_path_instances", C.c_uint64),
+        ("n_segments", C.c_uint64),
+        ("n_edges", C.c_uint64),
+        ("n_slots", C.c_uint64),
+        ("n_records", C.c_uint64),
+        ("n_tiles", C.c_uint64),
+        ("algorithmic_bytes", C.c_uint64),
+        ("kernel_launches", C.c_uint32),
+        ("retries", C.c_uint32),
+    ]
+
+
+# every symbol include/swfr.h declares, with its prototype
+PROTOTYPES = {
+    "swfr_abi_version": (C.c_uint32, []),
+    "swfr_status_string": (C.c_char_p, [C.c_int]),
+    "swfr_last_error": (C.c_char_p, [C.c_void_p]),
+    "swfr_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "swfr_create_on_stream": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "swfr_destroy": (None, [C.c_void_p]),
+    "swfr_set_option": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
+    "swfr_register_shape": (C.c_int, [C.c_void_p, C.POINTER(DefineShape), C.POINTER(C.c_uint32)]),
+    "swfr_register_morph_shape": (C.c_int, [C.c_void_p, C.POINTER(DefineShape), C.POINTER(C.c_uint32)]),
+    "swfr_register_bitmap": (C.c_int, [C.c_void_p, C.c_uint16, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "swfr_register_bitmap_xswfbmp": (C.c_int, [C.c_void_p, C.c_uint16, C.c_void_p, C.c_size_t]),
+    "swfr_decode_xswfbmp": (
+        C.c_int,
+        [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+    ),
+    "swfr_render": (C.c_int, [C.c_void_p, C.POINTER(Stage)]),
+    "swfr_render_batch": (C.c_int, [C.c_void_p, C.POINTER(Stage), C.c_uint32]),
+    "swfr_batch_create": (C.c_int, [C.c_void_p, C.POINTER(Stage), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "swfr_batch_render": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "swfr_batch_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "swfr_sync": (C.c_int, [C.c_void_p]),
+    "swfr_read_image": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int]),
+    "swfr_read_frames_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "swfr_device_frames": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    "swfr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "swfr_debug_compiled": (
+        C.c_int,
+        [
+            C.c_void_p,
+            C.c_uint32,
+            C.c_uint32,
+            C.c_void_p,
+            C.c_uint64,
+            C.POINTER(C.c_uint64),
+            C.c_void_p,
+            C.c_uint64,
+            C.POINTER(C.c_uint64),
+        ],
+    ),
+    "swfr_debug_segments": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "swfr_debug_edges": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "swfr_debug_tile_counts": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+}
+
+_LIB = None
+
+
+def load():
+    """Load libswfr_b200.so and attach prototypes.  Raises if the library was not built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libswfr_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C swf_renderer_b200/csrc`. There is no CPU fallback." % LIB_PATH
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+PROTOTYPES["swfr_compile_debug"] = (
+    C.c_int,
+    [
+        C.POINTER(DefineShape),
+        C.c_int,
+        C.c_void_p,
+        C.c_uint64,
+        C.POINTER(C.c_uint64),
+        C.c_void_p,
+        C.c_uint64,
+        C.POINTER(C.c_uint64),
+        C.c_void_p,
+        C.c_uint64,
+        C.POINTER(C.c_uint64),
+    ],
+)

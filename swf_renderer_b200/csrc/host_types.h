@@ -1,0 +1,97 @@
+// Host-side internal types of libswfr_b200 (shape compiler, stroker, style tables).
+// Not part of the ABI; see include/swfr.h for the boundary.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/swfr.h"
+
+namespace swfr {
+
+// ---- device-visible PODs (also used by the kernels) -------------------------------------------------
+
+// One path segment of a static definition: 28 bytes.
+struct SegStatic {
+  float p[6];           // x0,y0,cx,cy,x1,y1 in twips
+  uint32_t path_flags;  // local path index | (is_curve << 31)
+};
+// One path segment of a morph definition: 52 bytes.
+struct SegMorph {
+  float s[6];
+  float e[6];
+  uint32_t path_flags;
+};
+
+enum PaintType : uint32_t { PAINT_SOLID = 0, PAINT_LINEAR = 1, PAINT_FOCAL = 2, PAINT_BITMAP = 3 };
+enum PaintFlags : uint32_t { PF_COLOR_MORPH = 1u, PF_OPAQUE_RAMP = 2u };
+
+// Per-path paint of a definition ("style table" entry).
+struct DefPaint {
+  uint32_t type;
+  uint32_t spread;
+  uint32_t repeating;
+  uint32_t flags;
+  uint8_t color0[4];
+  uint8_t color1[4];
+  double matrix[6];  // scale_x, rotate_skew0, rotate_skew1, scale_y, tx, ty  (fill space -> twips)
+  double focal;
+  int32_t lut;       // index of the 257-entry ramp in the ramp store, -1 if none
+  uint32_t bitmap_id;
+};
+
+// Definition table entry.
+struct DefEntry {
+  uint32_t seg_first, seg_count;  // into the static or morph segment store
+  uint32_t paint_first, path_count;
+  uint32_t is_morph;
+  uint32_t pad;
+};
+
+// ---- host-only ---------------------------------------------------------------------------------------
+
+struct Command {  // reference CommandType encoding: LineTo=0, CurveTo=1, MoveTo=2 (path.ts:4-8)
+  int type;
+  double s[4];  // x|endX, y|endY, controlX, controlY (start state)
+  double e[4];  // end state (== s for static shapes)
+};
+
+struct CompiledPath {
+  std::vector<Command> commands;
+  bool has_fill = false, has_line = false;
+  swfr_fill_style fill{};   // when has_fill
+  swfr_line_style line{};   // when has_line
+  std::vector<swfr_color_stop> stops;  // owned copy of the gradient stops
+};
+
+struct CompiledDef {
+  bool is_morph = false;
+  std::vector<CompiledPath> paths;       // reference order: per layer fills then lines
+  // device form
+  std::vector<SegMorph> segs;            // static defs use s only
+  std::vector<DefPaint> paints;          // one per emitted device path
+  std::vector<std::vector<float>> luts;  // ramps referenced by paints[].lut (local indices)
+  bool has_visible_morph_stroke = false;
+};
+
+// Compiles records into ordered style paths and the device segment/paint form.
+// Returns a swfr_status; `err` receives a message on failure.
+int compile_definition(const swfr_define_shape *tag, bool morph, CompiledDef &out, std::string &err);
+
+// Stroke-to-fill expansion of one path's commands in user space (twips).
+// cmds use the same encoding as Command (start state only).  Appends float32-rounded segments.
+struct StrokeSeg {
+  bool curve;
+  float p[6];
+};
+void stroke_commands(const std::vector<Command> &cmds, double width, bool round_style, std::vector<StrokeSeg> &out);
+
+// 257 x 4 straight-RGBA ramp for a gradient.
+void build_ramp(const swfr_color_stop *stops, uint32_t n, bool linear_rgb, bool morph_end, std::vector<float> &out,
+                bool *all_opaque);
+
+// image/x-swf-bmp format 3 -> straight RGBA8.  Returns a swfr_status.
+int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, uint32_t *w, uint32_t *h, std::string &err);
+
+}  // namespace swfr

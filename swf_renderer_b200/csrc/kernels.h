@@ -1,0 +1,103 @@
+// Device data layout and kernel launchers of libswfr_b200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "host_types.h"
+
+namespace swfr {
+
+constexpr int kTile = 16;          // px
+constexpr int kTileFx = 4096;      // 16 px in 1/256 px
+constexpr int kMaxLenFx = 16384;   // flattened edges span at most 64 px per axis
+constexpr int kNumSM = 148;        // B200
+
+// One draw item after host flattening of the stage: 48 bytes.
+struct DrawItem {
+  float m[6];           // Matrix2D order
+  uint32_t seg_first;   // first segment of the definition in its store
+  uint32_t paint_first; // first DefPaint of the definition
+  uint32_t path_off;    // first path instance of this item
+  uint32_t frame;       // frame index within the batch
+  uint16_t ratio;
+  uint16_t is_morph;
+  uint32_t pad;
+};
+
+// Per path instance, read by binning and by the fine kernel: 16 bytes.
+struct PathRec {
+  uint32_t xy0;    // bx0 | by0 << 16   (tile bbox origin)
+  uint32_t wh;     // bw  | bh  << 16   (0 when empty)
+  uint32_t info;   // paint type | flags << 8   (flag bit0: opaque source)
+  uint32_t color;  // premultiplied RGBA8 of a solid paint
+};
+
+// Per path instance paint parameters for non-solid paints: 64 bytes.
+struct PaintInst {
+  float inv[6];  // device px -> fill space
+  float focal, omf;
+  float rx, ry;
+  unsigned long long ptr;  // ramp pointer (gradients) or texture object (bitmaps)
+  int32_t bw, bh;          // bitmap size
+  uint32_t spread, repeating;
+};
+
+struct BitmapDev {
+  unsigned long long tex;
+  int32_t w, h;
+  uint32_t opaque, valid;
+};
+
+// Counters written by the device, read by the host after a sync.
+struct Totals {
+  uint32_t n_edges, n_slots, n_records;
+  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records
+  uint32_t error;     // bit0: unknown bitmap id
+  uint32_t work;      // fine-kernel tile queue
+  uint32_t pad[2];
+};
+
+struct Caps {
+  uint32_t edges, slots, records;
+};
+
+// Everything a render launch needs (device pointers unless noted).
+struct RenderArgs {
+  int width, height, tiles_x, tiles_y;
+  uint32_t n_items, n_seginst, n_paths, n_frames;  // host-known
+  const DrawItem *items;
+  const uint32_t *item_seg_off;   // n_items + 1
+  const uint32_t *item_path_off;  // n_items + 1
+  const uint32_t *frame_path_off; // n_frames + 1
+  const SegStatic *segs_static;
+  const SegMorph *segs_morph;
+  const DefPaint *def_paints;
+  const float *ramps;
+  const BitmapDev *bitmaps;
+  uint32_t *seg_edge_off;   // n_seginst + 1 (piece counts, then exclusive scan)
+  int32_t *path_bbox;       // n_paths * 4 (min x, min y, max x, max y in 24.8)
+  PathRec *path_rec;        // n_paths
+  PaintInst *paint_inst;    // n_paths
+  uint32_t *path_slot_off;  // n_paths + 1
+  int4 *edges;              // caps.edges
+  uint32_t *edge_pid;       // caps.edges
+  uint32_t *slot_count;     // caps.slots (+1)
+  int32_t *slot_backdrop;   // caps.slots
+  uint32_t *slot_off;       // caps.slots + 1
+  unsigned long long *records;  // caps.records
+  uint32_t *frames;         // n_frames * width * height
+  uint32_t *scan_tmp;       // >= 4096 words
+  Totals *totals;
+  Caps caps;
+};
+
+// Enqueues every kernel of one render on `stream`; returns the number of kernels launched.
+int launch_render(const RenderArgs &a, cudaStream_t stream);
+
+void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
+void launch_premultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
+void launch_tile_counts(const RenderArgs &a, uint32_t frame, uint32_t *counts, cudaStream_t stream);
+
+}  // namespace swfr

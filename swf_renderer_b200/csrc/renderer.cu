@@ -1,0 +1,867 @@
+// Host side of libswfr_b200: asset store, stage flattening, working-memory management and the C ABI
+// (include/swfr.h).  Mirrors the reference Rust crate's surface:
+//   rs/src/asset.rs:9-20            ClientAssetStore / ServerAssetStore
+//   rs/src/swf_renderer.rs:3-5      SwfRenderer::render(stage)
+//   rs/src/stage.rs:4-59            Stage, DisplayPrimitive, Matrix2D, MorphRatio
+//   rs/src/renderer.rs:81-103       Renderer::set_stage, Image{meta,data}
+//   rs/src/headless_renderer.rs:60-64, 229-244, 725-868   new / define_shape / get_image / download_image
+// There is no CPU fallback: every entry point that renders needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace swfr;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t reserve(size_t bytes, bool keep = false, cudaStream_t st = 0) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = std::max(bytes, cap + cap / 2);
+    ncap = (ncap + 255) & ~(size_t)255;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    if (p) {
+      if (keep) cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+      cudaStreamSynchronize(st);
+      cudaFree(p);
+    }
+    p = np;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+struct PinnedBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t ncap = (bytes + bytes / 4 + 4095) & ~(size_t)4095;
+    cudaError_t e = cudaHostAlloc(&p, ncap, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = ncap;
+    return e;
+  }
+};
+
+// One set of launches: a contiguous range of frames whose working set shares the arena.
+struct Pass {
+  uint32_t f0 = 0, n_frames = 0, n_items = 0, n_seginst = 0, n_paths = 0;
+  // offsets into the batch-wide host/device arrays
+  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0;
+};
+
+struct BitmapRes {
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+};
+
+}  // namespace
+
+struct swfr_batch {
+  uint32_t n_frames = 0;
+  std::vector<Pass> passes;
+  std::vector<DrawItem> items;
+  std::vector<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
+  DevBuf d_items, d_seg_off, d_path_off, d_frame_off;
+  bool resident = false;
+  uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
+};
+
+struct swfr_renderer {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint32_t width = 0, height = 0, tiles_x = 0, tiles_y = 0;
+  std::string last_error;
+  bool retain_compiled = true;
+  uint32_t frames_per_pass = 4;
+
+  // ---- asset store (host mirrors + device copies) ----
+  std::vector<SegStatic> h_static;
+  std::vector<SegMorph> h_morph;
+  std::vector<DefPaint> h_paints;
+  std::vector<float> h_ramps;
+  std::vector<DefEntry> shape_defs, morph_defs;
+  std::vector<uint8_t> morph_has_stroke;
+  std::vector<std::unique_ptr<CompiledDef>> shape_dbg, morph_dbg;
+  DevBuf d_static, d_morph, d_paints, d_ramps, d_bitmaps;
+  size_t up_static = 0, up_morph = 0, up_paints = 0, up_ramps = 0;  // elements already uploaded
+  std::vector<BitmapRes> bitmaps;                                   // by id, lazily sized 65536
+  std::vector<BitmapDev> h_bitmaps;
+
+  // ---- working memory ----
+  DevBuf seg_edge_off, path_bbox, path_rec, paint_inst, path_slot_off, edges, edge_pid, slot_count, slot_backdrop,
+      slot_off, records, frames, scan_tmp, totals, scratch;
+  Caps caps{0, 0, 0};
+  PinnedBuf pin_items, pin_off, pin_totals;
+  swfr_batch scratch_batch;  // used by swfr_render / swfr_render_batch
+
+  // ---- last render ----
+  swfr_batch *last = nullptr;
+  bool pending = false;
+  uint32_t frames_rendered = 0;
+  swfr_stats stats{};
+  std::vector<Totals> last_totals;
+  size_t arena_pass = 0;  // index of the pass whose working set is in the arena
+};
+
+namespace {
+
+int fail(swfr_renderer *r, int code, const std::string &msg) {
+  if (r) r->last_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t _e = (call);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      return fail(r, _e == cudaErrorMemoryAllocation ? SWFR_ERR_OOM : SWFR_ERR_CUDA,                    \
+                  std::string(#call) + ": " + cudaGetErrorString(_e));                                  \
+  } while (0)
+
+int flush_store(swfr_renderer *r) {
+  cudaStream_t st = r->stream;
+  auto up = [&](DevBuf &d, const void *h, size_t elem, size_t n, size_t &done) -> cudaError_t {
+    if (n == done) return cudaSuccess;
+    cudaError_t e = d.reserve(std::max<size_t>(n * elem, 256), true, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync((char *)d.p + done * elem, (const char *)h + done * elem, (n - done) * elem,
+                        cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors may be reallocated by later registrations
+    done = n;
+    return e;
+  };
+  CK(up(r->d_static, r->h_static.data(), sizeof(SegStatic), r->h_static.size(), r->up_static));
+  CK(up(r->d_morph, r->h_morph.data(), sizeof(SegMorph), r->h_morph.size(), r->up_morph));
+  CK(up(r->d_paints, r->h_paints.data(), sizeof(DefPaint), r->h_paints.size(), r->up_paints));
+  CK(up(r->d_ramps, r->h_ramps.data(), sizeof(float), r->h_ramps.size(), r->up_ramps));
+  CK(r->d_static.reserve(256));
+  CK(r->d_morph.reserve(256));
+  CK(r->d_paints.reserve(256));
+  CK(r->d_ramps.reserve(256));
+  if (!r->d_bitmaps.p) {
+    CK(r->d_bitmaps.reserve(65536 * sizeof(BitmapDev)));
+    CK(cudaMemsetAsync(r->d_bitmaps.p, 0, 65536 * sizeof(BitmapDev), st));
+  }
+  return SWFR_OK;
+}
+
+// Flattens stages into draw items and splits them into passes.
+int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_batch &b) {
+  b.n_frames = n;
+  b.passes.clear();
+  b.items.clear();
+  b.seg_off.clear();
+  b.path_off.clear();
+  b.frame_off.clear();
+  b.n_prims = b.n_seginst = b.n_paths = 0;
+  uint32_t fpp = std::max<uint32_t>(1, r->frames_per_pass);
+  for (uint32_t f0 = 0; f0 < n; f0 += fpp) {
+    Pass p;
+    p.f0 = f0;
+    p.n_frames = std::min(fpp, n - f0);
+    p.items_at = b.items.size();
+    p.seg_off_at = b.seg_off.size();
+    p.path_off_at = b.path_off.size();
+    p.frame_off_at = b.frame_off.size();
+    uint32_t seg_run = 0, path_run = 0;
+    for (uint32_t f = f0; f < f0 + p.n_frames; f++) {
+      const swfr_stage &st = stages[f];
+      b.frame_off.push_back(path_run);
+      if (st.n_primitives && !st.display_root) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "stage.display_root is NULL");
+      for (uint32_t i = 0; i < st.n_primitives; i++) {
+        const swfr_display_primitive &pr = st.display_root[i];
+        const DefEntry *de;
+        if (pr.kind == SWFR_PRIM_SHAPE) {
+          if (pr.id >= r->shape_defs.size()) return fail(r, SWFR_ERR_INVALID_ID, "unknown ShapeId " + std::to_string(pr.id));
+          de = &r->shape_defs[pr.id];
+        } else if (pr.kind == SWFR_PRIM_MORPH_SHAPE) {
+          if (pr.id >= r->morph_defs.size())
+            return fail(r, SWFR_ERR_INVALID_ID, "unknown MorphShapeId " + std::to_string(pr.id));
+          de = &r->morph_defs[pr.id];
+          if (r->morph_has_stroke[pr.id])
+            return fail(r, SWFR_ERR_UNSUPPORTED_STYLE, "morph shapes with visible strokes are not supported yet");
+        } else {
+          return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown display primitive kind");
+        }
+        DrawItem it;
+        memcpy(it.m, pr.matrix, sizeof it.m);
+        it.seg_first = de->seg_first;
+        it.paint_first = de->paint_first;
+        it.path_off = path_run;
+        it.frame = f - f0;
+        it.ratio = pr.ratio;
+        it.is_morph = (uint16_t)de->is_morph;
+        it.pad = 0;
+        b.items.push_back(it);
+        b.seg_off.push_back(seg_run);
+        b.path_off.push_back(path_run);
+        seg_run += de->seg_count;
+        path_run += de->path_count;
+      }
+    }
+    b.seg_off.push_back(seg_run);
+    b.path_off.push_back(path_run);
+    b.frame_off.push_back(path_run);
+    p.n_items = (uint32_t)(b.items.size() - p.items_at);
+    p.n_seginst = seg_run;
+    p.n_paths = path_run;
+    b.n_prims += p.n_items;
+    b.n_seginst += seg_run;
+    b.n_paths += path_run;
+    b.passes.push_back(p);
+  }
+  return SWFR_OK;
+}
+
+int upload_batch(swfr_renderer *r, swfr_batch &b, bool pinned_staging) {
+  cudaStream_t st = r->stream;
+  CK(b.d_items.reserve(std::max<size_t>(b.items.size() * sizeof(DrawItem), 256)));
+  CK(b.d_seg_off.reserve(std::max<size_t>(b.seg_off.size() * 4, 256)));
+  CK(b.d_path_off.reserve(std::max<size_t>(b.path_off.size() * 4, 256)));
+  CK(b.d_frame_off.reserve(std::max<size_t>(b.frame_off.size() * 4, 256)));
+  const void *hi = b.items.data();
+  const void *hs = b.seg_off.data(), *hp = b.path_off.data(), *hf = b.frame_off.data();
+  size_t ni = b.items.size() * sizeof(DrawItem), ns = b.seg_off.size() * 4, np = b.path_off.size() * 4,
+         nf = b.frame_off.size() * 4;
+  if (pinned_staging) {
+    CK(cudaStreamSynchronize(st));  // the staging buffers may still feed a previous copy
+    CK(r->pin_items.reserve(ni + 16));
+    CK(r->pin_off.reserve(ns + np + nf + 64));
+    memcpy(r->pin_items.p, hi, ni);
+    char *po = (char *)r->pin_off.p;
+    memcpy(po, hs, ns);
+    memcpy(po + ns, hp, np);
+    memcpy(po + ns + np, hf, nf);
+    hi = r->pin_items.p;
+    hs = po;
+    hp = po + ns;
+    hf = po + ns + np;
+  }
+  if (ni) CK(cudaMemcpyAsync(b.d_items.p, hi, ni, cudaMemcpyHostToDevice, st));
+  if (ns) CK(cudaMemcpyAsync(b.d_seg_off.p, hs, ns, cudaMemcpyHostToDevice, st));
+  if (np) CK(cudaMemcpyAsync(b.d_path_off.p, hp, np, cudaMemcpyHostToDevice, st));
+  if (nf) CK(cudaMemcpyAsync(b.d_frame_off.p, hf, nf, cudaMemcpyHostToDevice, st));
+  if (!pinned_staging) CK(cudaStreamSynchronize(st));
+  b.resident = true;
+  return SWFR_OK;
+}
+
+int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
+  uint32_t max_seg = 0, max_paths = 0;
+  for (const Pass &p : b.passes) {
+    max_seg = std::max(max_seg, p.n_seginst);
+    max_paths = std::max(max_paths, p.n_paths);
+  }
+  CK(r->seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
+  CK(r->path_bbox.reserve((size_t)max_paths * 16 + 256));
+  CK(r->path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
+  CK(r->paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
+  CK(r->path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
+  CK(r->scan_tmp.reserve(8192 * 4));
+  CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
+  CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
+  Caps want = r->caps;
+  want.edges = std::max<uint32_t>(want.edges, std::max<uint32_t>(1u << 16, max_seg * 4));
+  want.slots = std::max<uint32_t>(want.slots, std::max<uint32_t>(1u << 16, max_paths * 32));
+  want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
+  CK(r->edges.reserve((size_t)want.edges * 16));
+  CK(r->edge_pid.reserve((size_t)want.edges * 4));
+  CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
+  CK(r->slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
+  CK(r->slot_off.reserve(((size_t)want.slots + 1) * 4));
+  CK(r->records.reserve((size_t)want.records * 8));
+  r->caps = want;
+  return SWFR_OK;
+}
+
+RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_t pass_index) {
+  RenderArgs a{};
+  a.width = (int)r->width;
+  a.height = (int)r->height;
+  a.tiles_x = (int)r->tiles_x;
+  a.tiles_y = (int)r->tiles_y;
+  a.n_items = p.n_items;
+  a.n_seginst = p.n_seginst;
+  a.n_paths = p.n_paths;
+  a.n_frames = p.n_frames;
+  a.items = b.d_items.as<DrawItem>() + p.items_at;
+  a.item_seg_off = b.d_seg_off.as<uint32_t>() + p.seg_off_at;
+  a.item_path_off = b.d_path_off.as<uint32_t>() + p.path_off_at;
+  a.frame_path_off = b.d_frame_off.as<uint32_t>() + p.frame_off_at;
+  a.segs_static = r->d_static.as<SegStatic>();
+  a.segs_morph = r->d_morph.as<SegMorph>();
+  a.def_paints = r->d_paints.as<DefPaint>();
+  a.ramps = r->d_ramps.as<float>();
+  a.bitmaps = r->d_bitmaps.as<BitmapDev>();
+  a.seg_edge_off = r->seg_edge_off.as<uint32_t>();
+  a.path_bbox = r->path_bbox.as<int32_t>();
+  a.path_rec = r->path_rec.as<PathRec>();
+  a.paint_inst = r->paint_inst.as<PaintInst>();
+  a.path_slot_off = r->path_slot_off.as<uint32_t>();
+  a.edges = r->edges.as<int4>();
+  a.edge_pid = r->edge_pid.as<uint32_t>();
+  a.slot_count = r->slot_count.as<uint32_t>();
+  a.slot_backdrop = r->slot_backdrop.as<int32_t>();
+  a.slot_off = r->slot_off.as<uint32_t>();
+  a.records = r->records.as<unsigned long long>();
+  a.frames = r->frames.as<uint32_t>() + (size_t)p.f0 * r->width * r->height;
+  a.scan_tmp = r->scan_tmp.as<uint32_t>();
+  a.totals = r->totals.as<Totals>() + pass_index;
+  a.caps = r->caps;
+  return a;
+}
+
+int finish(swfr_renderer *r);
+
+int launch_batch(swfr_renderer *r, swfr_batch &b) {
+  int rc = finish(r);  // settle (and possibly retry) the previous render before reusing the arena
+  if (rc != SWFR_OK) return rc;
+  rc = flush_store(r);
+  if (rc != SWFR_OK) return rc;
+  rc = ensure_arena(r, b);
+  if (rc != SWFR_OK) return rc;
+  uint32_t launches = 0;
+  for (size_t i = 0; i < b.passes.size(); i++) launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
+  CK(cudaGetLastError());
+  r->last = &b;
+  r->arena_pass = b.passes.empty() ? 0 : b.passes.size() - 1;
+  r->pending = true;
+  r->frames_rendered = b.n_frames;
+  memset(&r->stats, 0, sizeof r->stats);
+  r->stats.kernel_launches = launches;
+  return SWFR_OK;
+}
+
+// Waits for the last render, grows working memory and re-runs passes that overflowed it.
+int finish(swfr_renderer *r) {
+  if (!r->pending) return SWFR_OK;
+  swfr_batch &b = *r->last;
+  size_t np = b.passes.size();
+  r->last_totals.assign(np, Totals{});
+  CK(cudaMemcpyAsync(r->last_totals.data(), r->totals.p, np * sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
+  CK(cudaStreamSynchronize(r->stream));
+  for (size_t i = 0; i < np; i++) {
+    int guard = 0;
+    while (r->last_totals[i].overflow) {
+      if (++guard > 6) return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
+      const Totals &t = r->last_totals[i];
+      Caps want = r->caps;
+      auto grow = [](uint32_t need) { return (uint32_t)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0xfffffff0ull); };
+      if (t.overflow & 1u) want.edges = std::max(want.edges, grow(t.n_edges));
+      if (t.overflow & 2u) want.slots = std::max(want.slots, grow(t.n_slots));
+      if (t.overflow & 4u) want.records = std::max(want.records, grow(t.n_records));
+      if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
+      CK(r->edges.reserve((size_t)want.edges * 16));
+      CK(r->edge_pid.reserve((size_t)want.edges * 4));
+      CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
+      CK(r->slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
+      CK(r->slot_off.reserve(((size_t)want.slots + 1) * 4));
+      CK(r->records.reserve((size_t)want.records * 8));
+      r->caps = want;
+      r->stats.retries++;
+      r->arena_pass = i;
+      r->stats.kernel_launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
+      CK(cudaMemcpyAsync(&r->last_totals[i], r->totals.as<Totals>() + i, sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
+      CK(cudaStreamSynchronize(r->stream));
+    }
+  }
+  r->pending = false;
+  uint32_t err = 0;
+  r->stats.n_primitives = b.n_prims;
+  r->stats.n_segments = b.n_seginst;
+  r->stats.n_path_instances = b.n_paths;
+  r->stats.n_tiles = (uint64_t)r->tiles_x * r->tiles_y * b.n_frames;
+  for (const Totals &t : r->last_totals) {
+    r->stats.n_edges += t.n_edges;
+    r->stats.n_slots += t.n_slots;
+    r->stats.n_records += t.n_records;
+    err |= t.error;
+  }
+  // segments read once, draw items read once, binned records written + read once (8 B each),
+  // framebuffer written once (frames start from a clear, so there is no load).
+  r->stats.algorithmic_bytes = b.n_seginst * sizeof(SegStatic) + b.n_prims * sizeof(DrawItem) +
+                               2ull * 8ull * r->stats.n_records + 4ull * r->width * r->height * b.n_frames;
+  if (err & 1u) return fail(r, SWFR_ERR_INVALID_ID, "BitmapNotFound: a bitmap fill references an unregistered bitmap id");
+  return SWFR_OK;
+}
+
+int register_def(swfr_renderer *r, const swfr_define_shape *tag, bool morph, uint32_t *out_id) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!tag || !out_id) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL argument");
+  auto def = std::make_unique<CompiledDef>();
+  std::string err;
+  int rc = compile_definition(tag, morph, *def, err);
+  if (rc != SWFR_OK) return fail(r, rc, err);
+  DefEntry de{};
+  de.is_morph = morph ? 1 : 0;
+  de.paint_first = (uint32_t)r->h_paints.size();
+  de.path_count = (uint32_t)def->paints.size();
+  de.seg_count = (uint32_t)def->segs.size();
+  size_t ramp_base = r->h_ramps.size() / (257 * 4);
+  for (auto &l : def->luts) r->h_ramps.insert(r->h_ramps.end(), l.begin(), l.end());
+  for (DefPaint p : def->paints) {
+    if (p.lut >= 0) p.lut += (int32_t)ramp_base;
+    r->h_paints.push_back(p);
+  }
+  if (morph) {
+    de.seg_first = (uint32_t)r->h_morph.size();
+    r->h_morph.insert(r->h_morph.end(), def->segs.begin(), def->segs.end());
+    *out_id = (uint32_t)r->morph_defs.size();
+    r->morph_defs.push_back(de);
+    r->morph_has_stroke.push_back(def->has_visible_morph_stroke ? 1 : 0);
+    r->morph_dbg.push_back(r->retain_compiled ? std::move(def) : nullptr);
+  } else {
+    de.seg_first = (uint32_t)r->h_static.size();
+    for (const SegMorph &s : def->segs) {
+      SegStatic g;
+      memcpy(g.p, s.s, sizeof g.p);
+      g.path_flags = s.path_flags;
+      r->h_static.push_back(g);
+    }
+    *out_id = (uint32_t)r->shape_defs.size();
+    r->shape_defs.push_back(de);
+    r->shape_dbg.push_back(r->retain_compiled ? std::move(def) : nullptr);
+  }
+  return SWFR_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+
+extern "C" {
+
+uint32_t swfr_abi_version(void) { return SWFR_ABI_VERSION; }
+
+const char *swfr_status_string(int s) {
+  switch (s) {
+    case SWFR_OK: return "ok";
+    case SWFR_ERR_INVALID_HANDLE: return "invalid handle";
+    case SWFR_ERR_INVALID_ID: return "invalid id";
+    case SWFR_ERR_INVALID_FILL_ID: return "invalid fill id";
+    case SWFR_ERR_UNSUPPORTED_STYLE: return "unsupported style";
+    case SWFR_ERR_OOM: return "out of memory";
+    case SWFR_ERR_CUDA: return "CUDA error";
+    case SWFR_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case SWFR_ERR_MALFORMED: return "malformed input";
+    default: return "unknown status";
+  }
+}
+
+const char *swfr_last_error(const swfr_renderer *r) { return r ? r->last_error.c_str() : "invalid handle"; }
+
+int swfr_create_on_stream(int device, uint32_t width, uint32_t height, void *cuda_stream, swfr_renderer **out) {
+  if (!out) return SWFR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (width == 0 || height == 0 || width > 16384 || height > 16384) return SWFR_ERR_INVALID_ARGUMENT;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SWFR_ERR_CUDA;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return SWFR_ERR_CUDA;
+  swfr_renderer *r = new swfr_renderer();
+  r->device = device;
+  r->width = width;
+  r->height = height;
+  r->tiles_x = (width + kTile - 1) / kTile;
+  r->tiles_y = (height + kTile - 1) / kTile;
+  if (cuda_stream) {
+    r->stream = (cudaStream_t)cuda_stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete r;
+      return SWFR_ERR_CUDA;
+    }
+    r->own_stream = true;
+  }
+  if (const char *e = getenv("SWFR_FRAMES_PER_PASS")) r->frames_per_pass = (uint32_t)std::max(1, atoi(e));
+  *out = r;
+  return SWFR_OK;
+}
+
+int swfr_create(int device, uint32_t width, uint32_t height, swfr_renderer **out) {
+  return swfr_create_on_stream(device, width, height, nullptr, out);
+}
+
+void swfr_destroy(swfr_renderer *r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  cudaStreamSynchronize(r->stream);
+  for (BitmapRes &b : r->bitmaps) {
+    if (b.tex) cudaDestroyTextureObject(b.tex);
+    if (b.arr) cudaFreeArray(b.arr);
+  }
+  if (r->own_stream) cudaStreamDestroy(r->stream);
+  delete r;
+}
+
+int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  switch (key) {
+    case 1: r->retain_compiled = value != 0; return SWFR_OK;
+    case 2: r->frames_per_pass = (uint32_t)std::max<uint64_t>(1, value); return SWFR_OK;
+    default: return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown option");
+  }
+}
+
+int swfr_register_shape(swfr_renderer *r, const swfr_define_shape *tag, uint32_t *out_id) {
+  return register_def(r, tag, false, out_id);
+}
+int swfr_register_morph_shape(swfr_renderer *r, const swfr_define_shape *tag, uint32_t *out_id) {
+  return register_def(r, tag, true, out_id);
+}
+
+int swfr_register_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, const uint8_t *rgba, size_t stride) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!rgba || w == 0 || h == 0 || stride < (size_t)w * 4) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad bitmap");
+  cudaSetDevice(r->device);
+  int rc = finish(r);
+  if (rc != SWFR_OK) return rc;
+  rc = flush_store(r);
+  if (rc != SWFR_OK) return rc;
+  if (r->bitmaps.empty()) {
+    r->bitmaps.resize(65536);
+    r->h_bitmaps.resize(65536);
+  }
+  // straight -> premultiplied 8-bit (what a Canvas stores), then into a 2D array behind a texture object
+  std::vector<uint8_t> pm((size_t)w * h * 4);
+  bool opaque = true;
+  for (uint32_t y = 0; y < h; y++)
+    for (uint32_t x = 0; x < w; x++) {
+      const uint8_t *s = rgba + (size_t)y * stride + 4 * x;
+      uint8_t *d = &pm[4 * ((size_t)y * w + x)];
+      uint32_t a = s[3];
+      d[0] = (uint8_t)((s[0] * a + 127u) / 255u);
+      d[1] = (uint8_t)((s[1] * a + 127u) / 255u);
+      d[2] = (uint8_t)((s[2] * a + 127u) / 255u);
+      d[3] = (uint8_t)a;
+      if (a != 255) opaque = false;
+    }
+  BitmapRes &res = r->bitmaps[id];
+  if (res.tex) cudaDestroyTextureObject(res.tex);
+  if (res.arr) cudaFreeArray(res.arr);
+  res = BitmapRes{};
+  cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+  CK(cudaMallocArray(&res.arr, &cd, w, h));
+  CK(cudaMemcpy2DToArray(res.arr, 0, 0, pm.data(), (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice));
+  cudaResourceDesc rd{};
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = res.arr;
+  cudaTextureDesc td{};
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint;  // filtering is done explicitly (box footprint), texels fetched exactly
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  CK(cudaCreateTextureObject(&res.tex, &rd, &td, nullptr));
+  BitmapDev bd{};
+  bd.tex = (unsigned long long)res.tex;
+  bd.w = (int32_t)w;
+  bd.h = (int32_t)h;
+  bd.opaque = opaque ? 1 : 0;
+  bd.valid = 1;
+  r->h_bitmaps[id] = bd;
+  CK(cudaMemcpyAsync(r->d_bitmaps.as<BitmapDev>() + id, &r->h_bitmaps[id], sizeof(BitmapDev), cudaMemcpyHostToDevice,
+                     r->stream));
+  CK(cudaStreamSynchronize(r->stream));
+  return SWFR_OK;
+}
+
+int swfr_register_bitmap_xswfbmp(swfr_renderer *r, uint16_t id, const uint8_t *data, size_t len) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!data) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL data");
+  std::vector<uint8_t> rgba;
+  uint32_t w = 0, h = 0;
+  std::string err;
+  int rc = decode_xswfbmp(data, len, rgba, &w, &h, err);
+  if (rc != SWFR_OK) return fail(r, rc, err);
+  return swfr_register_bitmap(r, id, w, h, rgba.data(), (size_t)w * 4);
+}
+
+int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t cap, uint32_t *w, uint32_t *h) {
+  std::vector<uint8_t> out;
+  std::string err;
+  uint32_t ww = 0, hh = 0;
+  int rc = decode_xswfbmp(data, len, out, &ww, &hh, err);
+  if (rc != SWFR_OK) return rc;
+  if (w) *w = ww;
+  if (h) *h = hh;
+  if (rgba && cap >= out.size()) memcpy(rgba, out.data(), out.size());
+  return SWFR_OK;
+}
+
+int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!stages || n == 0) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
+  cudaSetDevice(r->device);
+  int rc = finish(r);
+  if (rc != SWFR_OK) return rc;
+  rc = build_batch(r, stages, n, r->scratch_batch);
+  if (rc != SWFR_OK) return rc;
+  rc = upload_batch(r, r->scratch_batch, true);
+  if (rc != SWFR_OK) return rc;
+  return launch_batch(r, r->scratch_batch);
+}
+
+int swfr_render(swfr_renderer *r, const swfr_stage *stage) { return swfr_render_batch(r, stage, 1); }
+
+int swfr_batch_create(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_batch **out) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!stages || n == 0 || !out) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
+  cudaSetDevice(r->device);
+  auto b = std::make_unique<swfr_batch>();
+  int rc = build_batch(r, stages, n, *b);
+  if (rc != SWFR_OK) return rc;
+  rc = upload_batch(r, *b, false);
+  if (rc != SWFR_OK) return rc;
+  *out = b.release();
+  return SWFR_OK;
+}
+
+int swfr_batch_render(swfr_renderer *r, swfr_batch *b) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!b) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL batch");
+  cudaSetDevice(r->device);
+  return launch_batch(r, *b);
+}
+
+void swfr_batch_destroy(swfr_renderer *r, swfr_batch *b) {
+  if (!b) return;
+  if (r) {
+    cudaSetDevice(r->device);
+    finish(r);
+    if (r->last == b) r->last = nullptr;
+  }
+  delete b;
+}
+
+int swfr_sync(swfr_renderer *r) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  cudaSetDevice(r->device);
+  int rc = finish(r);
+  if (rc != SWFR_OK) return rc;
+  CK(cudaStreamSynchronize(r->stream));
+  return SWFR_OK;
+}
+
+int swfr_get_stats(swfr_renderer *r, swfr_stats *out) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!out) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL out");
+  int rc = swfr_sync(r);
+  *out = r->stats;
+  return rc;
+}
+
+int swfr_read_image(swfr_renderer *r, uint32_t frame, uint8_t *dst, size_t stride, int premultiplied) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!dst || stride < (size_t)r->width * 4) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad destination");
+  if (frame >= r->frames_rendered) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "Failed to render: no such frame");
+  cudaSetDevice(r->device);
+  int rc = finish(r);
+  if (rc != SWFR_OK) return rc;
+  size_t npx = (size_t)r->width * r->height;
+  const uint32_t *src = r->frames.as<uint32_t>() + (size_t)frame * npx;
+  if (!premultiplied) {
+    CK(r->scratch.reserve(npx * 4));
+    launch_unpremultiply(src, r->scratch.as<uint32_t>(), npx, r->stream);
+    src = r->scratch.as<uint32_t>();
+  }
+  CK(cudaMemcpy2DAsync(dst, stride, src, (size_t)r->width * 4, (size_t)r->width * 4, r->height, cudaMemcpyDeviceToHost,
+                       r->stream));
+  CK(cudaStreamSynchronize(r->stream));
+  return SWFR_OK;
+}
+
+int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uint8_t *dst) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!dst || first + count > r->frames_rendered) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad frame range");
+  cudaSetDevice(r->device);
+  size_t fb = (size_t)r->width * r->height * 4;
+  CK(cudaMemcpyAsync(dst, (const char *)r->frames.p + (size_t)first * fb, (size_t)count * fb, cudaMemcpyDeviceToHost,
+                     r->stream));
+  return SWFR_OK;
+}
+
+int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (out_ptr) *out_ptr = r->frames.p;
+  if (out_n) *out_n = r->frames_rendered;
+  return SWFR_OK;
+}
+
+// ---- parity taps ------------------------------------------------------------------------------------
+
+int swfr_debug_compiled(swfr_renderer *r, uint32_t kind, uint32_t id, double *commands, uint64_t commands_cap,
+                        uint64_t *n_commands, int32_t *path_info, uint64_t path_cap, uint64_t *n_paths) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  auto &v = kind == SWFR_PRIM_MORPH_SHAPE ? r->morph_dbg : r->shape_dbg;
+  if (id >= v.size() || !v[id]) return fail(r, SWFR_ERR_INVALID_ID, "definition unknown or not retained");
+  const CompiledDef &d = *v[id];
+  uint64_t nc = 0;
+  for (size_t p = 0; p < d.paths.size(); p++) {
+    const CompiledPath &cp = d.paths[p];
+    if (path_info && p < path_cap) {
+      path_info[3 * p] = (int32_t)cp.commands.size();
+      path_info[3 * p + 1] = cp.has_fill;
+      path_info[3 * p + 2] = cp.has_line;
+    }
+    for (const Command &c : cp.commands) {
+      if (commands && nc < commands_cap) {
+        double *o = commands + 9 * nc;
+        o[0] = c.type;
+        for (int k = 0; k < 4; k++) o[1 + k] = c.s[k], o[5 + k] = c.e[k];
+      }
+      nc++;
+    }
+  }
+  if (n_commands) *n_commands = nc;
+  if (n_paths) *n_paths = d.paths.size();
+  return SWFR_OK;
+}
+
+// Host-only: compiles a tag without a renderer (no CUDA needed) and returns commands, path info and segments.
+int swfr_compile_debug(const swfr_define_shape *tag, int morph, double *commands, uint64_t commands_cap,
+                       uint64_t *n_commands, int32_t *path_info, uint64_t path_cap, uint64_t *n_paths, double *segs,
+                       uint64_t segs_cap, uint64_t *n_segs) {
+  if (!tag) return SWFR_ERR_INVALID_ARGUMENT;
+  CompiledDef d;
+  std::string err;
+  int rc = compile_definition(tag, morph != 0, d, err);
+  if (rc != SWFR_OK) return rc;
+  uint64_t nc = 0;
+  for (size_t p = 0; p < d.paths.size(); p++) {
+    const CompiledPath &cp = d.paths[p];
+    if (path_info && p < path_cap) {
+      path_info[3 * p] = (int32_t)cp.commands.size();
+      path_info[3 * p + 1] = cp.has_fill;
+      path_info[3 * p + 2] = cp.has_line;
+    }
+    for (const Command &c : cp.commands) {
+      if (commands && nc < commands_cap) {
+        double *o = commands + 9 * nc;
+        o[0] = c.type;
+        for (int k = 0; k < 4; k++) o[1 + k] = c.s[k], o[5 + k] = c.e[k];
+      }
+      nc++;
+    }
+  }
+  if (n_commands) *n_commands = nc;
+  if (n_paths) *n_paths = d.paths.size();
+  for (size_t i = 0; i < d.segs.size() && segs && i < segs_cap; i++) {
+    double *o = segs + 14 * i;
+    o[0] = d.segs[i].path_flags >> 31;
+    o[1] = d.segs[i].path_flags & 0x7fffffffu;
+    for (int k = 0; k < 6; k++) o[2 + k] = d.segs[i].s[k], o[8 + k] = d.segs[i].e[k];
+  }
+  if (n_segs) *n_segs = d.segs.size();
+  return SWFR_OK;
+}
+
+int swfr_debug_segments(swfr_renderer *r, uint32_t kind, uint32_t id, double *segs, uint64_t cap, uint64_t *n) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  auto &v = kind == SWFR_PRIM_MORPH_SHAPE ? r->morph_dbg : r->shape_dbg;
+  if (id >= v.size() || !v[id]) return fail(r, SWFR_ERR_INVALID_ID, "definition unknown or not retained");
+  const CompiledDef &d = *v[id];
+  for (size_t i = 0; i < d.segs.size() && segs && i < cap; i++) {
+    double *o = segs + 14 * i;
+    o[0] = d.segs[i].path_flags >> 31;
+    o[1] = d.segs[i].path_flags & 0x7fffffffu;
+    for (int k = 0; k < 6; k++) o[2 + k] = d.segs[i].s[k], o[8 + k] = d.segs[i].e[k];
+  }
+  if (n) *n = d.segs.size();
+  return SWFR_OK;
+}
+
+static int debug_pass(swfr_renderer *r, uint32_t frame, const Pass **pass, size_t *index) {
+  if (!r->last || frame >= r->frames_rendered) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no such frame");
+  int rc = finish(r);
+  if (rc != SWFR_OK) return rc;
+  const swfr_batch &b = *r->last;
+  // the arena holds the working set of one pass only (the last one launched)
+  const Pass &p = b.passes[r->arena_pass];
+  if (frame < p.f0 || frame >= p.f0 + p.n_frames)
+    return fail(r, SWFR_ERR_INVALID_ARGUMENT, "debug taps need the frame to be in the last pass (render fewer frames)");
+  *pass = &p;
+  *index = r->arena_pass;
+  return SWFR_OK;
+}
+
+int swfr_debug_edges(swfr_renderer *r, uint32_t frame, int32_t *edges, int32_t *edge_path, uint64_t cap, uint64_t *n) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  cudaSetDevice(r->device);
+  const Pass *p;
+  size_t pi;
+  int rc = debug_pass(r, frame, &p, &pi);
+  if (rc != SWFR_OK) return rc;
+  const swfr_batch &b = *r->last;
+  // frame -> path range -> item range -> segment-instance range -> edge range
+  uint32_t lf = frame - p->f0;
+  uint32_t path_lo = b.frame_off[p->frame_off_at + lf], path_hi = b.frame_off[p->frame_off_at + lf + 1];
+  const uint32_t *po = &b.path_off[p->path_off_at], *so = &b.seg_off[p->seg_off_at];
+  uint32_t i_lo = 0, i_hi = p->n_items;
+  // items of a frame are contiguous; find them by their frame tag
+  while (i_lo < p->n_items && b.items[p->items_at + i_lo].frame < lf) i_lo++;
+  i_hi = i_lo;
+  while (i_hi < p->n_items && b.items[p->items_at + i_hi].frame == lf) i_hi++;
+  (void)po;
+  (void)path_hi;
+  uint32_t s_lo = so[i_lo], s_hi = so[i_hi];
+  uint32_t e_lo = 0, e_hi = 0;
+  CK(cudaMemcpy(&e_lo, r->seg_edge_off.as<uint32_t>() + s_lo, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&e_hi, r->seg_edge_off.as<uint32_t>() + s_hi, 4, cudaMemcpyDeviceToHost));
+  uint64_t cnt = e_hi - e_lo;
+  if (n) *n = cnt;
+  uint64_t take = std::min<uint64_t>(cnt, cap);
+  if (edges && take) CK(cudaMemcpy(edges, r->edges.as<int4>() + e_lo, take * 16, cudaMemcpyDeviceToHost));
+  if (edge_path && take) {
+    CK(cudaMemcpy(edge_path, r->edge_pid.as<uint32_t>() + e_lo, take * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < take; i++) edge_path[i] -= (int32_t)path_lo;  // index within the frame
+  }
+  return SWFR_OK;
+}
+
+int swfr_debug_tile_counts(swfr_renderer *r, uint32_t frame, uint32_t *counts, uint64_t cap) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  cudaSetDevice(r->device);
+  const Pass *p;
+  size_t pi;
+  int rc = debug_pass(r, frame, &p, &pi);
+  if (rc != SWFR_OK) return rc;
+  size_t nt = (size_t)r->tiles_x * r->tiles_y;
+  if (!counts || cap < nt) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "counts buffer too small");
+  CK(r->scratch.reserve(std::max<size_t>(nt * 4, (size_t)r->width * r->height * 4)));
+  CK(cudaMemsetAsync(r->scratch.p, 0, nt * 4, r->stream));
+  RenderArgs a = make_args(r, *r->last, *p, pi);
+  launch_tile_counts(a, frame - p->f0, r->scratch.as<uint32_t>(), r->stream);
+  CK(cudaMemcpyAsync(counts, r->scratch.p, nt * 4, cudaMemcpyDeviceToHost, r->stream));
+  CK(cudaStreamSynchronize(r->stream));
+  return SWFR_OK;
+}
+
+}  // extern "C"

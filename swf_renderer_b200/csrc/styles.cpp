@@ -1,0 +1,105 @@
+// Gradient ramps and SWF bitmap decoding (host, at registration time).
+//   ramps:   decodeGradient (ts/src/lib/shape/decode-swf-shape.ts:99-105) + Canvas addColorStop semantics
+//            (ts/src/lib/renderers/canvas-renderer.ts:327-329)
+//   bitmaps: decodeXSwfBmpSync (ts/src/lib/decode-x-swf-bmp.ts:9-41)
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "host_types.h"
+
+namespace swfr {
+
+static double srgb_to_linear(double c) { return c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4); }
+static double linear_to_srgb(double c) { return c <= 0.0031308 ? 12.92 * c : 1.055 * std::pow(c, 1.0 / 2.4) - 0.055; }
+
+void build_ramp(const swfr_color_stop *stops_in, uint32_t n, bool linear_rgb, bool morph_end, std::vector<float> &out,
+                bool *all_opaque) {
+  struct Stop {
+    double ratio;
+    double c[4];
+  };
+  std::vector<Stop> stops;
+  for (uint32_t i = 0; i < n; i++) {
+    const swfr_rgba8 &col = morph_end ? stops_in[i].morph_color : stops_in[i].color;
+    Stop s;
+    s.ratio = (double)stops_in[i].ratio / 255.0;
+    s.c[0] = col.r / 255.0, s.c[1] = col.g / 255.0, s.c[2] = col.b / 255.0, s.c[3] = col.a / 255.0;
+    if (linear_rgb)
+      for (int k = 0; k < 3; k++) s.c[k] = srgb_to_linear(s.c[k]);
+    stops.push_back(s);
+  }
+  std::stable_sort(stops.begin(), stops.end(), [](const Stop &a, const Stop &b) { return a.ratio < b.ratio; });
+  out.assign(257 * 4, 0.0f);
+  bool opaque = n > 0;
+  for (int k = 0; k <= 256; k++) {
+    double t = k / 256.0;
+    int j = -1;
+    for (size_t i = 0; i < stops.size(); i++)
+      if (stops[i].ratio <= t) j = (int)i;
+    double col[4] = {0, 0, 0, 0};
+    if (!stops.empty()) {
+      if (j < 0) {
+        memcpy(col, stops[0].c, sizeof col);
+      } else if (j == (int)stops.size() - 1) {
+        memcpy(col, stops[j].c, sizeof col);
+      } else {
+        const Stop &a = stops[j], &b = stops[j + 1];
+        double u = (t - a.ratio) / (b.ratio - a.ratio);
+        for (int c = 0; c < 4; c++) col[c] = a.c[c] + (b.c[c] - a.c[c]) * u;
+      }
+    }
+    if (linear_rgb)
+      for (int c = 0; c < 3; c++) col[c] = linear_to_srgb(col[c]);
+    for (int c = 0; c < 4; c++) out[4 * k + c] = (float)col[c];
+    if (out[4 * k + 3] != 1.0f) opaque = false;
+  }
+  if (all_opaque) *all_opaque = opaque;
+}
+
+int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, uint32_t *w, uint32_t *h, std::string &err) {
+  if (len < 6) {
+    err = "x-swf-bmp: truncated header";
+    return SWFR_ERR_MALFORMED;
+  }
+  if (data[0] != 3) {
+    err = "UnsupportedXSwfBmpFormatId";
+    return SWFR_ERR_UNSUPPORTED_STYLE;
+  }
+  uint32_t width = data[1] | (data[2] << 8), height = data[3] | (data[4] << 8);
+  uint32_t padded = width + ((4 - (width % 4)) % 4);
+  uint32_t color_count = (uint32_t)data[5] + 1;
+  size_t table = 3 * (size_t)color_count;
+  size_t need = table + (size_t)padded * height;
+  std::vector<uint8_t> src(need);
+  uLongf got = (uLongf)need;
+  int zr = uncompress(src.data(), &got, data + 6, (uLong)(len - 6));
+  if (zr != Z_OK && zr != Z_BUF_ERROR) {
+    err = "x-swf-bmp: zlib stream is corrupt";
+    return SWFR_ERR_MALFORMED;
+  }
+  if (got < need) {
+    err = "x-swf-bmp: pixel data is truncated";
+    return SWFR_ERR_MALFORMED;
+  }
+  rgba.resize((size_t)width * height * 4);
+  for (uint32_t y = 0; y < height; y++) {
+    for (uint32_t x = 0; x < width; x++) {
+      uint32_t ci = src[table + (size_t)y * padded + x];
+      uint8_t *o = &rgba[4 * ((size_t)y * width + x)];
+      if (ci < color_count) {
+        o[0] = src[3 * ci], o[1] = src[3 * ci + 1], o[2] = src[3 * ci + 2];
+      } else {
+        o[0] = o[1] = o[2] = 0;  // out-of-range index: opaque black (decode-x-swf-bmp.ts:35-36)
+      }
+      o[3] = 255;
+    }
+  }
+  *w = width;
+  *h = height;
+  return SWFR_OK;
+}
+
+}  // namespace swfr

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference renderer interface, on top of the C ABI (include/swfr.h).
+
+Names and argument meaning follow the reference so that tests read like its own:
+
+  rs/src/stage.rs:4-59            Stage, DisplayPrimitive::{Shape, MorphShape}, Matrix2D, MorphRatio
+  rs/src/asset.rs:9-12            ClientAssetStore.register_shape / register_morph_shape -> ShapeId / MorphShapeId
+  rs/src/swf_renderer.rs:3-5      SwfRenderer.render(stage)
+  rs/src/renderer.rs:89-103       Image{meta{width,height,stride}, data}
+  rs/src/headless_renderer.rs     HeadlessGfxRenderer.new(w, h) / define_shape / get_image
+  ts/src/lib/renderer.ts:4-8      Renderer.render(stage) / addBitmap(tag)
+
+Errors: the reference panics / throws / returns ``Err(&'static str)``; here every failing call raises
+``SwfrError`` carrying the status code of swfr.h and the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import capi
+from .swf_tree import convert_define_shape
+
+
+class SwfrError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("%s (status %d)" % (message, status))
+        self.status = status
+
+
+@dataclass
+class Matrix2D:
+    """rs/src/stage.rs:12-26: [scale_x, scale_y, rotate_skew0, rotate_skew1, translate_x, translate_y]."""
+
+    c: Sequence[float] = (1.0, 1.0, 0.0, 0.0, 0.0, 0.0)
+
+    @staticmethod
+    def translate(tx: float, ty: float) -> "Matrix2D":
+        return Matrix2D((1.0, 1.0, 0.0, 0.0, float(tx), float(ty)))
+
+
+@dataclass
+class StoredShape:  # DisplayPrimitive::Shape
+    id: int
+    matrix: Matrix2D = field(default_factory=Matrix2D)
+
+
+@dataclass
+class StoredMorphShape:  # DisplayPrimitive::MorphShape
+    id: int
+    matrix: Matrix2D = field(default_factory=Matrix2D)
+    ratio: int = 0  # MorphRatio(u16): 0 = start, 65535 = end
+
+
+DisplayPrimitive = Union[StoredShape, StoredMorphShape]
+
+
+@dataclass
+class Stage:
+    display_root: List[DisplayPrimitive] = field(default_factory=list)
+    background_color: Sequence[int] = (0, 0, 0, 0)
+
+
+@dataclass
+class ImageMetadata:
+    width: int
+    height: int
+    stride: int
+
+
+@dataclass
+class Image:
+    meta: ImageMetadata
+    data: np.ndarray  # (height, width, 4) uint8 RGBA
+
+
+def _stage_arrays(stages: Sequence[Stage]):
+    """Stage objects -> (swfr_stage[], keep-alive list)."""
+    arr = (capi.Stage * len(stages))()
+    keep = []
+    for i, st in enumerate(stages):
+        prims = (capi.DisplayPrimitive * max(1, len(st.display_root)))()
+        for j, p in enumerate(st.display_root):
+            prims[j].id = p.id
+            prims[j].matrix[:] = [float(v) for v in p.matrix.c]
+            if isinstance(p, StoredMorphShape):
+                prims[j].kind = capi.PRIM_MORPH_SHAPE
+                prims[j].ratio = int(p.ratio)
+            else:
+                prims[j].kind = capi.PRIM_SHAPE
+        keep.append(prims)
+        arr[i].background_color = capi.Rgba8(*[int(v) for v in st.background_color])
+        arr[i].n_primitives = len(st.display_root)
+        arr[i].display_root = C.cast(prims, C.POINTER(capi.DisplayPrimitive))
+    return arr, keep
+
+
+class HeadlessRenderer:
+    """SwfRenderer + ClientAssetStore over libswfr_b200 (one CUDA device, one stream per instance)."""
+
+    def __init__(self, width: int, height: int, device: int = 0, cuda_stream: Optional[int] = None):
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        self.width, self.height = int(width), int(height)
+        if cuda_stream is None:
+            rc = self._lib.swfr_create(device, self.width, self.height, C.byref(self._h))
+        else:
+            rc = self._lib.swfr_create_on_stream(device, self.width, self.height, C.c_void_p(cuda_stream), C.byref(self._h))
+        if rc != capi.OK:
+            self._h = C.c_void_p()
+            raise SwfrError(rc, "swfr_create failed: %s" % self._lib.swfr_status_string(rc).decode())
+
+    # -- lifecycle ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.swfr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != capi.OK:
+            raise SwfrError(rc, self._lib.swfr_last_error(self._h).decode() or self._lib.swfr_status_string(rc).decode())
+
+    def set_option(self, key: int, value: int):
+        self._check(self._lib.swfr_set_option(self._h, key, value))
+
+    # -- ClientAssetStore -----------------------------------------------------------------------------
+    def register_shape(self, tag) -> int:
+        """``tag``: define-shape AST dict (swf-tree JSON) or a converted capi.DefineShape."""
+        cv = convert_define_shape(tag) if isinstance(tag, dict) else None
+        out = C.c_uint32()
+        self._check(self._lib.swfr_register_shape(self._h, C.byref(cv.tag if cv else tag), C.byref(out)))
+        return out.value
+
+    define_shape = register_shape  # HeadlessGfxRenderer::define_shape
+
+    def register_morph_shape(self, tag) -> int:
+        cv = convert_define_shape(tag) if isinstance(tag, dict) else None
+        out = C.c_uint32()
+        self._check(self._lib.swfr_register_morph_shape(self._h, C.byref(cv.tag if cv else tag), C.byref(out)))
+        return out.value
+
+    def add_bitmap(self, tag: dict):
+        """Renderer.addBitmap(tag: DefineBitmap) (ts/src/lib/renderer.ts:7)."""
+        if tag["media_type"] != "image/x-swf-bmp":
+            raise SwfrError(capi.ERR_UNSUPPORTED_STYLE, "NotImplemented: Support for %s images" % tag["media_type"])
+        data = bytes.fromhex(tag["data"])
+        self._check(self._lib.swfr_register_bitmap_xswfbmp(self._h, tag["id"], data, len(data)))
+
+    def register_bitmap(self, bitmap_id: int, rgba: np.ndarray):
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = rgba.shape[:2]
+        self._check(self._lib.swfr_register_bitmap(self._h, bitmap_id, w, h, rgba.ctypes.data, w * 4))
+
+    # -- SwfRenderer ----------------------------------------------------------------------------------
+    def render(self, stage: Stage):
+        arr, keep = _stage_arrays([stage])
+        self._check(self._lib.swfr_render(self._h, arr))
+
+    def render_batch(self, stages: Sequence[Stage]):
+        arr, keep = _stage_arrays(stages)
+        self._check(self._lib.swfr_render_batch(self._h, arr, len(stages)))
+
+    def sync(self):
+        self._check(self._lib.swfr_sync(self._h))
+
+    def get_image(self, frame: int = 0, premultiplied: bool = False) -> Image:
+        """HeadlessGfxRenderer::get_image / download_image.  Straight alpha by default (PNG-export rounding)."""
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self._check(self._lib.swfr_read_image(self._h, frame, out.ctypes.data, self.width * 4, 1 if premultiplied else 0))
+        return Image(ImageMetadata(self.width, self.height, self.width * 4), out)
+
+    def stats(self) -> dict:
+        st = capi.Stats()
+        self._check(self._lib.swfr_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in capi.Stats._fields_}
+
+    # -- parity taps ----------------------------------------------------------------------------------
+    def debug_compiled(self, kind: int, def_id: int):
+        nc, npth = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.swfr_debug_compiled(self._h, kind, def_id, None, 0, C.byref(nc), None, 0, C.byref(npth)))
+        cmds = np.zeros((max(1, nc.value), 9), dtype=np.float64)
+        info = np.zeros((max(1, npth.value), 3), dtype=np.int32)
+        self._check(
+            self._lib.swfr_debug_compiled(
+                self._h, kind, def_id, cmds.ctypes.data, nc.value, C.byref(nc), info.ctypes.data, npth.value, C.byref(npth)
+            )
+        )
+        return cmds[: nc.value], info[: npth.value]
+
+    def debug_segments(self, kind: int, def_id: int) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(self._lib.swfr_debug_segments(self._h, kind, def_id, None, 0, C.byref(n)))
+        segs = np.zeros((max(1, n.value), 14), dtype=np.float64)
+        self._check(self._lib.swfr_debug_segments(self._h, kind, def_id, segs.ctypes.data, n.value, C.byref(n)))
+        return segs[: n.value]
+
+    def debug_edges(self, frame: int = 0):
+        n = C.c_uint64()
+        self._check(self._lib.swfr_debug_edges(self._h, frame, None, None, 0, C.byref(n)))
+        edges = np.zeros((max(1, n.value), 4), dtype=np.int32)
+        epath = np.zeros(max(1, n.value), dtype=np.int32)
+        self._check(self._lib.swfr_debug_edges(self._h, frame, edges.ctypes.data, epath.ctypes.data, n.value, C.byref(n)))
+        return edges[: n.value], epath[: n.value]
+
+    def debug_tile_counts(self, frame: int = 0) -> np.ndarray:
+        ty, tx = (self.height + 15) // 16, (self.width + 15) // 16
+        out = np.zeros((ty, tx), dtype=np.uint32)
+        self._check(self._lib.swfr_debug_tile_counts(self._h, frame, out.ctypes.data, out.size))
+        return out
+
+
+def decode_x_swf_bmp(data: bytes) -> np.ndarray:
+    """decodeXSwfBmpSync through the library's host decoder (no GPU needed)."""
+    lib = capi.load()
+    w, h = C.c_uint32(), C.c_uint32()
+    rc = lib.swfr_decode_xswfbmp(data, len(data), None, 0, C.byref(w), C.byref(h))
+    if rc != capi.OK:
+        raise SwfrError(rc, lib.swfr_status_string(rc).decode())
+    out = np.empty((h.value, w.value, 4), dtype=np.uint8)
+    rc = lib.swfr_decode_xswfbmp(data, len(data), out.ctypes.data, out.size, C.byref(w), C.byref(h))
+    if rc != capi.OK:
+        raise SwfrError(rc, lib.swfr_status_string(rc).decode())
+    return out
+
+
+def compile_tag(tag: dict, morph: bool = False):
+    """Host-only shape compile (decodeSwfShape / decodeSwfMorphShape restated in the library).
+
+    Returns (commands[n,9], path_info[n_paths,3], segments[n_seg,14]); see swfr_debug_compiled in swfr.h."""
+    import numpy as _np
+
+    lib = capi.load()
+    cv = convert_define_shape(tag)
+    nc, npth, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib.swfr_compile_debug(C.byref(cv.tag), int(morph), None, 0, C.byref(nc), None, 0, C.byref(npth), None, 0, C.byref(ns))
+    if rc != capi.OK:
+        raise SwfrError(rc, lib.swfr_status_string(rc).decode())
+    cmds = _np.zeros((max(1, nc.value), 9), dtype=_np.float64)
+    info = _np.zeros((max(1, npth.value), 3), dtype=_np.int32)
+    segs = _np.zeros((max(1, ns.value), 14), dtype=_np.float64)
+    rc = lib.swfr_compile_debug(
+        C.byref(cv.tag), int(morph), cmds.ctypes.data, nc.value, C.byref(nc), info.ctypes.data, npth.value, C.byref(npth),
+        segs.ctypes.data, ns.value, C.byref(ns),
+    )
+    if rc != capi.OK:
+        raise SwfrError(rc, lib.swfr_status_string(rc).decode())
+    return cmds[: nc.value], info[: npth.value], segs[: ns.value]

