@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the shape -> pixels hot path on the BASELINE.json workload.
+
+Workload (config.workload): SURVEY.md 8(d) config 5 / BASELINE.json configs[4] - a synthetic stream of
+10 000 random SWF shapes per frame at 1920x1080 (curves, left+right fills, solid / gradient / bitmap paints,
+translucency), 64 distinct frames per step and per GPU; frames are sharded over ranks with no data-path
+collective (weak scaling).  A "step" renders one batch of 64 frames.
+
+  value     Mpixel/s of rasterized output, whole job, stages resident in HBM (swfr_batch_render), CUDA events.
+  e2e       the same metric through the reference-facing C ABI call with HOST buffers: swfr_render_batch on host
+            stage arrays (host flattening + H2D inside the timed region) + D2H of every finished frame to pinned
+            host memory.
+  roofline  dominant kernel (k_fine: per-tile coverage + paint + blend): algorithmic bytes / CUDA-event time.
+  cpu_baseline  the oracle's C restatement of the reference CPU path, 1 thread, one frame of the same stream.
+
+`--impl reference` times the reference's own CPU algorithm (oracle restatement; the TypeScript/node-canvas
+original cannot run here: no node, no Rust toolchain) on all host cores, one frame of the same stream per core
+and per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rasterized_Mpixel_per_s"
+UNIT = "Mpixel/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="distinct frames per step and per GPU")
+    ap.add_argument("--shapes", type=int, default=10000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--frames-per-pass", type=int, default=0, help="0 = library default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": "synthetic stream, %d random SWF shapes/frame at %dx%d (SURVEY 8d config 5, BASELINE configs[4])"
+        % (a.shapes, a.width, a.height),
+        "frames_per_step_per_gpu": a.frames,
+        "shapes_per_frame": a.shapes,
+        "resolution": [a.width, a.height],
+        "sharding": "frames over %d rank(s), no data-path collective" % n_gpus,
+        "cache": "inputs larger than L2: %d distinct frames (draw lists + %.0f MB of output) per step"
+        % (a.frames, a.frames * a.width * a.height * 4 / 1e6),
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arms (oracle = restatement of the reference CPU path; test infrastructure used here as the baseline only)
+# ----------------------------------------------------------------------------------------------------------
+
+
+def _oracle_scene(frame_index, a):
+    import synth
+    from oracle import compile_shape as cs
+    from oracle import raster
+
+    fr = synth.SynthFrame(frame_index, a.shapes, a.width, a.height)
+    b = raster._Builder({i: t for i, t in enumerate(synth.textures())})
+    for i in range(fr.n):
+        b.add_item(raster.add_shape_def(b, cs.compile_shape(fr.ast(i))), fr.matrix(i))
+    return b, b.scene(a.width, a.height)
+
+
+_WORKER = {}
+
+
+def _worker_init(frame_base, a_dict):
+    a = argparse.Namespace(**a_dict)
+    import multiprocessing as mp
+
+    idx = mp.current_process()._identity[0] - 1
+    _WORKER["scene"] = _oracle_scene(frame_base + idx, a)
+
+
+def _worker_step(_):
+    from oracle import raster
+
+    t = time.perf_counter()
+    raster.render_scene(_WORKER["scene"][1])
+    return time.perf_counter() - t
+
+
+def cpu_baseline_single(a):
+    from oracle import raster
+
+    _, sc = _oracle_scene(0, a)
+    t = time.perf_counter()
+    raster.render_scene(sc)
+    dt = time.perf_counter() - t
+    return {
+        "value": a.width * a.height / dt / 1e6,
+        "unit": UNIT,
+        "cores": 1,
+        "kind": "port",
+        "sample": "frame 0 of the same stream (1 of %d frames), C restatement of the reference CPU path, 1 thread, %.1f s"
+        % (a.frames, dt),
+    }
+
+
+def run_reference(a):
+    """Reference arm: the reference's CPU algorithm on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from oracle import raster
+
+    raster.build()
+    cores = max(1, len(os.sched_getaffinity(0)))
+    cores = min(cores, 64)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_worker_init, initargs=(0, vars(a))) as pool:
+        for _ in range(a.warmup):
+            pool.map(_worker_step, range(cores), chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            pool.map(_worker_step, range(cores), chunksize=1)
+        dt = time.perf_counter() - t0
+    px = cores * a.width * a.height * a.steps
+    value = px / dt / 1e6
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": a.gpus,
+        "steps": a.steps,
+        "warmup": a.warmup,
+        "ms_per_step": dt / a.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u8 (Q16 integer coverage, f32 paint)",
+        "data": "synthetic",
+        "config": workload_config(a, a.gpus),
+        "shapes_per_s": cores * a.shapes * a.steps / dt,
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": "%d frames of the same stream per step (one per core), C restatement of the reference's "
+            "TypeScript/Cairo path (node and cargo are absent, the original cannot run)" % cores,
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import synth
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import stage_array_from_numpy, stages_from_prims
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    r = sw.HeadlessRenderer(a.width, a.height, device=local, cuda_stream=stream.cuda_stream)
+    r.set_option(capi.OPT_RETAIN_COMPILED, 0)
+    if a.frames_per_pass:
+        r.set_option(capi.OPT_FRAMES_PER_PASS, a.frames_per_pass)
+
+    # ---- inputs: textures, definitions, stages (host arrays) ----
+    for i, t in enumerate(synth.textures()):
+        r.register_bitmap(i, t)
+    prim_arrays = []
+    for f in range(a.frames):
+        fr = synth.SynthFrame(rank * a.frames + f, a.shapes, a.width, a.height)
+        ids = fr.register(r)
+        prim_arrays.append(stage_array_from_numpy(ids, fr.matrices()))
+    stage_arr, keep = stages_from_prims(prim_arrays)
+    h2d_bytes = a.frames * a.shapes * 52  # 48 B draw item + 4 B offsets per primitive
+    d2h_bytes = a.frames * a.width * a.height * 4
+    px_per_step = a.frames * a.width * a.height
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: stages resident in HBM ----
+    batch = r.create_batch((stage_arr, keep))
+    for _ in range(max(a.warmup, 3)):
+        batch.render()
+    r.sync()
+    stats = r.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        batch.render()
+    e1.record(stream)
+    r.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = r.stats()["kernel_launches"] * a.steps
+    value = world * px_per_step * a.steps / (ms / 1e3) / 1e6
+
+    # ---- roofline of the dominant kernel, CUDA events on the launching stream (separate pass) ----
+    r.set_option(capi.OPT_PROFILE, 1)
+    acc = {}
+    n_prof = 3
+    passes = 0
+    for _ in range(n_prof):
+        batch.render()
+        st = r.stage_times()
+        passes = st["passes"]
+        for k, v in st["ms"].items():
+            acc[k] = acc.get(k, 0.0) + v / n_prof
+    r.set_option(capi.OPT_PROFILE, 0)
+    stats = r.stats()
+    fine_ms_per_launch = acc["fine"] / max(passes, 1)
+    fine_bytes_per_launch = (8 * stats["n_records"] + 4 * px_per_step) / max(passes, 1)
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    achieved = fine_bytes_per_launch / (fine_ms_per_launch / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            traffic = json.load(f).get("k_fine_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm",
+        "kernel": "k_fine (per-tile coverage + paint + blend)",
+        "achieved": achieved,
+        "peak": peak,
+        "peak_source": peak_src,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": traffic,
+        "algorithmic_bytes_per_launch": fine_bytes_per_launch,
+        "launch_ms": fine_ms_per_launch,
+        "launches_per_step": passes,
+        "stage_ms_per_step": acc,
+        "pipeline": {
+            "algorithmic_bytes_per_step": stats["algorithmic_bytes"],
+            "achieved": stats["algorithmic_bytes"] / (sum(acc.values()) / 1e3) / 1e9,
+            "frac": stats["algorithmic_bytes"] / (sum(acc.values()) / 1e3) / 1e9 / peak,
+        },
+    }
+
+    # ---- e2e: host stage arrays in, finished frames out to pinned host memory ----
+    host_out = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    for _ in range(2):
+        r.render_stage_array(stage_arr, a.frames)
+        r.read_frames_async(0, a.frames, host_out.data_ptr())
+        r.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r.render_stage_array(stage_arr, a.frames)
+        r.read_frames_async(0, a.frames, host_out.data_ptr())
+        r.sync()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * px_per_step * a.steps / e2e_s / 1e6
+    checksum = int(host_out[:: 4096].to(torch.int64).sum().item())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": a.steps,
+            "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u8 (Q16 integer coverage, f32 paint)",
+            "data": "synthetic",
+            "config": workload_config(a, world),
+            "shapes_per_s": world * a.frames * a.shapes * a.steps / (ms / 1e3),
+            "frames_per_s": world * a.frames * a.steps / (ms / 1e3),
+            "clocks": clocks,
+            "e2e": {
+                "value": e2e_value,
+                "unit": UNIT,
+                "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_s / a.steps * 1e3,
+                "checksum": checksum,
+            },
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "per_step": {k: stats[k] for k in ("n_primitives", "n_segments", "n_edges", "n_slots", "n_records", "retries")},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single(a)
+        print(json.dumps(line), flush=True)
+    batch.close()
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

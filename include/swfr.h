@@ -182,7 +182,7 @@ uint32_t swfr_abi_version(void);
 /* Options: SWFR_OPT_RETAIN_COMPILED (default 1) keeps the compiled paths of every definition on the host for
  * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 4) bounds how many frames
  * share one set of launches and one working set. */
-typedef enum swfr_option { SWFR_OPT_RETAIN_COMPILED = 1, SWFR_OPT_FRAMES_PER_PASS = 2 } swfr_option;
+typedef enum swfr_option { SWFR_OPT_RETAIN_COMPILED = 1, SWFR_OPT_FRAMES_PER_PASS = 2, SWFR_OPT_PROFILE = 3 } swfr_option;
 int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value);
 
 /* ---- asset store ------------------------------------------------------------------------------------ */
@@ -230,6 +230,11 @@ typedef struct swfr_stats {
   uint32_t retries;           /* re-runs caused by working-memory growth */
 } swfr_stats;
 int swfr_get_stats(swfr_renderer *r, swfr_stats *out);
+/* With SWFR_OPT_PROFILE = 1 every pass records CUDA events (on the renderer's stream) at its stage boundaries;
+ * this returns the per-stage device time of the last render summed over its passes, and the number of passes
+ * (= launches of each stage's kernels).  Stage names via swfr_stage_name(i). */
+int swfr_get_stage_times(swfr_renderer *r, float *ms, uint32_t cap, uint32_t *n_stages, uint32_t *n_passes);
+const char *swfr_stage_name(uint32_t i);
 
 /* ---- parity taps ------------------------------------------------------------------------------------ */
 

@@ -20,7 +20,7 @@ SPREAD_PAD, SPREAD_REFLECT, SPREAD_REPEAT = 0, 1, 2
 COLOR_SRGB, COLOR_LINEAR_RGB = 0, 1
 RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
 PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
-OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS = 1, 2
+OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE = 1, 2, 3
 
 
 class Rgba8(C.Structure):
@@ -179,6 +179,11 @@ PROTOTYPES = {
     "swfr_read_frames_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "swfr_device_frames": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "swfr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "swfr_get_stage_times": (
+        C.c_int,
+        [C.c_void_p, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+    ),
+    "swfr_stage_name": (C.c_char_p, [C.c_uint32]),
     "swfr_debug_compiled": (
         C.c_int,
         [

@@ -975,7 +975,14 @@ static void scan_u32(uint32_t *data, const uint32_t *n_ptr, uint32_t n_cap, uint
   launches += 3;
 }
 
-int launch_render(const RenderArgs &a, cudaStream_t st) {
+const char *stage_name(int i) {
+  static const char *names[kNumStages] = {"flatten_count", "scan_edges",   "path_setup",  "flatten_emit",
+                                          "bin_count",     "scan_records", "bin_scatter", "fine"};
+  return (i >= 0 && i < kNumStages) ? names[i] : "?";
+}
+
+// ev (optional): kNumStages + 1 events recorded at the stage boundaries (profiling runs only).
+int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   int launches = 0;
   const int T = 256;
   auto grid_for = [&](uint64_t n) {
@@ -983,16 +990,22 @@ int launch_render(const RenderArgs &a, cudaStream_t st) {
     uint64_t cap = (uint64_t)kNumSM * 16;
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
   };
+  auto mark = [&](int i) {
+    if (ev) cudaEventRecord(ev[i], st);
+  };
   const unsigned wide = kNumSM * 16;
+  mark(0);
   k_init<<<grid_for(a.n_paths), T, 0, st>>>(a);
   launches++;
   if (a.n_seginst) {
     k_flatten_count<<<grid_for(a.n_seginst), T, 0, st>>>(a);
     launches++;
   }
+  mark(1);
   // edges: seg_edge_off (piece counts) -> exclusive offsets, total -> totals.n_edges
   scan_u32(a.seg_edge_off, nullptr, a.n_seginst, a.scan_tmp, &a.totals->n_edges, a.caps.edges, &a.totals->overflow, 1u,
            st, launches);
+  mark(2);
   if (a.n_paths) {
     k_path_setup<<<grid_for(a.n_paths), T, 0, st>>>(a);
     launches++;
@@ -1001,12 +1014,18 @@ int launch_render(const RenderArgs &a, cudaStream_t st) {
            st, launches);
   k_zero_slots<<<wide, T, 0, st>>>(a);
   launches++;
+  mark(3);
   if (a.n_seginst) {
     k_flatten_emit<<<grid_for(a.n_seginst), T, 0, st>>>(a);
+    launches++;
+  }
+  mark(4);
+  if (a.n_seginst) {
     k_bin<0><<<wide, T, 0, st>>>(a);
     k_backdrop<<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    launches += 3;
+    launches += 2;
   }
+  mark(5);
   // records: slot_count -> slot_off (separate array so counts can be reused as scatter cursors)
   k_copy_counts<<<wide, T, 0, st>>>(a);
   launches++;
@@ -1014,11 +1033,17 @@ int launch_render(const RenderArgs &a, cudaStream_t st) {
            &a.totals->overflow, 4u, st, launches);
   if (a.n_seginst) {
     k_zero_cursor<<<wide, T, 0, st>>>(a);
-    k_bin<1><<<wide, T, 0, st>>>(a);
-    launches += 2;
+    launches++;
   }
+  mark(6);
+  if (a.n_seginst) {
+    k_bin<1><<<wide, T, 0, st>>>(a);
+    launches++;
+  }
+  mark(7);
   k_fine<<<kNumSM * 4, kFineWarps * 32, 0, st>>>(a);
   launches++;
+  mark(8);
   return launches;
 }
 

@@ -93,8 +93,13 @@ struct RenderArgs {
   Caps caps;
 };
 
+// Pipeline stages as seen by the profiler hooks (swfr_get_stage_times).
+constexpr int kNumStages = 8;
+const char *stage_name(int i);
+
 // Enqueues every kernel of one render on `stream`; returns the number of kernels launched.
-int launch_render(const RenderArgs &a, cudaStream_t stream);
+// `ev` (optional) points at kNumStages + 1 events recorded at the stage boundaries.
+int launch_render(const RenderArgs &a, cudaStream_t stream, cudaEvent_t *ev = nullptr);
 
 void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
 void launch_premultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);

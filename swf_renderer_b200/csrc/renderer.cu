@@ -128,6 +128,11 @@ struct swfr_renderer {
   swfr_stats stats{};
   std::vector<Totals> last_totals;
   size_t arena_pass = 0;  // index of the pass whose working set is in the arena
+  bool profile = false;   // record CUDA events at the stage boundaries of every pass
+  std::vector<cudaEvent_t> prof_events;
+  size_t prof_passes = 0;
+  float stage_ms[kNumStages] = {0};
+  uint32_t stage_launches = 0;
 };
 
 namespace {
@@ -348,7 +353,19 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
   rc = ensure_arena(r, b);
   if (rc != SWFR_OK) return rc;
   uint32_t launches = 0;
-  for (size_t i = 0; i < b.passes.size(); i++) launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
+  r->prof_passes = 0;
+  if (r->profile) {
+    size_t need = b.passes.size() * (kNumStages + 1);
+    while (r->prof_events.size() < need) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      r->prof_events.push_back(e);
+    }
+    r->prof_passes = b.passes.size();
+  }
+  for (size_t i = 0; i < b.passes.size(); i++)
+    launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream,
+                                        r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr);
   CK(cudaGetLastError());
   r->last = &b;
   r->arena_pass = b.passes.empty() ? 0 : b.passes.size() - 1;
@@ -393,6 +410,17 @@ int finish(swfr_renderer *r) {
     }
   }
   r->pending = false;
+  if (r->prof_passes) {
+    for (int k = 0; k < kNumStages; k++) r->stage_ms[k] = 0.f;
+    for (size_t i = 0; i < r->prof_passes; i++) {
+      cudaEvent_t *ev = r->prof_events.data() + i * (kNumStages + 1);
+      for (int k = 0; k < kNumStages; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) r->stage_ms[k] += ms;
+      }
+    }
+    r->stage_launches = (uint32_t)r->prof_passes;
+  }
   uint32_t err = 0;
   r->stats.n_primitives = b.n_prims;
   r->stats.n_segments = b.n_seginst;
@@ -527,6 +555,7 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
   switch (key) {
     case 1: r->retain_compiled = value != 0; return SWFR_OK;
     case 2: r->frames_per_pass = (uint32_t)std::max<uint64_t>(1, value); return SWFR_OK;
+    case 3: r->profile = value != 0; return SWFR_OK;
     default: return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown option");
   }
 }
@@ -669,6 +698,18 @@ int swfr_sync(swfr_renderer *r) {
   CK(cudaStreamSynchronize(r->stream));
   return SWFR_OK;
 }
+
+int swfr_get_stage_times(swfr_renderer *r, float *ms, uint32_t cap, uint32_t *n_stages, uint32_t *n_passes) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  int rc = swfr_sync(r);
+  if (rc != SWFR_OK) return rc;
+  for (uint32_t k = 0; k < (uint32_t)kNumStages && ms && k < cap; k++) ms[k] = r->stage_ms[k];
+  if (n_stages) *n_stages = kNumStages;
+  if (n_passes) *n_passes = r->stage_launches;
+  return SWFR_OK;
+}
+
+const char *swfr_stage_name(uint32_t i) { return stage_name((int)i); }
 
 int swfr_get_stats(swfr_renderer *r, swfr_stats *out) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;

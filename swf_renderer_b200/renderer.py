@@ -188,6 +188,29 @@ class HeadlessRenderer:
         self._check(self._lib.swfr_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in capi.Stats._fields_}
 
+    def stage_times(self) -> dict:
+        """Per-stage device milliseconds of the last render (needs set_option(OPT_PROFILE, 1) before it)."""
+        ms = (C.c_float * 16)()
+        n, passes = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.swfr_get_stage_times(self._h, ms, 16, C.byref(n), C.byref(passes)))
+        names = [self._lib.swfr_stage_name(i).decode() for i in range(n.value)]
+        return {"passes": passes.value, "ms": {names[i]: float(ms[i]) for i in range(n.value)}}
+
+    # -- stages resident in HBM (repeated rendering without host traffic) -------------------------------
+    def create_batch(self, stages) -> "ResidentBatch":
+        """``stages``: sequence of Stage objects, or a prebuilt (capi.Stage array, keep-alive) pair."""
+        arr, keep = stages if isinstance(stages, tuple) else _stage_arrays(stages)
+        h = C.c_void_p()
+        self._check(self._lib.swfr_batch_create(self._h, arr, len(arr), C.byref(h)))
+        return ResidentBatch(self, h, len(arr))
+
+    def render_stage_array(self, arr, n: int):
+        """swfr_render_batch on a prebuilt capi.Stage array (host buffers; used by the end-to-end benchmark)."""
+        self._check(self._lib.swfr_render_batch(self._h, arr, n))
+
+    def read_frames_async(self, first: int, count: int, dst_ptr: int):
+        self._check(self._lib.swfr_read_frames_async(self._h, first, count, C.c_void_p(dst_ptr)))
+
     # -- parity taps ----------------------------------------------------------------------------------
     def debug_compiled(self, kind: int, def_id: int):
         nc, npth = C.c_uint64(), C.c_uint64()
@@ -221,6 +244,51 @@ class HeadlessRenderer:
         out = np.zeros((ty, tx), dtype=np.uint32)
         self._check(self._lib.swfr_debug_tile_counts(self._h, frame, out.ctypes.data, out.size))
         return out
+
+
+class ResidentBatch:
+    """A set of stages flattened and uploaded once (swfr_batch_create)."""
+
+    def __init__(self, renderer: HeadlessRenderer, handle, n_frames: int):
+        self._r, self._h, self.n_frames = renderer, handle, n_frames
+
+    def render(self):
+        self._r._check(self._r._lib.swfr_batch_render(self._r._h, self._h))
+
+    def close(self):
+        if self._h and self._h.value and self._r._h.value:
+            self._r._lib.swfr_batch_destroy(self._r._h, self._h)
+        self._h = C.c_void_p()
+
+
+def stage_array_from_numpy(ids: np.ndarray, matrices: np.ndarray, kinds=None, ratios=None):
+    """Bulk construction of ONE swfr_stage from arrays (ids[n], matrices[n,6] float32) without Python loops."""
+    n = len(ids)
+    prims = (capi.DisplayPrimitive * max(1, n))()
+    P = capi.DisplayPrimitive
+    dt = np.dtype(
+        {
+            "names": ["kind", "id", "matrix", "ratio"],
+            "formats": [np.uint32, np.uint32, (np.float32, 6), np.uint16],
+            "offsets": [P.kind.offset, P.id.offset, P.matrix.offset, P.ratio.offset],
+            "itemsize": C.sizeof(P),
+        }
+    )
+    v = np.frombuffer(prims, dtype=dt)
+    v["id"][:n] = ids
+    v["matrix"][:n] = matrices
+    v["kind"][:n] = 0 if kinds is None else kinds
+    v["ratio"][:n] = 0 if ratios is None else ratios
+    return prims, n
+
+
+def stages_from_prims(prim_arrays):
+    """[(DisplayPrimitive array, n)] -> (capi.Stage array, keep-alive)."""
+    arr = (capi.Stage * len(prim_arrays))()
+    for i, (prims, n) in enumerate(prim_arrays):
+        arr[i].n_primitives = n
+        arr[i].display_root = C.cast(prims, C.POINTER(capi.DisplayPrimitive))
+    return arr, list(prim_arrays)
 
 
 def decode_x_swf_bmp(data: bytes) -> np.ndarray:
