@@ -8,6 +8,7 @@
 //   ts/src/lib/renderers/canvas-renderer.ts:179-188  applyMatrix -> x' = sx*x + rs1*y + tx, y' = rs0*x + sy*y + ty
 //   ts/src/lib/renderers/canvas-renderer.ts:269-350  one path = one fill(): non-zero, source-over, in order
 //   ts/src/lib/css-color.ts:11-13                    colour channel quantisation of morph-lerped colours
+#include <algorithm>
 #include <cstdio>
 
 #include "kernels.h"
@@ -24,12 +25,45 @@ __device__ __forceinline__ long long floordiv64(long long a, long long b) {  // 
   if ((a % b != 0) && (a < 0)) q -= 1;
   return q;
 }
-__device__ __forceinline__ long long rdiv64(long long a, long long b) {  // round half up, b != 0
+// round half up of a / b (b != 0): the exact integer floor((2a + b) / (2b)), computed without the 64-bit
+// integer divide subroutine.  Operands that fit 30/24 bits (every edge of ordinary size) take a float
+// reciprocal estimate; larger ones take an FP64 quotient; both are then corrected against the exact integer
+// remainder, so the result is the mathematical floor in all cases (same value as the oracle's rdiv64).
+__device__ __forceinline__ long long rdiv64(long long a, long long b) {
   if (b < 0) {
     a = -a;
     b = -b;
   }
-  return floordiv64(2 * a + b, 2 * b);
+  long long num = 2 * a + b, den = 2 * b;
+  long long an = num < 0 ? -num : num;
+  if (an < (1ll << 30) && den < (1ll << 24) && den >= 256) {  // |q| < 2^22: the estimate is off by at most 1-2
+    int n32 = (int)num, d32 = (int)den;
+    int q = (int)floorf(__fdividef((float)n32, (float)d32));
+    int r = n32 - q * d32;
+    while (r < 0) {
+      q--;
+      r += d32;
+    }
+    while (r >= d32) {
+      q++;
+      r -= d32;
+    }
+    return (long long)q;
+  }
+  if (an < (1ll << 52)) {
+    long long q = (long long)floor((double)num / (double)den);
+    long long r = num - q * den;
+    while (r < 0) {
+      q--;
+      r += den;
+    }
+    while (r >= den) {
+      q++;
+      r -= den;
+    }
+    return q;
+  }
+  return floordiv64(num, den);
 }
 __device__ __forceinline__ int iabs32(int a) { return a < 0 ? -a : a; }
 
@@ -85,15 +119,24 @@ __device__ int piece_count(bool curve, const int *p) {
   return (int)n;
 }
 
+// round-half-up of num / den for integer-valued doubles with |num| < 2^50, 0 < den < 2^25: every operand and
+// the numerator 2 num + den are exact in FP64 and the quotient cannot round across an integer (the distance of a
+// non-integer quotient to the next integer is >= 1/(2 den) >= 2^-26 while the rounding error is < 2^-27), so this
+// is the exact integer floor((2 num + den) / (2 den)), i.e. the oracle's rdiv64.
+__device__ __forceinline__ int rdiv_f64(double num, double den) {
+  return (int)floor((2.0 * num + den) / (2.0 * den));
+}
+
 __device__ __forceinline__ void piece_point(bool curve, const int *p, int n, int i, int &x, int &y) {
   if (!curve) {
-    x = p[0] + (int)rdiv64(((long long)p[4] - p[0]) * i, n);
-    y = p[1] + (int)rdiv64(((long long)p[5] - p[1]) * i, n);
+    x = p[0] + rdiv_f64(((double)p[4] - (double)p[0]) * (double)i, (double)n);
+    y = p[1] + rdiv_f64(((double)p[5] - (double)p[1]) * (double)i, (double)n);
   } else {
-    long long a = (long long)(n - i) * (n - i), b = 2 * (long long)i * (n - i), c = (long long)i * i,
-              nn = (long long)n * n;
-    x = (int)rdiv64(a * p[0] + b * p[2] + c * p[4], nn);
-    y = (int)rdiv64(a * p[1] + b * p[3] + c * p[5], nn);
+    // all products are exact: a, b, c <= n^2 <= 2^24 and |p| <= 2^24
+    double a = (double)(n - i) * (double)(n - i), b = 2.0 * (double)i * (double)(n - i), c = (double)i * (double)i,
+           nn = (double)n * (double)n;
+    x = rdiv_f64(a * (double)p[0] + b * (double)p[2] + c * (double)p[4], nn);
+    y = rdiv_f64(a * (double)p[1] + b * (double)p[3] + c * (double)p[5], nn);
   }
 }
 
@@ -153,6 +196,11 @@ __global__ void k_init(RenderArgs a) {
     a.totals->overflow = 0;
     a.totals->error = 0;
     a.totals->work = 0;
+    a.totals->n_list = 0;
+  }
+  for (uint32_t l = i; l < a.n_lists; l += stride) {
+    a.list_off[l] = 0;
+    a.list_cursor[l] = 0;
   }
   for (uint32_t p = i; p < a.n_paths; p += stride) {
     a.path_bbox[4 * p + 0] = INT_MAX;
@@ -428,6 +476,76 @@ __global__ void k_path_setup(RenderArgs a) {
   }
 }
 
+// Candidate lists: one entry per (tile row, column group) a path's bbox overlaps.  One warp per path instance,
+// lanes over its (row, group) cells.  FILL = false counts, FILL = true appends (unordered; sorted afterwards).
+template <bool FILL>
+__global__ void k_list_build(RenderArgs a) {
+  if (FILL && a.totals->overflow) return;
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t pid = warp; pid < a.n_paths; pid += nwarps) {
+    PathRec rec = a.path_rec[pid];
+    int bx0 = rec.xy0 & 0xffff, by0 = rec.xy0 >> 16, bw = rec.wh & 0xffff, bh = rec.wh >> 16;
+    if (bw == 0) continue;
+    uint32_t frame = a.items[find_owner(a.item_path_off, a.n_items, pid)].frame;
+    uint32_t g0 = (uint32_t)bx0 / kGroupTiles, ng = (uint32_t)(bx0 + bw - 1) / kGroupTiles - g0 + 1;
+    uint32_t cells = ng * (uint32_t)bh;
+    for (uint32_t c = lane; c < cells; c += 32) {
+      uint32_t y = c / ng, g = c - y * ng;
+      uint32_t l = (frame * (uint32_t)a.tiles_y + (uint32_t)by0 + y) * a.groups_x + g0 + g;
+      if (FILL) {
+        uint32_t pos = a.list_off[l] + atomicAdd(&a.list_cursor[l], 1u);
+        a.list_items[pos] = pid;
+      } else {
+        atomicAdd(&a.list_off[l], 1u);
+      }
+    }
+  }
+}
+
+// ... step 3: each list is sorted ascending, i.e. back into paint order (bitonic network without direction bits;
+// entries past the end behave as +inf).  One block per list; lists of up to kSortSmem entries sort in shared memory.
+constexpr int kSortThreads = 128;
+constexpr int kSortSmem = 4096;
+
+__global__ void __launch_bounds__(kSortThreads) k_list_sort(RenderArgs a) {
+  if (a.totals->overflow) return;
+  __shared__ uint32_t sh[kSortSmem];
+  for (uint32_t l = blockIdx.x; l < a.n_lists; l += gridDim.x) {
+    uint32_t off = a.list_off[l], n = a.list_off[l + 1] - off;
+    if (n < 2) continue;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    uint32_t *g = a.list_items + off;
+    const bool in_smem = P <= (uint32_t)kSortSmem;
+    uint32_t *d = in_smem ? sh : g;
+    const uint32_t lim = in_smem ? P : n;  // shared memory holds the +inf padding explicitly
+    if (in_smem) {
+      for (uint32_t i = threadIdx.x; i < P; i += kSortThreads) sh[i] = i < n ? g[i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = threadIdx.x; i < P; i += kSortThreads) {
+          uint32_t p = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+          if (p > i && p < lim) {
+            uint32_t x = d[i], y = d[p];
+            if (x > y) {
+              d[i] = y;
+              d[p] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (in_smem) {
+      for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) g[i] = sh[i];
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void k_zero_slots(RenderArgs a) {
   if (a.totals->overflow) return;
   uint32_t n = a.totals->n_slots;
@@ -456,8 +574,24 @@ __global__ void k_zero_cursor(RenderArgs a) {
 // K2: tile binning (count, then scatter of tile-clipped 8-byte records)
 // ======================================================================================================
 
-__device__ __forceinline__ int xat(int x0, int y0, int x1, int y1, int Y) {
-  return x0 + (int)rdiv64(((long long)Y - y0) * ((long long)x1 - x0), (long long)y1 - y0);
+// round-half-up of p * q / d (d != 0).  SMALL: |p|, |q|, |d| <= 2^14 (an edge of at most 64 px per axis) and
+// |p| <= |d|, so everything fits 32 bits and |result| <= 2^14: a float quotient is then off by at most one and a
+// single remainder check makes it the exact integer (same value as the oracle's rdiv64).
+template <bool SMALL>
+__device__ __forceinline__ int muldiv(int p, int q, int d) {
+  if (SMALL) {
+    int a = p * q;
+    if (d < 0) {
+      a = -a;
+      d = -d;
+    }
+    int num = 2 * a + d, den = 2 * d;
+    int qq = (int)floorf(__fdividef((float)num, (float)den));
+    int r = num - qq * den;
+    qq += (int)(r >= den) - (int)(r < 0);
+    return qq;
+  }
+  return (int)rdiv64((long long)p * (long long)q, (long long)d);
 }
 
 __device__ __forceinline__ unsigned long long pack_record(int xa, int ya, int xb, int yb, int fs, int fe) {
@@ -465,38 +599,40 @@ __device__ __forceinline__ unsigned long long pack_record(int xa, int ya, int xb
          ((unsigned long long)yb << 39) | ((unsigned long long)fs << 52) | ((unsigned long long)fe << 53);
 }
 
-template <int MODE>  // 0 = count + backdrop deltas, 1 = scatter records
+// Walks one edge over the tile grid of its path.  MODE 0 counts records and posts backdrop deltas, MODE 1
+// scatters the tile-clipped records.  Crossings with band and tile boundaries are computed once and carried.
+template <int MODE, bool SMALL>
 __device__ void bin_edge(const RenderArgs &a, int x0, int y0, int x1, int y1, int bx0, int by0, int bw, int bh,
                          uint32_t slot_base) {
   const int B = kTileFx;
-  int b_first, b_last;
-  if (y0 == y1) {
-    b_first = b_last = y0 >> 12;
-  } else {
-    int ylo = min(y0, y1), yhi = max(y0, y1);
-    b_first = ylo >> 12;
-    b_last = (yhi - 1) >> 12;
-  }
+  const bool horiz = y0 == y1;
+  const bool down = y0 < y1;
+  const int ylo = min(y0, y1), yhi = max(y0, y1);
+  const int x_ylo = down ? x0 : x1, x_yhi = down ? x1 : x0;  // x at the upper / lower end point
+  int b_first = ylo >> 12, b_last = horiz ? b_first : (yhi - 1) >> 12;
   // rows outside the path's grid are outside the viewport (the bbox covers every edge of the path)
   b_first = max(b_first, by0);
   b_last = min(b_last, by0 + bh - 1);
+  if (b_first > b_last) return;
+  int x_top = 0;  // x where the edge crosses the top line of the current band (when it starts above it)
+  if (!horiz && ylo < b_first * B) x_top = x0 + muldiv<SMALL>(b_first * B - y0, x1 - x0, y1 - y0);
   for (int b = b_first; b <= b_last; b++) {
-    int Yt = b * B, Yb = Yt + B;
+    const int Yt = b * B, Yb = Yt + B;
     int xs, ys, xe, ye;
-    if (y0 == y1) {
+    if (horiz) {
       xs = x0, ys = y0, xe = x1, ye = y1;
-    } else if (y0 < y1) {
-      ys = max(y0, Yt);
-      ye = min(y1, Yb);
-      xs = (ys == y0) ? x0 : xat(x0, y0, x1, y1, ys);
-      xe = (ye == y1) ? x1 : xat(x0, y0, x1, y1, ye);
     } else {
-      ys = min(y0, Yb);
-      ye = max(y1, Yt);
-      xs = (ys == y0) ? x0 : xat(x0, y0, x1, y1, ys);
-      xe = (ye == y1) ? x1 : xat(x0, y0, x1, y1, ye);
+      int yu = max(ylo, Yt), yl = min(yhi, Yb);
+      int xu = (ylo >= Yt) ? x_ylo : x_top;
+      int xl = (yhi <= Yb) ? x_yhi : x0 + muldiv<SMALL>(Yb - y0, x1 - x0, y1 - y0);
+      x_top = xl;
+      if (down) {
+        xs = xu, ys = yu, xe = xl, ye = yl;
+      } else {
+        xs = xl, ys = yl, xe = xu, ye = yu;
+      }
     }
-    uint32_t row_base = slot_base + (uint32_t)((b - by0) * bw);
+    const uint32_t row_base = slot_base + (uint32_t)((b - by0) * bw);
     if (MODE == 0) {
       if (ys == Yt) {
         int lx = max((xs >> 12) + 1 - bx0, 0);
@@ -507,26 +643,29 @@ __device__ void bin_edge(const RenderArgs &a, int x0, int y0, int x1, int y1, in
         if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], -1);
       }
     }
-    int c0 = max(min(xs, xe) >> 12, bx0), c1 = min(max(xs, xe) >> 12, bx0 + bw - 1);
+    const int xlo = min(xs, xe), xhi = max(xs, xe);
+    const int c0 = max(xlo >> 12, bx0), c1 = min(xhi >> 12, bx0 + bw - 1);
+    if (c0 > c1) continue;
+    const bool right = xs < xe;
+    // y where the sub-edge crosses the left boundary of the current tile (when it reaches further left)
+    int y_left = 0;
+    if (xlo < c0 * B) y_left = ys + muldiv<SMALL>(c0 * B - xs, ye - ys, xe - xs);
     for (int t = c0; t <= c1; t++) {
-      int X0 = t * B, X1 = X0 + B;
+      const int X0 = t * B, X1 = X0 + B;
+      const bool clip_l = xlo < X0, clip_r = xhi > X1;
+      int y_right = 0;  // also needed by the next tile when the sub-edge ends exactly on the boundary
+      if (clip_r || t < c1) y_right = ys + muldiv<SMALL>(X1 - xs, ye - ys, xe - xs);
       int ax, ay, bx, by, fs = 0, fe = 0;
-      if (xs < X0) {
-        ax = X0, ay = ys + (int)rdiv64(((long long)X0 - xs) * ((long long)ye - ys), (long long)xe - xs), fs = 1;
-      } else if (xs > X1) {
-        ax = X1, ay = ys + (int)rdiv64(((long long)X1 - xs) * ((long long)ye - ys), (long long)xe - xs);
+      if (right) {
+        ax = clip_l ? X0 : xs, ay = clip_l ? y_left : ys, fs = clip_l;
+        bx = clip_r ? X1 : xe, by = clip_r ? y_right : ye;
       } else {
-        ax = xs, ay = ys;
+        ax = clip_r ? X1 : xs, ay = clip_r ? y_right : ys;
+        bx = clip_l ? X0 : xe, by = clip_l ? y_left : ye, fe = clip_l;
       }
-      if (xe < X0) {
-        bx = X0, by = ys + (int)rdiv64(((long long)X0 - xs) * ((long long)ye - ys), (long long)xe - xs), fe = 1;
-      } else if (xe > X1) {
-        bx = X1, by = ys + (int)rdiv64(((long long)X1 - xs) * ((long long)ye - ys), (long long)xe - xs);
-      } else {
-        bx = xe, by = ye;
-      }
+      y_left = y_right;
       if (ay == by && !fs && !fe) continue;
-      uint32_t slot = row_base + (uint32_t)(t - bx0);
+      const uint32_t slot = row_base + (uint32_t)(t - bx0);
       if (MODE == 0) {
         atomicAdd(&a.slot_count[slot], 1u);
       } else {
@@ -548,11 +687,38 @@ __global__ void k_bin(RenderArgs a) {
     PathRec rec = a.path_rec[pid];
     int bw = rec.wh & 0xffff, bh = rec.wh >> 16;
     if (bw == 0) continue;
-    bin_edge<MODE>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, a.path_slot_off[pid]);
+    bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
+    if (small)
+      bin_edge<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, a.path_slot_off[pid]);
+    else
+      bin_edge<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, a.path_slot_off[pid]);
   }
 }
 
-// prefix sum of the backdrop deltas along each tile row of each path grid: one warp per path, lanes over rows
+// Prefix sum of the backdrop deltas along each tile row of each path grid.  Grids of up to kBackdropSmall slots:
+// one warp per path, a segmented (per row) scan over the flat grid, 32 slots per step, coalesced.  Larger grids:
+// one block per path, warps over rows (second kernel), so that a full-screen path is not a serial tail.
+constexpr int kBackdropSmall = 1024;
+
+__device__ __forceinline__ void backdrop_rows(int32_t *p, int bw, int row_begin, int row_end, int row_step, uint32_t lane) {
+  for (int row = row_begin; row < row_end; row += row_step) {
+    int32_t *q = p + row * bw;
+    int carry = 0;
+    for (int x0 = 0; x0 < bw; x0 += 32) {
+      int x = x0 + (int)lane;
+      int v = x < bw ? q[x] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += t;
+      }
+      v += carry;
+      if (x < bw) q[x] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+}
+
 __global__ void k_backdrop(RenderArgs a) {
   if (a.totals->overflow) return;
   uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -560,16 +726,37 @@ __global__ void k_backdrop(RenderArgs a) {
   for (uint32_t pid = warp; pid < a.n_paths; pid += nwarps) {
     uint32_t wh = a.path_rec[pid].wh;
     int bw = wh & 0xffff, bh = wh >> 16;
-    if (bw <= 1) continue;
-    uint32_t base = a.path_slot_off[pid];
-    for (int row = lane; row < bh; row += 32) {
-      int32_t *p = a.slot_backdrop + base + (uint32_t)row * bw;
-      int run = 0;
-      for (int x = 0; x < bw; x++) {
-        run += p[x];
-        p[x] = run;
+    const int n = bw * bh;
+    if (bw <= 1 || n > kBackdropSmall) continue;
+    int32_t *p = a.slot_backdrop + a.path_slot_off[pid];
+    int carry = 0, carry_row = -1;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      int i = i0 + (int)lane;
+      bool ok = i < n;
+      int row = ok ? i / bw : -2;
+      int col = ok ? i - row * bw : 0;
+      int v = ok ? p[i] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o && col >= o) v += t;
       }
+      if (row == carry_row) v += carry;
+      if (ok) p[i] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+      carry_row = __shfl_sync(0xffffffffu, row, 31);
     }
+  }
+}
+
+__global__ void k_backdrop_big(RenderArgs a) {
+  if (a.totals->overflow) return;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (uint32_t pid = blockIdx.x; pid < a.n_paths; pid += gridDim.x) {
+    uint32_t wh = a.path_rec[pid].wh;
+    int bw = wh & 0xffff, bh = wh >> 16;
+    if (bw <= 1 || bw * bh <= kBackdropSmall) continue;
+    backdrop_rows(a.slot_backdrop + a.path_slot_off[pid], bw, (int)w, bh, (int)nw, lane);
   }
 }
 
@@ -772,14 +959,17 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
     if (w >= total) break;
     uint32_t frame = w / tiles, tile = w - frame * tiles;
     int ty = (int)(tile / (uint32_t)a.tiles_x), tx = (int)(tile - (uint32_t)ty * a.tiles_x);
-    uint32_t p_begin = __ldg(a.frame_path_off + frame), p_end = __ldg(a.frame_path_off + frame + 1);
+    // candidates: the paint-ordered list of this tile's (row, column group)
+    const uint32_t li = (frame * (uint32_t)a.tiles_y + (uint32_t)ty) * a.groups_x + (uint32_t)tx / kGroupTiles;
+    const uint32_t p_begin = __ldg(a.list_off + li), p_end = __ldg(a.list_off + li + 1);
 
     // ---- pass 1: the last opaque full-tile cover hides everything painted before it ----
     uint32_t start = p_begin;
     for (uint32_t hi = p_end; hi > p_begin;) {
       uint32_t lo = hi - p_begin >= 32 ? hi - 32 : p_begin;
-      uint32_t pid = lo + lane;
-      Probe pr = probe_slot(a, pid, pid < hi, tx, ty);
+      uint32_t idx = lo + lane;
+      uint32_t pid = idx < hi ? __ldg(a.list_items + idx) : 0u;
+      Probe pr = probe_slot(a, pid, idx < hi, tx, ty);
       bool cover = pr.hit && pr.o1 == pr.o0 && ((pr.info >> 8) & 1u);
       uint32_t mask = __ballot_sync(0xffffffffu, cover);
       if (mask) {
@@ -795,8 +985,9 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
     for (int i = 0; i < 8; i++) px[i] = 0;
     const int X0 = tx * kTile + half * 8, Y = ty * kTile + row;
     for (uint32_t base = start; base < p_end; base += 32) {
-      uint32_t pid = base + lane;
-      Probe pr = probe_slot(a, pid, pid < p_end, tx, ty);
+      uint32_t idx = base + lane;
+      uint32_t pid = idx < p_end ? __ldg(a.list_items + idx) : 0u;
+      Probe pr = probe_slot(a, pid, idx < p_end, tx, ty);
       uint32_t mask = __ballot_sync(0xffffffffu, pr.hit);
       while (mask) {
         int src_lane = __ffs(mask) - 1;
@@ -806,7 +997,7 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
         int bd = __shfl_sync(0xffffffffu, pr.bd, src_lane);
         uint32_t info = __shfl_sync(0xffffffffu, pr.info, src_lane);
         uint32_t color = __shfl_sync(0xffffffffu, pr.color, src_lane);
-        uint32_t cur_pid = base + src_lane;
+        uint32_t cur_pid = __shfl_sync(0xffffffffu, pid, src_lane);
         uint32_t type = info & 0xff;
         uint32_t m[8];
         if (o1 == o0) {
@@ -1012,8 +1203,19 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   scan_u32(a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
            st, launches);
+  if (a.n_paths) {
+    k_list_build<false><<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
+    launches++;
+  }
+  scan_u32(a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
+           launches);
   k_zero_slots<<<wide, T, 0, st>>>(a);
   launches++;
+  if (a.n_paths) {
+    k_list_build<true><<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
+    k_list_sort<<<(unsigned)std::min<uint32_t>(a.n_lists, kNumSM * 32), kSortThreads, 0, st>>>(a);
+    launches += 2;
+  }
   mark(3);
   if (a.n_seginst) {
     k_flatten_emit<<<grid_for(a.n_seginst), T, 0, st>>>(a);
@@ -1023,7 +1225,8 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   if (a.n_seginst) {
     k_bin<0><<<wide, T, 0, st>>>(a);
     k_backdrop<<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    launches += 2;
+    k_backdrop_big<<<kNumSM * 4, T, 0, st>>>(a);
+    launches += 3;
   }
   mark(5);
   // records: slot_count -> slot_off (separate array so counts can be reused as scatter cursors)

@@ -13,6 +13,7 @@ constexpr int kTile = 16;          // px
 constexpr int kTileFx = 4096;      // 16 px in 1/256 px
 constexpr int kMaxLenFx = 16384;   // flattened edges span at most 64 px per axis
 constexpr int kNumSM = 148;        // B200
+constexpr int kGroupTiles = 8;     // tile columns per candidate list (128 px)
 
 // One draw item after host flattening of the stage: 48 bytes.
 struct DrawItem {
@@ -53,14 +54,15 @@ struct BitmapDev {
 // Counters written by the device, read by the host after a sync.
 struct Totals {
   uint32_t n_edges, n_slots, n_records;
-  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records
+  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work;      // fine-kernel tile queue
-  uint32_t pad[2];
+  uint32_t n_list;    // candidate-list entries
+  uint32_t pad;
 };
 
 struct Caps {
-  uint32_t edges, slots, records;
+  uint32_t edges, slots, records, list;
 };
 
 // Everything a render launch needs (device pointers unless noted).
@@ -89,6 +91,12 @@ struct RenderArgs {
   unsigned long long *records;  // caps.records
   uint32_t *frames;         // n_frames * width * height
   uint32_t *scan_tmp;       // >= 4096 words
+  // candidate lists: for every (frame, tile row, group of kGroupTiles tile columns) the path instances whose
+  // tile bbox overlaps it, in paint order
+  uint32_t groups_x, n_lists;  // host-known: n_lists = n_frames * tiles_y * groups_x
+  uint32_t *list_off;          // n_lists + 1 (counts, then exclusive scan)
+  uint32_t *list_cursor;       // n_lists
+  uint32_t *list_items;        // caps.list
   Totals *totals;
   Caps caps;
 };

@@ -116,8 +116,8 @@ struct swfr_renderer {
 
   // ---- working memory ----
   DevBuf seg_edge_off, path_bbox, path_rec, paint_inst, path_slot_off, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch;
-  Caps caps{0, 0, 0};
+      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_cursor, list_items;
+  Caps caps{0, 0, 0, 0};
   PinnedBuf pin_items, pin_off, pin_totals;
   swfr_batch scratch_batch;  // used by swfr_render / swfr_render_batch
 
@@ -296,6 +296,13 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   want.edges = std::max<uint32_t>(want.edges, std::max<uint32_t>(1u << 16, max_seg * 4));
   want.slots = std::max<uint32_t>(want.slots, std::max<uint32_t>(1u << 16, max_paths * 32));
   want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
+  want.list = std::max<uint32_t>(want.list, std::max<uint32_t>(1u << 16, max_paths * 12));
+  uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
+  size_t max_lists = (size_t)std::max<uint32_t>(1, r->frames_per_pass) * r->tiles_y * groups_x;
+  for (const Pass &p : b.passes) max_lists = std::max(max_lists, (size_t)p.n_frames * r->tiles_y * groups_x);
+  CK(r->list_off.reserve((max_lists + 1) * 4 + 256));
+  CK(r->list_cursor.reserve((max_lists + 1) * 4 + 256));
+  CK(r->list_items.reserve((size_t)want.list * 4));
   CK(r->edges.reserve((size_t)want.edges * 16));
   CK(r->edge_pid.reserve((size_t)want.edges * 4));
   CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
@@ -338,6 +345,11 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.records = r->records.as<unsigned long long>();
   a.frames = r->frames.as<uint32_t>() + (size_t)p.f0 * r->width * r->height;
   a.scan_tmp = r->scan_tmp.as<uint32_t>();
+  a.groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
+  a.n_lists = p.n_frames * r->tiles_y * a.groups_x;
+  a.list_off = r->list_off.as<uint32_t>();
+  a.list_cursor = r->list_cursor.as<uint32_t>();
+  a.list_items = r->list_items.as<uint32_t>();
   a.totals = r->totals.as<Totals>() + pass_index;
   a.caps = r->caps;
   return a;
@@ -394,6 +406,8 @@ int finish(swfr_renderer *r) {
       if (t.overflow & 1u) want.edges = std::max(want.edges, grow(t.n_edges));
       if (t.overflow & 2u) want.slots = std::max(want.slots, grow(t.n_slots));
       if (t.overflow & 4u) want.records = std::max(want.records, grow(t.n_records));
+      if (t.overflow & 8u) want.list = std::max(want.list, grow(t.n_list));
+      CK(r->list_items.reserve((size_t)want.list * 4));
       if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
       CK(r->edges.reserve((size_t)want.edges * 16));
       CK(r->edge_pid.reserve((size_t)want.edges * 4));
