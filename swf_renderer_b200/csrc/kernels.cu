@@ -153,9 +153,19 @@ __device__ __forceinline__ uint32_t find_owner(const uint32_t *__restrict__ off,
   return lo;
 }
 
+// find_owner for consecutive j across a warp: one (uniform, broadcast) binary search for the first active lane,
+// then a short linear walk per lane.
+__device__ __forceinline__ uint32_t find_owner_warp(const uint32_t *__restrict__ off, uint32_t n, uint32_t j) {
+  unsigned mask = __activemask();
+  uint32_t j0 = __shfl_sync(mask, j, __ffs(mask) - 1);
+  uint32_t it = find_owner(off, n, j0);
+  while (it + 1 < n && __ldg(off + it + 1) <= j) it++;
+  return it;
+}
+
 // Fixed-point control points of segment instance j.
 __device__ void load_segment(const RenderArgs &a, uint32_t j, int p[6], bool &curve, uint32_t &pid) {
-  uint32_t it = find_owner(a.item_seg_off, a.n_items, j);
+  uint32_t it = find_owner_warp(a.item_seg_off, a.n_items, j);
   uint32_t local = j - __ldg(a.item_seg_off + it);
   const DrawItem &item = a.items[it];
   float m[6];
@@ -197,6 +207,7 @@ __global__ void k_init(RenderArgs a) {
     a.totals->error = 0;
     a.totals->work = 0;
     a.totals->n_list = 0;
+    a.totals->n_big = 0;
   }
   for (uint32_t l = i; l < a.n_lists; l += stride) {
     a.list_off[l] = 0;
@@ -274,8 +285,8 @@ __device__ __forceinline__ uint32_t block_reduce(uint32_t v, uint32_t *sh) {
   return t;
 }
 
-// n = n_ptr ? min(*n_ptr, n_cap) : n_cap
-__global__ void k_scan_partials(const uint32_t *__restrict__ data, const uint32_t *n_ptr, uint32_t n_cap,
+// n = n_ptr ? min(*n_ptr, n_cap) : n_cap.  src and dst may alias (in-place scan).
+__global__ void k_scan_partials(const uint32_t *__restrict__ src, const uint32_t *n_ptr, uint32_t n_cap,
                                 uint32_t *partials) {
   __shared__ uint32_t sh[32];
   uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
@@ -283,71 +294,98 @@ __global__ void k_scan_partials(const uint32_t *__restrict__ data, const uint32_
   uint64_t begin = (uint64_t)blockIdx.x * chunk;
   uint64_t end = min((uint64_t)n, begin + chunk);
   uint32_t s = 0;
-  for (uint64_t i = begin + threadIdx.x; i < end; i += blockDim.x) s += data[i];
+  for (uint64_t i = begin + threadIdx.x; i < end; i += blockDim.x) s += src[i];
   s = block_reduce(s, sh);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
-// Scans the block partials; stores the grand total at data[n] and *total_out; raises overflow_bit when the
-// total exceeds total_cap.
-__global__ void k_scan_spine(uint32_t *partials, uint32_t *data, const uint32_t *n_ptr, uint32_t n_cap,
-                             uint32_t *total_out, uint32_t total_cap, uint32_t *overflow, uint32_t overflow_bit) {
-  __shared__ uint32_t sh[kScanBlocks];
-  uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
-  for (int i = threadIdx.x; i < kScanBlocks; i += blockDim.x) sh[i] = partials[i];
+// exclusive block scan of one value per thread (blockDim.x <= 1024); returns the exclusive prefix, *total = sum
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *sh, uint32_t *total) {
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < kScanBlocks; i++) {
-      uint32_t v = sh[i];
-      sh[i] = run;
-      run += v;
-    }
-    data[n] = run;
-    if (total_out) *total_out = run;
-    if (overflow && run > total_cap) atomicOr(overflow, overflow_bit);
+  uint32_t wbase = 0, tot = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+    uint32_t x = sh[w];
+    if (w < (int)(threadIdx.x >> 5)) wbase += x;
+    tot += x;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kScanBlocks; i += blockDim.x) partials[i] = sh[i];
+  *total = tot;
+  return wbase + inc - v;
 }
 
-__global__ void k_scan_apply(uint32_t *data, const uint32_t *n_ptr, uint32_t n_cap, const uint32_t *partials) {
+// Scans the block partials (one thread each); stores the grand total at dst[n] and *total_out; raises
+// overflow_bit when the total exceeds total_cap.
+__global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *partials, uint32_t *dst, const uint32_t *n_ptr,
+                                                    uint32_t n_cap, uint32_t *total_out, uint32_t total_cap,
+                                                    uint32_t *overflow, uint32_t overflow_bit) {
   __shared__ uint32_t sh[32];
-  __shared__ uint32_t carry_sh;
+  uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
+  uint32_t v = threadIdx.x < (uint32_t)kScanBlocks ? partials[threadIdx.x] : 0u;
+  uint32_t total;
+  uint32_t ex = block_exclusive(v, sh, &total);
+  if (threadIdx.x < (uint32_t)kScanBlocks) partials[threadIdx.x] = ex;
+  if (threadIdx.x == 0) {
+    dst[n] = total;
+    if (total_out) *total_out = total;
+    if (overflow && total > total_cap) atomicOr(overflow, overflow_bit);
+  }
+}
+
+__global__ void k_scan_apply(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, uint32_t n_cap,
+                             const uint32_t *partials) {
+  __shared__ uint32_t sh[32];
   uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
   uint32_t chunk = scan_chunk(n);
   uint64_t begin = (uint64_t)blockIdx.x * chunk;
   uint64_t end = min((uint64_t)n, begin + chunk);
-  if (threadIdx.x == 0) carry_sh = partials[blockIdx.x];
-  __syncthreads();
+  uint32_t carry = partials[blockIdx.x];
   for (uint64_t base = begin; base < end; base += kScanTile) {
     uint64_t i0 = base + (uint64_t)threadIdx.x * 4;
     uint32_t v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = (i0 + k < end) ? data[i0 + k] : 0u;
-    uint32_t tsum = v[0] + v[1] + v[2] + v[3];
-    // inclusive warp scan of thread sums
-    uint32_t inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((threadIdx.x & 31) >= o) inc += t;
-    }
-    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wbase += sh[w];
-    uint32_t tile_total = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tile_total += sh[w];
-    uint32_t ex = carry_sh + wbase + inc - tsum;
+    for (int k = 0; k < 4; k++) v[k] = (i0 + k < end) ? src[i0 + k] : 0u;
+    uint32_t tile_total;
+    uint32_t ex = carry + block_exclusive(v[0] + v[1] + v[2] + v[3], sh, &tile_total);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      if (i0 + k < end) data[i0 + k] = ex;
+      if (i0 + k < end) dst[i0 + k] = ex;
       ex += v[k];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) carry_sh += tile_total;
-    __syncthreads();
+    carry += tile_total;
+  }
+}
+
+// Whole scan in one block, for short arrays (n <= kScanSmallMax, known on the host).
+constexpr uint32_t kScanSmallMax = 16384;
+__global__ void __launch_bounds__(1024) k_scan_small(const uint32_t *src, uint32_t *dst, uint32_t n, uint32_t *total_out,
+                                                    uint32_t total_cap, uint32_t *overflow, uint32_t overflow_bit) {
+  __shared__ uint32_t sh[32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += 4096) {
+    uint32_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? src[i0 + k] : 0u;
+    uint32_t tile_total;
+    uint32_t ex = carry + block_exclusive(v[0] + v[1] + v[2] + v[3], sh, &tile_total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n) dst[i0 + k] = ex;
+      ex += v[k];
+    }
+    carry += tile_total;
+  }
+  if (threadIdx.x == 0) {
+    dst[n] = carry;
+    if (total_out) *total_out = carry;
+    if (overflow && carry > total_cap) atomicOr(overflow, overflow_bit);
   }
 }
 
@@ -473,6 +511,7 @@ __global__ void k_path_setup(RenderArgs a) {
     rec.info = dp.type | (flags << 8);
     a.path_rec[pid] = rec;
     a.path_slot_off[pid] = (uint32_t)(bw * bh);
+    if (bw > 1 && bw * bh > kBackdropSmall) a.big_list[atomicAdd(&a.totals->n_big, 1u)] = pid;
   }
 }
 
@@ -508,12 +547,48 @@ __global__ void k_list_build(RenderArgs a) {
 constexpr int kSortThreads = 128;
 constexpr int kSortSmem = 4096;
 
+constexpr int kSortWarpMax = 1024;  // lists up to this length are sorted by one warp in shared memory
+
+__global__ void __launch_bounds__(kSortThreads) k_list_sort_warp(RenderArgs a) {
+  if (a.totals->overflow) return;
+  __shared__ uint32_t sh_all[kSortThreads / 32][kSortWarpMax];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t *sh = sh_all[w];
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t l = warp; l < a.n_lists; l += nwarps) {
+    uint32_t off = a.list_off[l], n = a.list_off[l + 1] - off;
+    if (n < 2 || n > (uint32_t)kSortWarpMax) continue;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    uint32_t *g = a.list_items + off;
+    for (uint32_t i = lane; i < P; i += 32) sh[i] = i < n ? g[i] : 0xffffffffu;
+    __syncwarp();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        // P / 2 compare-exchanges per step: thread t handles the pair whose lower index has bit j clear
+        for (uint32_t t = lane; t < (P >> 1); t += 32) {
+          uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          uint32_t p = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);
+          uint32_t x = sh[i], y = sh[p];
+          if (x > y) {
+            sh[i] = y;
+            sh[p] = x;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (uint32_t i = lane; i < n; i += 32) g[i] = sh[i];
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(kSortThreads) k_list_sort(RenderArgs a) {
   if (a.totals->overflow) return;
   __shared__ uint32_t sh[kSortSmem];
   for (uint32_t l = blockIdx.x; l < a.n_lists; l += gridDim.x) {
     uint32_t off = a.list_off[l], n = a.list_off[l + 1] - off;
-    if (n < 2) continue;
+    if (n <= (uint32_t)kSortWarpMax) continue;  // short lists belong to k_list_sort_warp
     uint32_t P = 1;
     while (P < n) P <<= 1;
     uint32_t *g = a.list_items + off;
@@ -554,20 +629,6 @@ __global__ void k_zero_slots(RenderArgs a) {
     a.slot_count[i] = 0;
     a.slot_backdrop[i] = 0;
   }
-}
-
-__global__ void k_copy_counts(RenderArgs a) {
-  if (a.totals->overflow) return;
-  uint32_t n = a.totals->n_slots;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a.slot_off[i] = a.slot_count[i];
-}
-
-__global__ void k_zero_cursor(RenderArgs a) {
-  if (a.totals->overflow) return;
-  uint32_t n = a.totals->n_slots;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a.slot_count[i] = 0;
 }
 
 // ======================================================================================================
@@ -669,7 +730,9 @@ __device__ void bin_edge(const RenderArgs &a, int x0, int y0, int x1, int y1, in
       if (MODE == 0) {
         atomicAdd(&a.slot_count[slot], 1u);
       } else {
-        uint32_t pos = a.slot_off[slot] + atomicAdd(&a.slot_count[slot], 1u);
+        // the counts of pass 0 double as cursors: they run back down to zero (order inside a slot is irrelevant,
+        // coverage accumulation is integer)
+        uint32_t pos = a.slot_off[slot] + atomicSub(&a.slot_count[slot], 1u) - 1u;
         a.records[pos] = pack_record(ax - X0, ay - Yt, bx - X0, by - Yt, fs, fe);
       }
     }
@@ -698,8 +761,6 @@ __global__ void k_bin(RenderArgs a) {
 // Prefix sum of the backdrop deltas along each tile row of each path grid.  Grids of up to kBackdropSmall slots:
 // one warp per path, a segmented (per row) scan over the flat grid, 32 slots per step, coalesced.  Larger grids:
 // one block per path, warps over rows (second kernel), so that a full-screen path is not a serial tail.
-constexpr int kBackdropSmall = 1024;
-
 __device__ __forceinline__ void backdrop_rows(int32_t *p, int bw, int row_begin, int row_end, int row_step, uint32_t lane) {
   for (int row = row_begin; row < row_end; row += row_step) {
     int32_t *q = p + row * bw;
@@ -752,10 +813,11 @@ __global__ void k_backdrop(RenderArgs a) {
 __global__ void k_backdrop_big(RenderArgs a) {
   if (a.totals->overflow) return;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (uint32_t pid = blockIdx.x; pid < a.n_paths; pid += gridDim.x) {
+  const uint32_t n_big = a.totals->n_big;
+  for (uint32_t i = blockIdx.x; i < n_big; i += gridDim.x) {
+    uint32_t pid = a.big_list[i];
     uint32_t wh = a.path_rec[pid].wh;
     int bw = wh & 0xffff, bh = wh >> 16;
-    if (bw <= 1 || bw * bh <= kBackdropSmall) continue;
     backdrop_rows(a.slot_backdrop + a.path_slot_off[pid], bw, (int)w, bh, (int)nw, lane);
   }
 }
@@ -1158,11 +1220,17 @@ __global__ void k_tile_counts(RenderArgs a, uint32_t frame, uint32_t *counts) {
 // launchers
 // ======================================================================================================
 
-static void scan_u32(uint32_t *data, const uint32_t *n_ptr, uint32_t n_cap, uint32_t *tmp, uint32_t *total_out,
-                     uint32_t total_cap, uint32_t *overflow, uint32_t bit, cudaStream_t st, int &launches) {
-  k_scan_partials<<<kScanBlocks, kScanThreads, 0, st>>>(data, n_ptr, n_cap, tmp);
-  k_scan_spine<<<1, 256, 0, st>>>(tmp, data, n_ptr, n_cap, total_out, total_cap, overflow, bit);
-  k_scan_apply<<<kScanBlocks, kScanThreads, 0, st>>>(data, n_ptr, n_cap, tmp);
+static void scan_u32(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, uint32_t n_cap, uint32_t *tmp,
+                     uint32_t *total_out, uint32_t total_cap, uint32_t *overflow, uint32_t bit, cudaStream_t st,
+                     int &launches) {
+  if (!n_ptr && n_cap <= kScanSmallMax) {
+    k_scan_small<<<1, 1024, 0, st>>>(src, dst, n_cap, total_out, total_cap, overflow, bit);
+    launches += 1;
+    return;
+  }
+  k_scan_partials<<<kScanBlocks, kScanThreads, 0, st>>>(src, n_ptr, n_cap, tmp);
+  k_scan_spine<<<1, 1024, 0, st>>>(tmp, dst, n_ptr, n_cap, total_out, total_cap, overflow, bit);
+  k_scan_apply<<<kScanBlocks, kScanThreads, 0, st>>>(src, dst, n_ptr, n_cap, tmp);
   launches += 3;
 }
 
@@ -1194,27 +1262,28 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   mark(1);
   // edges: seg_edge_off (piece counts) -> exclusive offsets, total -> totals.n_edges
-  scan_u32(a.seg_edge_off, nullptr, a.n_seginst, a.scan_tmp, &a.totals->n_edges, a.caps.edges, &a.totals->overflow, 1u,
+  scan_u32(a.seg_edge_off, a.seg_edge_off, nullptr, a.n_seginst, a.scan_tmp, &a.totals->n_edges, a.caps.edges, &a.totals->overflow, 1u,
            st, launches);
   mark(2);
   if (a.n_paths) {
     k_path_setup<<<grid_for(a.n_paths), T, 0, st>>>(a);
     launches++;
   }
-  scan_u32(a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
+  scan_u32(a.path_slot_off, a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
            st, launches);
   if (a.n_paths) {
     k_list_build<false><<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
     launches++;
   }
-  scan_u32(a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
+  scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
            launches);
   k_zero_slots<<<wide, T, 0, st>>>(a);
   launches++;
   if (a.n_paths) {
     k_list_build<true><<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    k_list_sort<<<(unsigned)std::min<uint32_t>(a.n_lists, kNumSM * 32), kSortThreads, 0, st>>>(a);
-    launches += 2;
+    k_list_sort_warp<<<(unsigned)std::min<uint32_t>((a.n_lists + 3) / 4, kNumSM * 16), kSortThreads, 0, st>>>(a);
+    k_list_sort<<<(unsigned)std::min<uint32_t>(a.n_lists, kNumSM * 8), kSortThreads, 0, st>>>(a);
+    launches += 3;
   }
   mark(3);
   if (a.n_seginst) {
@@ -1230,14 +1299,8 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   mark(5);
   // records: slot_count -> slot_off (separate array so counts can be reused as scatter cursors)
-  k_copy_counts<<<wide, T, 0, st>>>(a);
-  launches++;
-  scan_u32(a.slot_off, &a.totals->n_slots, a.caps.slots, a.scan_tmp, &a.totals->n_records, a.caps.records,
+  scan_u32(a.slot_count, a.slot_off, &a.totals->n_slots, a.caps.slots, a.scan_tmp, &a.totals->n_records, a.caps.records,
            &a.totals->overflow, 4u, st, launches);
-  if (a.n_seginst) {
-    k_zero_cursor<<<wide, T, 0, st>>>(a);
-    launches++;
-  }
   mark(6);
   if (a.n_seginst) {
     k_bin<1><<<wide, T, 0, st>>>(a);

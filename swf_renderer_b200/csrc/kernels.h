@@ -14,6 +14,7 @@ constexpr int kTileFx = 4096;      // 16 px in 1/256 px
 constexpr int kMaxLenFx = 16384;   // flattened edges span at most 64 px per axis
 constexpr int kNumSM = 148;        // B200
 constexpr int kGroupTiles = 8;     // tile columns per candidate list (128 px)
+constexpr int kBackdropSmall = 1024;  // grids up to this many slots get their backdrop prefix from one warp
 
 // One draw item after host flattening of the stage: 48 bytes.
 struct DrawItem {
@@ -58,7 +59,7 @@ struct Totals {
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work;      // fine-kernel tile queue
   uint32_t n_list;    // candidate-list entries
-  uint32_t pad;
+  uint32_t n_big;     // path instances whose tile grid is larger than kBackdropSmall
 };
 
 struct Caps {
@@ -97,6 +98,7 @@ struct RenderArgs {
   uint32_t *list_off;          // n_lists + 1 (counts, then exclusive scan)
   uint32_t *list_cursor;       // n_lists
   uint32_t *list_items;        // caps.list
+  uint32_t *big_list;          // n_paths: path instances with large tile grids
   Totals *totals;
   Caps caps;
 };

@@ -99,7 +99,7 @@ struct swfr_renderer {
   uint32_t width = 0, height = 0, tiles_x = 0, tiles_y = 0;
   std::string last_error;
   bool retain_compiled = true;
-  uint32_t frames_per_pass = 4;
+  uint32_t frames_per_pass = 16;
 
   // ---- asset store (host mirrors + device copies) ----
   std::vector<SegStatic> h_static;
@@ -116,7 +116,7 @@ struct swfr_renderer {
 
   // ---- working memory ----
   DevBuf seg_edge_off, path_bbox, path_rec, paint_inst, path_slot_off, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_cursor, list_items;
+      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_cursor, list_items, big_list;
   Caps caps{0, 0, 0, 0};
   PinnedBuf pin_items, pin_off, pin_totals;
   swfr_batch scratch_batch;  // used by swfr_render / swfr_render_batch
@@ -289,6 +289,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   CK(r->path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
   CK(r->paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
   CK(r->path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
+  CK(r->big_list.reserve((size_t)max_paths * 4 + 256));
   CK(r->scan_tmp.reserve(8192 * 4));
   CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
   CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
@@ -350,6 +351,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.list_off = r->list_off.as<uint32_t>();
   a.list_cursor = r->list_cursor.as<uint32_t>();
   a.list_items = r->list_items.as<uint32_t>();
+  a.big_list = r->big_list.as<uint32_t>();
   a.totals = r->totals.as<Totals>() + pass_index;
   a.caps = r->caps;
   return a;
