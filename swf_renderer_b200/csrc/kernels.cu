@@ -153,45 +153,47 @@ __device__ __forceinline__ uint32_t find_owner(const uint32_t *__restrict__ off,
   return lo;
 }
 
-// find_owner for consecutive j across a warp: one (uniform, broadcast) binary search for the first active lane,
-// then a short linear walk per lane.
-__device__ __forceinline__ uint32_t find_owner_warp(const uint32_t *__restrict__ off, uint32_t n, uint32_t j) {
-  unsigned mask = __activemask();
-  uint32_t j0 = __shfl_sync(mask, j, __ffs(mask) - 1);
-  uint32_t it = find_owner(off, n, j0);
-  while (it + 1 < n && __ldg(off + it + 1) <= j) it++;
-  return it;
+// Fixed-point control points of segment `local` of a draw item (item fields are warp-uniform).
+struct ItemRegs {
+  float m[6];
+  uint32_t seg_first, path_off;
+  bool is_morph;
+  double ratio;
+};
+
+__device__ __forceinline__ ItemRegs load_item(const RenderArgs &a, uint32_t it) {
+  const DrawItem &item = a.items[it];
+  ItemRegs r;
+#pragma unroll
+  for (int k = 0; k < 6; k++) r.m[k] = __ldg(&item.m[k]);
+  r.seg_first = __ldg(&item.seg_first);
+  r.path_off = __ldg(&item.path_off);
+  r.is_morph = __ldg(&item.is_morph) != 0;
+  r.ratio = (double)__ldg(&item.ratio) / 65535.0;
+  return r;
 }
 
-// Fixed-point control points of segment instance j.
-__device__ void load_segment(const RenderArgs &a, uint32_t j, int p[6], bool &curve, uint32_t &pid) {
-  uint32_t it = find_owner_warp(a.item_seg_off, a.n_items, j);
-  uint32_t local = j - __ldg(a.item_seg_off + it);
-  const DrawItem &item = a.items[it];
-  float m[6];
-#pragma unroll
-  for (int k = 0; k < 6; k++) m[k] = __ldg(&item.m[k]);
-  uint32_t seg_first = __ldg(&item.seg_first);
+__device__ __forceinline__ void load_segment(const RenderArgs &a, const ItemRegs &item, uint32_t local, int p[6],
+                                             bool &curve, uint32_t &pid) {
   double c[6];
   uint32_t pf;
-  if (__ldg(&item.is_morph)) {
-    const SegMorph &s = a.segs_morph[seg_first + local];
-    double r = (double)__ldg(&item.ratio) / 65535.0;
+  if (item.is_morph) {
+    const SegMorph &s = a.segs_morph[item.seg_first + local];
 #pragma unroll
-    for (int k = 0; k < 6; k++) c[k] = lerp_ref((double)__ldg(&s.s[k]), (double)__ldg(&s.e[k]), r);
+    for (int k = 0; k < 6; k++) c[k] = lerp_ref((double)__ldg(&s.s[k]), (double)__ldg(&s.e[k]), item.ratio);
     pf = __ldg(&s.path_flags);
   } else {
-    const SegStatic &s = a.segs_static[seg_first + local];
+    const SegStatic &s = a.segs_static[item.seg_first + local];
 #pragma unroll
     for (int k = 0; k < 6; k++) c[k] = (double)__ldg(&s.p[k]);
     pf = __ldg(&s.path_flags);
   }
   curve = (pf >> 31) != 0;
-  pid = __ldg(&item.path_off) + (pf & 0x7fffffffu);
-  to_device_fx(m, c[0], c[1], p[0], p[1]);
-  to_device_fx(m, c[4], c[5], p[4], p[5]);
+  pid = item.path_off + (pf & 0x7fffffffu);
+  to_device_fx(item.m, c[0], c[1], p[0], p[1]);
+  to_device_fx(item.m, c[4], c[5], p[4], p[5]);
   if (curve) {
-    to_device_fx(m, c[2], c[3], p[2], p[3]);
+    to_device_fx(item.m, c[2], c[3], p[2], p[3]);
   } else {
     p[2] = p[0];
     p[3] = p[1];
@@ -221,42 +223,65 @@ __global__ void k_init(RenderArgs a) {
   }
 }
 
+// One warp per draw item, lanes over its segments (contiguous in the segment store).
 __global__ void k_flatten_count(RenderArgs a) {
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_seginst; j += stride) {
-    int p[6];
-    bool curve;
-    uint32_t pid;
-    load_segment(a, j, p, curve, pid);
-    a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
-    int minx = min(p[0], min(p[2], p[4])), maxx = max(p[0], max(p[2], p[4]));
-    int miny = min(p[1], min(p[3], p[5])), maxy = max(p[1], max(p[3], p[5]));
-    atomicMin(&a.path_bbox[4 * pid + 0], minx);
-    atomicMin(&a.path_bbox[4 * pid + 1], miny);
-    atomicMax(&a.path_bbox[4 * pid + 2], maxx);
-    atomicMax(&a.path_bbox[4 * pid + 3], maxy);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t it = warp; it < a.n_items; it += nwarps) {
+    const uint32_t s0 = __ldg(a.item_seg_off + it), s1 = __ldg(a.item_seg_off + it + 1);
+    if (s0 == s1) continue;
+    const ItemRegs item = load_item(a, it);
+    for (uint32_t j = s0 + lane; j < s1; j += 32) {
+      int p[6];
+      bool curve;
+      uint32_t pid;
+      load_segment(a, item, j - s0, p, curve, pid);
+      a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
+      int minx = min(p[0], min(p[2], p[4])), maxx = max(p[0], max(p[2], p[4]));
+      int miny = min(p[1], min(p[3], p[5])), maxy = max(p[1], max(p[3], p[5]));
+      // lanes working on the same path combine their bounds before touching memory
+      const unsigned active = __activemask();
+      const unsigned grp = __match_any_sync(active, pid);
+      minx = __reduce_min_sync(grp, minx);
+      miny = __reduce_min_sync(grp, miny);
+      maxx = __reduce_max_sync(grp, maxx);
+      maxy = __reduce_max_sync(grp, maxy);
+      if (lane == (uint32_t)(__ffs(grp) - 1)) {
+        atomicMin(&a.path_bbox[4 * pid + 0], minx);
+        atomicMin(&a.path_bbox[4 * pid + 1], miny);
+        atomicMax(&a.path_bbox[4 * pid + 2], maxx);
+        atomicMax(&a.path_bbox[4 * pid + 3], maxy);
+      }
+    }
   }
 }
 
+// Emits the flattened edges (16 bytes of geometry + the path instance index).
 __global__ void k_flatten_emit(RenderArgs a) {
   if (a.totals->overflow) return;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_seginst; j += stride) {
-    int p[6];
-    bool curve;
-    uint32_t pid;
-    load_segment(a, j, p, curve, pid);
-    uint32_t off = a.seg_edge_off[j];
-    int n = (int)(a.seg_edge_off[j + 1] - off);
-    int px, py;
-    piece_point(curve, p, n, 0, px, py);
-    for (int i = 1; i <= n; i++) {
-      int qx, qy;
-      piece_point(curve, p, n, i, qx, qy);
-      a.edges[off + i - 1] = make_int4(px, py, qx, qy);
-      a.edge_pid[off + i - 1] = pid;
-      px = qx;
-      py = qy;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t it = warp; it < a.n_items; it += nwarps) {
+    const uint32_t s0 = __ldg(a.item_seg_off + it), s1 = __ldg(a.item_seg_off + it + 1);
+    if (s0 == s1) continue;
+    const ItemRegs item = load_item(a, it);
+    for (uint32_t j = s0 + lane; j < s1; j += 32) {
+      int p[6];
+      bool curve;
+      uint32_t pid;
+      load_segment(a, item, j - s0, p, curve, pid);
+      const uint32_t off = a.seg_edge_off[j];
+      const int n = (int)(a.seg_edge_off[j + 1] - off);
+      int px, py;
+      piece_point(curve, p, n, 0, px, py);
+      for (int i = 1; i <= n; i++) {
+        int qx, qy;
+        piece_point(curve, p, n, i, qx, qy);
+        a.edges[off + i - 1] = make_int4(px, py, qx, qy);
+        a.edge_pid[off + i - 1] = pid;
+        px = qx;
+        py = qy;
+      }
     }
   }
 }
@@ -745,16 +770,17 @@ __global__ void k_bin(RenderArgs a) {
   uint32_t n = a.totals->n_edges;
   uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-    int4 ed = a.edges[e];
-    uint32_t pid = a.edge_pid[e];
-    PathRec rec = a.path_rec[pid];
-    int bw = rec.wh & 0xffff, bh = rec.wh >> 16;
+    const int4 ed = a.edges[e];
+    const uint32_t pid = a.edge_pid[e];
+    const PathRec rec = a.path_rec[pid];
+    const int bw = rec.wh & 0xffff, bh = rec.wh >> 16;
     if (bw == 0) continue;
-    bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
+    const uint32_t slot_base = a.path_slot_off[pid];
+    const bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
     if (small)
-      bin_edge<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, a.path_slot_off[pid]);
+      bin_edge<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, slot_base);
     else
-      bin_edge<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, a.path_slot_off[pid]);
+      bin_edge<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, slot_base);
   }
 }
 
@@ -1257,7 +1283,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   k_init<<<grid_for(a.n_paths), T, 0, st>>>(a);
   launches++;
   if (a.n_seginst) {
-    k_flatten_count<<<grid_for(a.n_seginst), T, 0, st>>>(a);
+    k_flatten_count<<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
     launches++;
   }
   mark(1);
@@ -1287,7 +1313,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   mark(3);
   if (a.n_seginst) {
-    k_flatten_emit<<<grid_for(a.n_seginst), T, 0, st>>>(a);
+    k_flatten_emit<<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
     launches++;
   }
   mark(4);

@@ -85,7 +85,7 @@ struct RenderArgs {
   PaintInst *paint_inst;    // n_paths
   uint32_t *path_slot_off;  // n_paths + 1
   int4 *edges;              // caps.edges
-  uint32_t *edge_pid;       // caps.edges
+  uint32_t *edge_pid;       // caps.edges: path instance of each edge
   uint32_t *slot_count;     // caps.slots (+1)
   int32_t *slot_backdrop;   // caps.slots
   uint32_t *slot_off;       // caps.slots + 1
