@@ -180,8 +180,8 @@ const char *swfr_status_string(int status);
 uint32_t swfr_abi_version(void);
 
 /* Options: SWFR_OPT_RETAIN_COMPILED (default 1) keeps the compiled paths of every definition on the host for
- * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 4) bounds how many frames
- * share one set of launches and one working set. */
+ * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 16) bounds how many frames
+ * share one set of launches and one working set; SWFR_OPT_PROFILE = 1 records CUDA events at stage boundaries. */
 typedef enum swfr_option { SWFR_OPT_RETAIN_COMPILED = 1, SWFR_OPT_FRAMES_PER_PASS = 2, SWFR_OPT_PROFILE = 3 } swfr_option;
 int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value);
 
