@@ -256,32 +256,38 @@ __global__ void k_flatten_count(RenderArgs a) {
   }
 }
 
-// Emits the flattened edges (16 bytes of geometry + the path instance index).
+// find_owner for consecutive j across a warp: one (uniform, broadcast) binary search for the first active lane,
+// then a short linear walk per lane.
+__device__ __forceinline__ uint32_t find_owner_warp(const uint32_t *__restrict__ off, uint32_t n, uint32_t j) {
+  unsigned mask = __activemask();
+  uint32_t j0 = __shfl_sync(mask, j, __ffs(mask) - 1);
+  uint32_t it = find_owner(off, n, j0);
+  while (it + 1 < n && __ldg(off + it + 1) <= j) it++;
+  return it;
+}
+
+// Emits the flattened edges (16 bytes of geometry + the path instance index): one thread per segment instance.
 __global__ void k_flatten_emit(RenderArgs a) {
   if (a.totals->overflow) return;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t it = warp; it < a.n_items; it += nwarps) {
-    const uint32_t s0 = __ldg(a.item_seg_off + it), s1 = __ldg(a.item_seg_off + it + 1);
-    if (s0 == s1) continue;
+  uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_seginst; j += stride) {
+    const uint32_t it = find_owner_warp(a.item_seg_off, a.n_items, j);
     const ItemRegs item = load_item(a, it);
-    for (uint32_t j = s0 + lane; j < s1; j += 32) {
-      int p[6];
-      bool curve;
-      uint32_t pid;
-      load_segment(a, item, j - s0, p, curve, pid);
-      const uint32_t off = a.seg_edge_off[j];
-      const int n = (int)(a.seg_edge_off[j + 1] - off);
-      int px, py;
-      piece_point(curve, p, n, 0, px, py);
-      for (int i = 1; i <= n; i++) {
-        int qx, qy;
-        piece_point(curve, p, n, i, qx, qy);
-        a.edges[off + i - 1] = make_int4(px, py, qx, qy);
-        a.edge_pid[off + i - 1] = pid;
-        px = qx;
-        py = qy;
-      }
+    int p[6];
+    bool curve;
+    uint32_t pid;
+    load_segment(a, item, j - __ldg(a.item_seg_off + it), p, curve, pid);
+    const uint32_t off = a.seg_edge_off[j];
+    const int n = (int)(a.seg_edge_off[j + 1] - off);
+    int px, py;
+    piece_point(curve, p, n, 0, px, py);
+    for (int i = 1; i <= n; i++) {
+      int qx, qy;
+      piece_point(curve, p, n, i, qx, qy);
+      a.edges[off + i - 1] = make_int4(px, py, qx, qy);
+      a.edge_pid[off + i - 1] = pid;
+      px = qx;
+      py = qy;
     }
   }
 }
@@ -1313,7 +1319,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   mark(3);
   if (a.n_seginst) {
-    k_flatten_emit<<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
+    k_flatten_emit<<<grid_for(a.n_seginst), T, 0, st>>>(a);
     launches++;
   }
   mark(4);

@@ -133,6 +133,15 @@ struct swfr_renderer {
   size_t prof_passes = 0;
   float stage_ms[kNumStages] = {0};
   uint32_t stage_launches = 0;
+  // readback overlapped with rendering: one event per pass, copies on their own stream
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> pass_done;
+  bool copy_pending = false;
+  struct CopyReq {
+    uint32_t first, count;
+    uint8_t *dst;
+  };
+  std::vector<CopyReq> copy_reqs;  // since the last launch (re-issued if a pass had to be re-run)
 };
 
 namespace {
@@ -377,9 +386,17 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
     }
     r->prof_passes = b.passes.size();
   }
-  for (size_t i = 0; i < b.passes.size(); i++)
+  while (r->pass_done.size() < b.passes.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    r->pass_done.push_back(e);
+  }
+  r->copy_reqs.clear();
+  for (size_t i = 0; i < b.passes.size(); i++) {
     launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream,
                                         r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr);
+    CK(cudaEventRecord(r->pass_done[i], r->stream));
+  }
   CK(cudaGetLastError());
   r->last = &b;
   r->arena_pass = b.passes.empty() ? 0 : b.passes.size() - 1;
@@ -398,6 +415,11 @@ int finish(swfr_renderer *r) {
   r->last_totals.assign(np, Totals{});
   CK(cudaMemcpyAsync(r->last_totals.data(), r->totals.p, np * sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
   CK(cudaStreamSynchronize(r->stream));
+  if (r->copy_pending) {
+    CK(cudaStreamSynchronize(r->copy_stream));
+    r->copy_pending = false;
+  }
+  bool rerun = false;
   for (size_t i = 0; i < np; i++) {
     int guard = 0;
     while (r->last_totals[i].overflow) {
@@ -420,12 +442,20 @@ int finish(swfr_renderer *r) {
       r->caps = want;
       r->stats.retries++;
       r->arena_pass = i;
+      rerun = true;
       r->stats.kernel_launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
       CK(cudaMemcpyAsync(&r->last_totals[i], r->totals.as<Totals>() + i, sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
       CK(cudaStreamSynchronize(r->stream));
     }
   }
   r->pending = false;
+  if (rerun) {  // frames copied out before the re-run were incomplete: copy them again
+    size_t fb = (size_t)r->width * r->height * 4;
+    for (const swfr_renderer::CopyReq &q : r->copy_reqs)
+      CK(cudaMemcpyAsync(q.dst, (const char *)r->frames.p + (size_t)q.first * fb, (size_t)q.count * fb,
+                         cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+  }
   if (r->prof_passes) {
     for (int k = 0; k < kNumStages; k++) r->stage_ms[k] = 0.f;
     for (size_t i = 0; i < r->prof_passes; i++) {
@@ -562,6 +592,12 @@ void swfr_destroy(swfr_renderer *r) {
     if (b.tex) cudaDestroyTextureObject(b.tex);
     if (b.arr) cudaFreeArray(b.arr);
   }
+  if (r->copy_stream) {
+    cudaStreamSynchronize(r->copy_stream);
+    cudaStreamDestroy(r->copy_stream);
+  }
+  for (cudaEvent_t e : r->pass_done) cudaEventDestroy(e);
+  for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
   if (r->own_stream) cudaStreamDestroy(r->stream);
   delete r;
 }
@@ -760,8 +796,25 @@ int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uin
   if (!dst || first + count > r->frames_rendered) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad frame range");
   cudaSetDevice(r->device);
   size_t fb = (size_t)r->width * r->height * 4;
-  CK(cudaMemcpyAsync(dst, (const char *)r->frames.p + (size_t)first * fb, (size_t)count * fb, cudaMemcpyDeviceToHost,
-                     r->stream));
+  if (!r->pending || !r->last) {
+    CK(cudaMemcpyAsync(dst, (const char *)r->frames.p + (size_t)first * fb, (size_t)count * fb, cudaMemcpyDeviceToHost,
+                       r->stream));
+    return SWFR_OK;
+  }
+  // the render is still in flight: copy each pass' frames as soon as that pass is done, on the copy stream, so the
+  // transfer overlaps the passes that follow
+  if (!r->copy_stream) CK(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+  const swfr_batch &b = *r->last;
+  for (size_t i = 0; i < b.passes.size(); i++) {
+    const Pass &p = b.passes[i];
+    uint32_t lo = std::max(first, p.f0), hi = std::min(first + count, p.f0 + p.n_frames);
+    if (lo >= hi) continue;
+    CK(cudaStreamWaitEvent(r->copy_stream, r->pass_done[i], 0));
+    CK(cudaMemcpyAsync(dst + (size_t)(lo - first) * fb, (const char *)r->frames.p + (size_t)lo * fb, (size_t)(hi - lo) * fb,
+                       cudaMemcpyDeviceToHost, r->copy_stream));
+  }
+  r->copy_pending = true;
+  r->copy_reqs.push_back(swfr_renderer::CopyReq{first, count, dst});
   return SWFR_OK;
 }
 
