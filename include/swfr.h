@@ -181,8 +181,14 @@ uint32_t swfr_abi_version(void);
 
 /* Options: SWFR_OPT_RETAIN_COMPILED (default 1) keeps the compiled paths of every definition on the host for
  * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 16) bounds how many frames
- * share one set of launches and one working set; SWFR_OPT_PROFILE = 1 records CUDA events at stage boundaries. */
-typedef enum swfr_option { SWFR_OPT_RETAIN_COMPILED = 1, SWFR_OPT_FRAMES_PER_PASS = 2, SWFR_OPT_PROFILE = 3 } swfr_option;
+ * share one set of launches and one working set; SWFR_OPT_PROFILE = 1 records CUDA events at stage boundaries;
+ * SWFR_OPT_HOST_THREADS = threads that flatten stages into draw items (0 = default: min(8, hardware threads)). */
+typedef enum swfr_option {
+  SWFR_OPT_RETAIN_COMPILED = 1,
+  SWFR_OPT_FRAMES_PER_PASS = 2,
+  SWFR_OPT_PROFILE = 3,
+  SWFR_OPT_HOST_THREADS = 4
+} swfr_option;
 int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value);
 
 /* ---- asset store ------------------------------------------------------------------------------------ */
@@ -201,7 +207,10 @@ int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t
 
 /* Renders one stage into frame 0.  Asynchronous on the renderer's stream. */
 int swfr_render(swfr_renderer *r, const swfr_stage *stage);
-/* Renders n stages into frames 0..n-1 with one set of launches. */
+/* Renders n stages into frames 0..n-1 with one set of launches per SWFR_OPT_FRAMES_PER_PASS frames.  Asynchronous:
+ * the call flattens the stages on the host and uploads them while the PREVIOUS render (if still in flight) runs,
+ * then waits for that render and enqueues this one - so a caller that streams batches (render k, read k async,
+ * render k+1, ...) keeps the host flattening, both PCIe directions and the GPU busy at the same time. */
 int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n);
 
 /* Stages kept resident in HBM, for repeated rendering without host traffic. */
@@ -216,7 +225,10 @@ int swfr_sync(swfr_renderer *r);
  * PNG-export rounding of the reference test (c = (c*255 + a/2) / a).  Synchronises the stream. */
 int swfr_read_image(swfr_renderer *r, uint32_t frame, uint8_t *dst, size_t stride, int premultiplied);
 /* Copies frames [first, first+count) premultiplied and tightly packed (width*height*4 bytes each) into pinned
- * or pageable host memory without synchronising; pair with swfr_sync. */
+ * or pageable host memory without synchronising.  While the render is in flight each pass' frames are copied on a
+ * separate copy stream as soon as that pass is done, overlapping the passes that follow and - if the caller goes on
+ * to the next swfr_render_batch - the start of the next render (which waits before overwriting a frame still being
+ * copied).  `dst` is valid after swfr_sync(). */
 int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uint8_t *dst);
 /* Device pointer of frame 0 of the last render (premultiplied RGBA8, frames width*height*4 bytes apart). */
 int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n_frames);

@@ -124,18 +124,22 @@ static inline double lerp_ref(double start, double end, double r) { /* canvas-re
   return a + c;
 }
 
-/* twips -> device px -> 24.8 fixed.  m in Matrix2D order. */
+/* twips -> device px -> 24.8 fixed.  m = the canvas CTM in Matrix2D order: the reference starts every frame with
+ * ctx.scale(1 / 20, 1 / 20) (canvas-renderer.ts:74) and multiplies the shape matrix in with ctx.transform
+ * (canvas-renderer.ts:179-188), i.e. Cairo holds CTM = 0.05 * M entry by entry (ctm_from_matrix below) and transforms
+ * path points with it at path-build time: x' = xx x + xy y + x0. */
+static inline void ctm_from_matrix(const double m[6], double ctm[6]) {
+  for (int i = 0; i < 6; i++) ctm[i] = m[i] * 0.05;
+}
 static inline void to_device_fx(const double m[6], double x, double y, int32_t *fx, int32_t *fy) {
   double px = m[0] * x;
   double qx = m[3] * y;
   double sx = px + qx;
   sx = sx + m[4];
-  sx = sx / 20.0;
   double py = m[2] * x;
   double qy = m[1] * y;
   double sy = py + qy;
   sy = sy + m[5];
-  sy = sy / 20.0;
   if (!(sx > -SWFO_CLAMP_PX)) sx = -SWFO_CLAMP_PX; /* also catches NaN */
   if (sx > SWFO_CLAMP_PX) sx = SWFO_CLAMP_PX;
   if (!(sy > -SWFO_CLAMP_PX)) sy = -SWFO_CLAMP_PX;
@@ -602,8 +606,9 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
   for (int it = 0; it < sc->n_items; it++) {
     const swfo_item *item = &sc->items[it];
     const swfo_def *def = &sc->defs[item->def];
-    double m[6];
-    for (int i = 0; i < 6; i++) m[i] = (double)item->m[i];
+    double m0[6], m[6];
+    for (int i = 0; i < 6; i++) m0[i] = (double)item->m[i];
+    ctm_from_matrix(m0, m);
     double ratio = (double)item->ratio / 65535.0;
     for (int lp = 0; lp < def->n_path; lp++, path_inst++) {
       /* ---- flatten this path's segments ---- */
@@ -685,7 +690,7 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
         for (int32_t lx = 1; lx < g.bw; lx++) g.backdrop[ly * g.bw + lx] += g.backdrop[ly * g.bw + lx - 1];
       /* ---- paint ---- */
       paint_inst paint;
-      make_paint(sc, &sc->paints[def->first_path + lp], m, ratio, &paint);
+      make_paint(sc, &sc->paints[def->first_path + lp], m0, ratio, &paint);
       if (paint.valid) {
         for (int32_t ly = 0; ly < g.bh; ly++) {
           for (int32_t lx = 0; lx < g.bw; lx++) {

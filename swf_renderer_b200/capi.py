@@ -20,7 +20,7 @@ SPREAD_PAD, SPREAD_REFLECT, SPREAD_REPEAT = 0, 1, 2
 COLOR_SRGB, COLOR_LINEAR_RGB = 0, 1
 RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
 PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
-OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE = 1, 2, 3
+OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS = 1, 2, 3, 4
 
 
 class Rgba8(C.Structure):

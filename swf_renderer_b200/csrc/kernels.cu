@@ -78,17 +78,17 @@ __device__ __forceinline__ double lerp_ref(double start, double end, double r) {
   return a + c;
 }
 
-__device__ __forceinline__ void to_device_fx(const float *m, double x, double y, int &fx, int &fy) {
-  double px = (double)m[0] * x;
-  double qx = (double)m[3] * y;
+// m = the canvas CTM (Matrix2D order): 0.05 * shape matrix, entry by entry - ctx.scale(1/20, 1/20) followed by
+// ctx.transform (canvas-renderer.ts:74, 179-188); Cairo transforms path points with it at path-build time.
+__device__ __forceinline__ void to_device_fx(const double *m, double x, double y, int &fx, int &fy) {
+  double px = m[0] * x;
+  double qx = m[3] * y;
   double sx = px + qx;
-  sx = sx + (double)m[4];
-  sx = sx / 20.0;
-  double py = (double)m[2] * x;
-  double qy = (double)m[1] * y;
+  sx = sx + m[4];
+  double py = m[2] * x;
+  double qy = m[1] * y;
   double sy = py + qy;
-  sy = sy + (double)m[5];
-  sy = sy / 20.0;
+  sy = sy + m[5];
   if (!(sx > -32768.0)) sx = -32768.0;
   if (sx > 32768.0) sx = 32768.0;
   if (!(sy > -32768.0)) sy = -32768.0;
@@ -123,20 +123,36 @@ __device__ int piece_count(bool curve, const int *p) {
 // the numerator 2 num + den are exact in FP64 and the quotient cannot round across an integer (the distance of a
 // non-integer quotient to the next integer is >= 1/(2 den) >= 2^-26 while the rounding error is < 2^-27), so this
 // is the exact integer floor((2 num + den) / (2 den)), i.e. the oracle's rdiv64.
-__device__ __forceinline__ int rdiv_f64(double num, double den) {
-  return (int)floor((2.0 * num + den) / (2.0 * den));
+// The division itself is replaced by a multiplication with inv2den = 1 / (2 den) (one FP64 division per segment
+// instead of two per point): the estimate floor(N * inv2den) is off by at most one (relative error < 2^-51, quotient
+// < 2^27), and the remainder N - q * 2 den is exact in FP64 (q * 2 den < 2^53), so one correction step gives the
+// exact floor again.
+__device__ __forceinline__ int rdiv_f64(double num, double den, double inv2den) {
+  const double N = 2.0 * num + den, D = 2.0 * den;
+  double q = floor(N * inv2den);
+  const double r = N - q * D;
+  if (r < 0.0)
+    q -= 1.0;
+  else if (r >= D)
+    q += 1.0;
+  return (int)q;
 }
 
-__device__ __forceinline__ void piece_point(bool curve, const int *p, int n, int i, int &x, int &y) {
+// den = n (lines) or n^2 (curves); inv2den = 1 / (2 den)
+__device__ __forceinline__ double piece_inv2den(bool curve, int n) {
+  return curve ? 1.0 / (2.0 * ((double)n * (double)n)) : 1.0 / (2.0 * (double)n);
+}
+
+__device__ __forceinline__ void piece_point(bool curve, const int *p, int n, int i, double inv2den, int &x, int &y) {
   if (!curve) {
-    x = p[0] + rdiv_f64(((double)p[4] - (double)p[0]) * (double)i, (double)n);
-    y = p[1] + rdiv_f64(((double)p[5] - (double)p[1]) * (double)i, (double)n);
+    x = p[0] + rdiv_f64(((double)p[4] - (double)p[0]) * (double)i, (double)n, inv2den);
+    y = p[1] + rdiv_f64(((double)p[5] - (double)p[1]) * (double)i, (double)n, inv2den);
   } else {
     // all products are exact: a, b, c <= n^2 <= 2^24 and |p| <= 2^24
     double a = (double)(n - i) * (double)(n - i), b = 2.0 * (double)i * (double)(n - i), c = (double)i * (double)i,
            nn = (double)n * (double)n;
-    x = rdiv_f64(a * (double)p[0] + b * (double)p[2] + c * (double)p[4], nn);
-    y = rdiv_f64(a * (double)p[1] + b * (double)p[3] + c * (double)p[5], nn);
+    x = rdiv_f64(a * (double)p[0] + b * (double)p[2] + c * (double)p[4], nn, inv2den);
+    y = rdiv_f64(a * (double)p[1] + b * (double)p[3] + c * (double)p[5], nn, inv2den);
   }
 }
 
@@ -155,7 +171,7 @@ __device__ __forceinline__ uint32_t find_owner(const uint32_t *__restrict__ off,
 
 // Fixed-point control points of segment `local` of a draw item (item fields are warp-uniform).
 struct ItemRegs {
-  float m[6];
+  double m[6];  // canvas CTM = 0.05 * Matrix2D
   uint32_t seg_first, path_off;
   bool is_morph;
   double ratio;
@@ -165,11 +181,11 @@ __device__ __forceinline__ ItemRegs load_item(const RenderArgs &a, uint32_t it) 
   const DrawItem &item = a.items[it];
   ItemRegs r;
 #pragma unroll
-  for (int k = 0; k < 6; k++) r.m[k] = __ldg(&item.m[k]);
+  for (int k = 0; k < 6; k++) r.m[k] = (double)__ldg(&item.m[k]) * 0.05;
   r.seg_first = __ldg(&item.seg_first);
   r.path_off = __ldg(&item.path_off);
   r.is_morph = __ldg(&item.is_morph) != 0;
-  r.ratio = (double)__ldg(&item.ratio) / 65535.0;
+  r.ratio = r.is_morph ? (double)__ldg(&item.ratio) / 65535.0 : 0.0;
   return r;
 }
 
@@ -210,11 +226,9 @@ __global__ void k_init(RenderArgs a) {
     a.totals->work = 0;
     a.totals->n_list = 0;
     a.totals->n_big = 0;
+    a.totals->n_rowent = 0;
   }
-  for (uint32_t l = i; l < a.n_lists; l += stride) {
-    a.list_off[l] = 0;
-    a.list_cursor[l] = 0;
-  }
+  for (uint32_t l = i; l < a.n_frames * (uint32_t)a.tiles_y; l += stride) a.row_count[l] = 0;
   for (uint32_t p = i; p < a.n_paths; p += stride) {
     a.path_bbox[4 * p + 0] = INT_MAX;
     a.path_bbox[4 * p + 1] = INT_MAX;
@@ -237,6 +251,7 @@ __global__ void k_flatten_count(RenderArgs a) {
       uint32_t pid;
       load_segment(a, item, j - s0, p, curve, pid);
       a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
+      a.seg_item[j] = it;
       int minx = min(p[0], min(p[2], p[4])), maxx = max(p[0], max(p[2], p[4]));
       int miny = min(p[1], min(p[3], p[5])), maxy = max(p[1], max(p[3], p[5]));
       // lanes working on the same path combine their bounds before touching memory
@@ -256,39 +271,81 @@ __global__ void k_flatten_count(RenderArgs a) {
   }
 }
 
-// find_owner for consecutive j across a warp: one (uniform, broadcast) binary search for the first active lane,
-// then a short linear walk per lane.
-__device__ __forceinline__ uint32_t find_owner_warp(const uint32_t *__restrict__ off, uint32_t n, uint32_t j) {
-  unsigned mask = __activemask();
-  uint32_t j0 = __shfl_sync(mask, j, __ffs(mask) - 1);
-  uint32_t it = find_owner(off, n, j0);
-  while (it + 1 < n && __ldg(off + it + 1) <= j) it++;
-  return it;
-}
+// Emits the flattened edges (16 bytes of geometry + the path instance index).  One warp takes 32 consecutive segment
+// instances (their edges are contiguous in the output), and spreads the pieces of all of them evenly over its lanes:
+// lane k computes the END point of piece k; the start point is the neighbour lane's end point, the segment's first
+// control point, or the last point of the previous round.  Stores are coalesced 16-byte writes.
+constexpr int kEmitWarps = 8;
 
-// Emits the flattened edges (16 bytes of geometry + the path instance index): one thread per segment instance.
-__global__ void k_flatten_emit(RenderArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a) {
   if (a.totals->overflow) return;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_seginst; j += stride) {
-    const uint32_t it = find_owner_warp(a.item_seg_off, a.n_items, j);
-    const ItemRegs item = load_item(a, it);
-    int p[6];
-    bool curve;
-    uint32_t pid;
-    load_segment(a, item, j - __ldg(a.item_seg_off + it), p, curve, pid);
-    const uint32_t off = a.seg_edge_off[j];
-    const int n = (int)(a.seg_edge_off[j + 1] - off);
-    int px, py;
-    piece_point(curve, p, n, 0, px, py);
-    for (int i = 1; i <= n; i++) {
-      int qx, qy;
-      piece_point(curve, p, n, i, qx, qy);
-      a.edges[off + i - 1] = make_int4(px, py, qx, qy);
-      a.edge_pid[off + i - 1] = pid;
-      px = qx;
-      py = qy;
+  __shared__ int sh_p[kEmitWarps][32][6];
+  __shared__ double sh_inv[kEmitWarps][32];
+  __shared__ uint32_t sh_pid[kEmitWarps][32];  // path instance | curve << 31
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t stride = gridDim.x * kEmitWarps * 32;
+  for (uint32_t base = (blockIdx.x * kEmitWarps + w) * 32; base < a.n_seginst; base += stride) {
+    const uint32_t j = base + lane;
+    int n = 0;
+    uint32_t off = 0;
+    if (j < a.n_seginst) {
+      const uint32_t it = a.seg_item[j];
+      const ItemRegs item = load_item(a, it);
+      int p[6];
+      bool curve;
+      uint32_t pid;
+      load_segment(a, item, j - __ldg(a.item_seg_off + it), p, curve, pid);
+      off = a.seg_edge_off[j];
+      n = (int)(a.seg_edge_off[j + 1] - off);
+#pragma unroll
+      for (int k = 0; k < 6; k++) sh_p[w][lane][k] = p[k];
+      sh_inv[w][lane] = piece_inv2den(curve, n);
+      sh_pid[w][lane] = pid | (curve ? 0x80000000u : 0u);
     }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - n;
+    const uint32_t off0 = __shfl_sync(0xffffffffu, off, 0);  // edges of this warp's segments start here
+    __syncwarp();
+    int carry_x = 0, carry_y = 0;
+    for (int k0 = 0; k0 < total; k0 += 32) {
+      const int k = min(k0 + (int)lane, total - 1);
+      int o = 0;  // owner = the last lane whose first piece is <= k
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        int v = __shfl_sync(0xffffffffu, excl, o + step);
+        if (v <= k) o += step;
+      }
+      const int first = __shfl_sync(0xffffffffu, excl, o);
+      const int n_o = __shfl_sync(0xffffffffu, n, o);
+      const int i = k - first + 1;  // 1..n_o
+      int p[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) p[q] = sh_p[w][o][q];
+      const uint32_t pc = sh_pid[w][o];
+      int qx, qy;
+      piece_point((pc >> 31) != 0, p, n_o, i, sh_inv[w][o], qx, qy);
+      int px = __shfl_up_sync(0xffffffffu, qx, 1), py = __shfl_up_sync(0xffffffffu, qy, 1);
+      if (i == 1) {
+        px = p[0];
+        py = p[1];
+      } else if (lane == 0) {
+        px = carry_x;
+        py = carry_y;
+      }
+      carry_x = __shfl_sync(0xffffffffu, qx, 31);
+      carry_y = __shfl_sync(0xffffffffu, qy, 31);
+      if (k0 + (int)lane < total) {
+        a.edges[off0 + (uint32_t)k] = make_int4(px, py, qx, qy);
+        a.edge_pid[off0 + (uint32_t)k] = pc & 0x7fffffffu;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -522,6 +579,8 @@ __global__ void k_path_setup(RenderArgs a) {
             if (dy < 1.0 / 0.75) dy = 1.0;
             pi.rx = (float)dx;
             pi.ry = (float)dy;
+            pi.focal = 1.0f / pi.rx;  // bitmaps: focal / omf carry 1 / rx, 1 / ry
+            pi.omf = 1.0f / pi.ry;
             if (bm.opaque && dp.repeating) flags |= 1u;
           }
         } else {
@@ -543,112 +602,93 @@ __global__ void k_path_setup(RenderArgs a) {
     a.path_rec[pid] = rec;
     a.path_slot_off[pid] = (uint32_t)(bw * bh);
     if (bw > 1 && bw * bh > kBackdropSmall) a.big_list[atomicAdd(&a.totals->n_big, 1u)] = pid;
-  }
-}
-
-// Candidate lists: one entry per (tile row, column group) a path's bbox overlaps.  One warp per path instance,
-// lanes over its (row, group) cells.  FILL = false counts, FILL = true appends (unordered; sorted afterwards).
-template <bool FILL>
-__global__ void k_list_build(RenderArgs a) {
-  if (FILL && a.totals->overflow) return;
-  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t pid = warp; pid < a.n_paths; pid += nwarps) {
-    PathRec rec = a.path_rec[pid];
-    int bx0 = rec.xy0 & 0xffff, by0 = rec.xy0 >> 16, bw = rec.wh & 0xffff, bh = rec.wh >> 16;
-    if (bw == 0) continue;
-    uint32_t frame = a.items[find_owner(a.item_path_off, a.n_items, pid)].frame;
-    uint32_t g0 = (uint32_t)bx0 / kGroupTiles, ng = (uint32_t)(bx0 + bw - 1) / kGroupTiles - g0 + 1;
-    uint32_t cells = ng * (uint32_t)bh;
-    for (uint32_t c = lane; c < cells; c += 32) {
-      uint32_t y = c / ng, g = c - y * ng;
-      uint32_t l = (frame * (uint32_t)a.tiles_y + (uint32_t)by0 + y) * a.groups_x + g0 + g;
-      if (FILL) {
-        uint32_t pos = a.list_off[l] + atomicAdd(&a.list_cursor[l], 1u);
-        a.list_items[pos] = pid;
-      } else {
-        atomicAdd(&a.list_off[l], 1u);
-      }
+    // candidate lists, step 0: how many path instances touch each tile row of the frame
+    if (bw > 0) {
+      uint32_t *rc = a.row_count + item.frame * (uint32_t)a.tiles_y + (uint32_t)by0;
+      for (int y = 0; y < bh; y++) atomicAdd(rc + y, 1u);
     }
   }
 }
 
-// ... step 3: each list is sorted ascending, i.e. back into paint order (bitonic network without direction bits;
-// entries past the end behave as +inf).  One block per list; lists of up to kSortSmem entries sort in shared memory.
-constexpr int kSortThreads = 128;
-constexpr int kSortSmem = 4096;
+// Candidate lists: for every (frame, tile row, group of kGroupTiles tile columns) the path instances whose tile bbox
+// overlaps it, IN PAINT ORDER.  Built without atomics on the data path and without sorting, by two ordered
+// compactions (ballot + popc prefix):
+//   k_row_lists   - one block per (frame, tile row) sweeps the frame's path instances in order and keeps those whose
+//                   bbox covers the row, as (path instance, tile x-range); it also counts entries per column group;
+//   k_group_lists - one warp per (frame, row, group) sweeps that row list in order and keeps the overlapping ones.
+constexpr int kRowThreads = 256;
+constexpr int kMaxGroups = 512;  // tile columns <= 4096: frames up to 65536 px wide
 
-constexpr int kSortWarpMax = 1024;  // lists up to this length are sorted by one warp in shared memory
-
-__global__ void __launch_bounds__(kSortThreads) k_list_sort_warp(RenderArgs a) {
+__global__ void __launch_bounds__(kRowThreads) k_row_lists(RenderArgs a) {
   if (a.totals->overflow) return;
-  __shared__ uint32_t sh_all[kSortThreads / 32][kSortWarpMax];
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t *sh = sh_all[w];
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  __shared__ uint32_t sh_warp[kRowThreads / 32];
+  __shared__ uint32_t sh_grp[kMaxGroups];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t n_rows = a.n_frames * (uint32_t)a.tiles_y;
+  for (uint32_t rl = blockIdx.x; rl < n_rows; rl += gridDim.x) {
+    const uint32_t frame = rl / (uint32_t)a.tiles_y;
+    const int row = (int)(rl - frame * (uint32_t)a.tiles_y);
+    const uint32_t p0 = a.frame_path_off[frame], p1 = a.frame_path_off[frame + 1];
+    for (uint32_t g = tid; g < a.groups_x; g += kRowThreads) sh_grp[g] = 0;
+    __syncthreads();
+    uint32_t out = a.row_off[rl];
+    for (uint32_t base = p0; base < p1; base += kRowThreads) {
+      const uint32_t pid = base + tid;
+      bool hit = false;
+      uint32_t xr = 0;
+      if (pid < p1) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));  // xy0, wh
+        const int by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
+        hit = bw > 0 && row >= by0 && row < by0 + bh;
+        xr = (r.x & 0xffffu) | ((uint32_t)bw << 16);
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) sh_warp[w] = __popc(mask);
+      __syncthreads();
+      uint32_t wbase = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < kRowThreads / 32; k++) {
+        const uint32_t c = sh_warp[k];
+        if (k < (int)w) wbase += c;
+        tot += c;
+      }
+      if (hit) {
+        a.row_items[out + wbase + __popc(mask & ((1u << lane) - 1u))] = make_uint2(pid, xr);
+        const uint32_t bx0 = xr & 0xffffu, bw = xr >> 16;
+        const uint32_t g0 = bx0 / kGroupTiles, g1 = (bx0 + bw - 1) / kGroupTiles;
+        for (uint32_t g = g0; g <= g1; g++) atomicAdd(&sh_grp[g], 1u);
+      }
+      out += tot;
+      __syncthreads();
+    }
+    for (uint32_t g = tid; g < a.groups_x; g += kRowThreads) a.list_off[rl * a.groups_x + g] = sh_grp[g];
+    __syncthreads();
+  }
+}
+
+__global__ void k_group_lists(RenderArgs a) {
+  if (a.totals->overflow) return;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t l = warp; l < a.n_lists; l += nwarps) {
-    uint32_t off = a.list_off[l], n = a.list_off[l + 1] - off;
-    if (n < 2 || n > (uint32_t)kSortWarpMax) continue;
-    uint32_t P = 1;
-    while (P < n) P <<= 1;
-    uint32_t *g = a.list_items + off;
-    for (uint32_t i = lane; i < P; i += 32) sh[i] = i < n ? g[i] : 0xffffffffu;
-    __syncwarp();
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        // P / 2 compare-exchanges per step: thread t handles the pair whose lower index has bit j clear
-        for (uint32_t t = lane; t < (P >> 1); t += 32) {
-          uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          uint32_t p = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);
-          uint32_t x = sh[i], y = sh[p];
-          if (x > y) {
-            sh[i] = y;
-            sh[p] = x;
-          }
-        }
-        __syncwarp();
+    const uint32_t rl = l / a.groups_x, g = l - rl * a.groups_x;
+    const uint32_t r0 = a.row_off[rl], r1 = a.row_off[rl + 1];
+    uint32_t out = a.list_off[l];
+    const uint32_t gx0 = g * kGroupTiles, gx1 = gx0 + kGroupTiles;
+    for (uint32_t base = r0; base < r1; base += 32) {
+      const uint32_t i = base + lane;
+      bool hit = false;
+      uint32_t pid = 0;
+      if (i < r1) {
+        const uint2 e = __ldg(a.row_items + i);
+        const uint32_t bx0 = e.y & 0xffffu, bw = e.y >> 16;
+        hit = bx0 < gx1 && bx0 + bw > gx0;
+        pid = e.x;
       }
+      const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      if (hit) a.list_items[out + __popc(mask & ((1u << lane) - 1u))] = pid;
+      out += __popc(mask);
     }
-    for (uint32_t i = lane; i < n; i += 32) g[i] = sh[i];
-    __syncwarp();
-  }
-}
-
-__global__ void __launch_bounds__(kSortThreads) k_list_sort(RenderArgs a) {
-  if (a.totals->overflow) return;
-  __shared__ uint32_t sh[kSortSmem];
-  for (uint32_t l = blockIdx.x; l < a.n_lists; l += gridDim.x) {
-    uint32_t off = a.list_off[l], n = a.list_off[l + 1] - off;
-    if (n <= (uint32_t)kSortWarpMax) continue;  // short lists belong to k_list_sort_warp
-    uint32_t P = 1;
-    while (P < n) P <<= 1;
-    uint32_t *g = a.list_items + off;
-    const bool in_smem = P <= (uint32_t)kSortSmem;
-    uint32_t *d = in_smem ? sh : g;
-    const uint32_t lim = in_smem ? P : n;  // shared memory holds the +inf padding explicitly
-    if (in_smem) {
-      for (uint32_t i = threadIdx.x; i < P; i += kSortThreads) sh[i] = i < n ? g[i] : 0xffffffffu;
-    }
-    __syncthreads();
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < P; i += kSortThreads) {
-          uint32_t p = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
-          if (p > i && p < lim) {
-            uint32_t x = d[i], y = d[p];
-            if (x > y) {
-              d[i] = y;
-              d[p] = x;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    if (in_smem) {
-      for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) g[i] = sh[i];
-    }
-    __syncthreads();
   }
 }
 
@@ -691,102 +731,142 @@ __device__ __forceinline__ unsigned long long pack_record(int xa, int ya, int xb
          ((unsigned long long)yb << 39) | ((unsigned long long)fs << 52) | ((unsigned long long)fe << 53);
 }
 
-// Walks one edge over the tile grid of its path.  MODE 0 counts records and posts backdrop deltas, MODE 1
-// scatters the tile-clipped records.  Crossings with band and tile boundaries are computed once and carried.
+// Bins the part of one edge that lies in tile row (band) `b` of its path's grid.  MODE 0 counts records and posts
+// backdrop deltas, MODE 1 scatters the tile-clipped records.  The crossings with the band's top and bottom lines come
+// straight from the edge's end points (x0 + round((Y - y0) (x1 - x0) / (y1 - y0))), so every band of an edge can be
+// processed independently of the others; crossings with tile columns are carried along the band.
 template <int MODE, bool SMALL>
-__device__ void bin_edge(const RenderArgs &a, int x0, int y0, int x1, int y1, int bx0, int by0, int bw, int bh,
-                         uint32_t slot_base) {
+__device__ __forceinline__ void bin_band(const RenderArgs &a, int x0, int y0, int x1, int y1, int bx0, int by0, int bw,
+                                         uint32_t slot_base, int b) {
   const int B = kTileFx;
   const bool horiz = y0 == y1;
   const bool down = y0 < y1;
   const int ylo = min(y0, y1), yhi = max(y0, y1);
-  const int x_ylo = down ? x0 : x1, x_yhi = down ? x1 : x0;  // x at the upper / lower end point
-  int b_first = ylo >> 12, b_last = horiz ? b_first : (yhi - 1) >> 12;
-  // rows outside the path's grid are outside the viewport (the bbox covers every edge of the path)
-  b_first = max(b_first, by0);
-  b_last = min(b_last, by0 + bh - 1);
-  if (b_first > b_last) return;
-  int x_top = 0;  // x where the edge crosses the top line of the current band (when it starts above it)
-  if (!horiz && ylo < b_first * B) x_top = x0 + muldiv<SMALL>(b_first * B - y0, x1 - x0, y1 - y0);
-  for (int b = b_first; b <= b_last; b++) {
-    const int Yt = b * B, Yb = Yt + B;
-    int xs, ys, xe, ye;
-    if (horiz) {
-      xs = x0, ys = y0, xe = x1, ye = y1;
+  const int Yt = b * B, Yb = Yt + B;
+  int xs, ys, xe, ye;
+  if (horiz) {
+    xs = x0, ys = y0, xe = x1, ye = y1;
+  } else {
+    const int yu = max(ylo, Yt), yl = min(yhi, Yb);
+    const int xu = (ylo >= Yt) ? (down ? x0 : x1) : x0 + muldiv<SMALL>(Yt - y0, x1 - x0, y1 - y0);
+    const int xl = (yhi <= Yb) ? (down ? x1 : x0) : x0 + muldiv<SMALL>(Yb - y0, x1 - x0, y1 - y0);
+    if (down) {
+      xs = xu, ys = yu, xe = xl, ye = yl;
     } else {
-      int yu = max(ylo, Yt), yl = min(yhi, Yb);
-      int xu = (ylo >= Yt) ? x_ylo : x_top;
-      int xl = (yhi <= Yb) ? x_yhi : x0 + muldiv<SMALL>(Yb - y0, x1 - x0, y1 - y0);
-      x_top = xl;
-      if (down) {
-        xs = xu, ys = yu, xe = xl, ye = yl;
-      } else {
-        xs = xl, ys = yl, xe = xu, ye = yu;
-      }
+      xs = xl, ys = yl, xe = xu, ye = yu;
     }
-    const uint32_t row_base = slot_base + (uint32_t)((b - by0) * bw);
+  }
+  const uint32_t row_base = slot_base + (uint32_t)((b - by0) * bw);
+  if (MODE == 0) {
+    if (ys == Yt) {
+      int lx = max((xs >> 12) + 1 - bx0, 0);
+      if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], 1);
+    }
+    if (ye == Yt) {
+      int lx = max((xe >> 12) + 1 - bx0, 0);
+      if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], -1);
+    }
+  }
+  const int xlo = min(xs, xe), xhi = max(xs, xe);
+  const int c0 = max(xlo >> 12, bx0), c1 = min(xhi >> 12, bx0 + bw - 1);
+  if (c0 > c1) return;
+  const bool right = xs < xe;
+  // y where the sub-edge crosses the left boundary of the current tile (when it reaches further left)
+  int y_left = 0;
+  if (xlo < c0 * B) y_left = ys + muldiv<SMALL>(c0 * B - xs, ye - ys, xe - xs);
+  for (int t = c0; t <= c1; t++) {
+    const int X0 = t * B, X1 = X0 + B;
+    const bool clip_l = xlo < X0, clip_r = xhi > X1;
+    int y_right = 0;  // also needed by the next tile when the sub-edge ends exactly on the boundary
+    if (clip_r || t < c1) y_right = ys + muldiv<SMALL>(X1 - xs, ye - ys, xe - xs);
+    int ax, ay, bx, by, fs = 0, fe = 0;
+    if (right) {
+      ax = clip_l ? X0 : xs, ay = clip_l ? y_left : ys, fs = clip_l;
+      bx = clip_r ? X1 : xe, by = clip_r ? y_right : ye;
+    } else {
+      ax = clip_r ? X1 : xs, ay = clip_r ? y_right : ys;
+      bx = clip_l ? X0 : xe, by = clip_l ? y_left : ye, fe = clip_l;
+    }
+    y_left = y_right;
+    if (ay == by && !fs && !fe) continue;
+    const uint32_t slot = row_base + (uint32_t)(t - bx0);
     if (MODE == 0) {
-      if (ys == Yt) {
-        int lx = max((xs >> 12) + 1 - bx0, 0);
-        if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], 1);
-      }
-      if (ye == Yt) {
-        int lx = max((xe >> 12) + 1 - bx0, 0);
-        if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], -1);
-      }
-    }
-    const int xlo = min(xs, xe), xhi = max(xs, xe);
-    const int c0 = max(xlo >> 12, bx0), c1 = min(xhi >> 12, bx0 + bw - 1);
-    if (c0 > c1) continue;
-    const bool right = xs < xe;
-    // y where the sub-edge crosses the left boundary of the current tile (when it reaches further left)
-    int y_left = 0;
-    if (xlo < c0 * B) y_left = ys + muldiv<SMALL>(c0 * B - xs, ye - ys, xe - xs);
-    for (int t = c0; t <= c1; t++) {
-      const int X0 = t * B, X1 = X0 + B;
-      const bool clip_l = xlo < X0, clip_r = xhi > X1;
-      int y_right = 0;  // also needed by the next tile when the sub-edge ends exactly on the boundary
-      if (clip_r || t < c1) y_right = ys + muldiv<SMALL>(X1 - xs, ye - ys, xe - xs);
-      int ax, ay, bx, by, fs = 0, fe = 0;
-      if (right) {
-        ax = clip_l ? X0 : xs, ay = clip_l ? y_left : ys, fs = clip_l;
-        bx = clip_r ? X1 : xe, by = clip_r ? y_right : ye;
-      } else {
-        ax = clip_r ? X1 : xs, ay = clip_r ? y_right : ys;
-        bx = clip_l ? X0 : xe, by = clip_l ? y_left : ye, fe = clip_l;
-      }
-      y_left = y_right;
-      if (ay == by && !fs && !fe) continue;
-      const uint32_t slot = row_base + (uint32_t)(t - bx0);
-      if (MODE == 0) {
-        atomicAdd(&a.slot_count[slot], 1u);
-      } else {
-        // the counts of pass 0 double as cursors: they run back down to zero (order inside a slot is irrelevant,
-        // coverage accumulation is integer)
-        uint32_t pos = a.slot_off[slot] + atomicSub(&a.slot_count[slot], 1u) - 1u;
-        a.records[pos] = pack_record(ax - X0, ay - Yt, bx - X0, by - Yt, fs, fe);
-      }
+      atomicAdd(&a.slot_count[slot], 1u);
+    } else {
+      // the counts of pass 0 double as cursors: they run back down to zero (order inside a slot is irrelevant,
+      // coverage accumulation is integer)
+      uint32_t pos = a.slot_off[slot] + atomicSub(&a.slot_count[slot], 1u) - 1u;
+      a.records[pos] = pack_record(ax - X0, ay - Yt, bx - X0, by - Yt, fs, fe);
     }
   }
 }
 
+// One warp takes 32 consecutive edges, counts the bands each of them touches inside its path's grid, and then
+// spreads the (edge, band) pairs evenly over its lanes (warp prefix sum + search), so that a 64 px edge crossing
+// five bands does not leave 31 lanes idle.
+constexpr int kBinWarps = 8;
+
 template <int MODE>
-__global__ void k_bin(RenderArgs a) {
+__global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
   if (a.totals->overflow) return;
-  uint32_t n = a.totals->n_edges;
-  uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-    const int4 ed = a.edges[e];
-    const uint32_t pid = a.edge_pid[e];
-    const PathRec rec = a.path_rec[pid];
-    const int bw = rec.wh & 0xffff, bh = rec.wh >> 16;
-    if (bw == 0) continue;
-    const uint32_t slot_base = a.path_slot_off[pid];
-    const bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
-    if (small)
-      bin_edge<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, slot_base);
-    else
-      bin_edge<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, rec.xy0 & 0xffff, rec.xy0 >> 16, bw, bh, slot_base);
+  __shared__ int4 sh_edge[kBinWarps][32];
+  __shared__ uint4 sh_path[kBinWarps][32];  // xy0, bw | bh << 16, slot base, first band
+  const uint32_t n = a.totals->n_edges;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t stride = gridDim.x * kBinWarps * 32;
+  for (uint32_t base = (blockIdx.x * kBinWarps + w) * 32; base < n; base += stride) {
+    const uint32_t e = base + lane;
+    int nb = 0;
+    if (e < n) {
+      const int4 ed = a.edges[e];
+      const uint32_t pid = a.edge_pid[e];
+      const PathRec rec = a.path_rec[pid];
+      const int bw = rec.wh & 0xffff, bh = rec.wh >> 16, by0 = rec.xy0 >> 16;
+      if (bw) {
+        const int ylo = min(ed.y, ed.w), yhi = max(ed.y, ed.w);
+        int b_first = ylo >> 12, b_last = (ed.y == ed.w) ? b_first : (yhi - 1) >> 12;
+        // rows outside the path's grid are outside the viewport (the bbox covers every edge of the path)
+        b_first = max(b_first, by0);
+        b_last = min(b_last, by0 + bh - 1);
+        if (b_first <= b_last) {
+          nb = b_last - b_first + 1;
+          sh_edge[w][lane] = ed;
+          sh_path[w][lane] = make_uint4(rec.xy0, rec.wh, a.path_slot_off[pid], (uint32_t)b_first);
+        }
+      }
+    }
+    int incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - nb;
+    __syncwarp();
+    for (int k0 = 0; k0 < total; k0 += 32) {
+      const int k = min(k0 + (int)lane, total - 1);
+      // owner = the last lane whose first item is <= k (lanes without items share their successor's start)
+      int o = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        int v = __shfl_sync(0xffffffffu, excl, o + step);
+        if (v <= k) o += step;
+      }
+      const int first = __shfl_sync(0xffffffffu, excl, o);
+      if (k0 + (int)lane < total) {
+        const int4 ed = sh_edge[w][o];
+        const uint4 pp = sh_path[w][o];
+        const int b = (int)pp.w + (k - first);
+        const int bx0 = pp.x & 0xffff, by0 = pp.x >> 16, bw = pp.y & 0xffff;
+        const bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
+        if (small)
+          bin_band<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, b);
+        else
+          bin_band<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, b);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -926,29 +1006,34 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
   float gx = (p.inv[0] * xc + p.inv[2] * yc) + p.inv[4];
   float gy = (p.inv[1] * xc + p.inv[3] * yc) + p.inv[5];
   if (type == PAINT_BITMAP) {
+    // box(rx) x box(ry) footprint around the sample point, texel by texel, rows outer / columns inner (the oracle's
+    // summation order).  Wrapped texel indices are carried along instead of taking a modulo per tap; 1 / rx and
+    // 1 / ry come from path setup (p.focal / p.omf are reused for them: same IEEE division, done once per path).
     cudaTextureObject_t tex = (cudaTextureObject_t)p.ptr;
-    float hrx = p.rx * 0.5f, hry = p.ry * 0.5f;
-    float irx = 1.0f / p.rx, iry = 1.0f / p.ry;
-    float lox = gx - hrx, hix = gx + hrx, loy = gy - hry, hiy = gy + hry;
-    int i0 = (int)floorf(lox), j0 = (int)floorf(loy);
+    const float hrx = p.rx * 0.5f, hry = p.ry * 0.5f;
+    const float irx = p.focal, iry = p.omf;
+    const float lox = gx - hrx, hix = gx + hrx, loy = gy - hry, hiy = gy + hry;
+    const int i0 = (int)floorf(lox), j0 = (int)floorf(loy);
+    const bool rep = p.repeating != 0;
+    const int ii0 = rep ? floormod(i0, p.bw) : i0;
+    int jj = rep ? floormod(j0, p.bh) : j0;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     for (int j = j0; (float)j < hiy; j++) {
+      const int jcur = jj;
+      jj++;
+      if (rep && jj == p.bh) jj = 0;
+      if (!rep && (j < 0 || j >= p.bh)) continue;
       float wl = fmaxf(loy, (float)j), wh = fminf(hiy, (float)(j + 1));
       float wy = fmaxf(wh - wl, 0.0f) * iry;
-      int jj = j;
-      if (p.repeating)
-        jj = floormod(j, p.bh);
-      else if (j < 0 || j >= p.bh)
-        continue;
+      int ii = ii0;
       for (int i = i0; (float)i < hix; i++) {
+        const int icur = ii;
+        ii++;
+        if (rep && ii == p.bw) ii = 0;
+        if (!rep && (i < 0 || i >= p.bw)) continue;
         float vl = fmaxf(lox, (float)i), vh = fminf(hix, (float)(i + 1));
         float wx = fmaxf(vh - vl, 0.0f) * irx;
-        int ii = i;
-        if (p.repeating)
-          ii = floormod(i, p.bw);
-        else if (i < 0 || i >= p.bw)
-          continue;
-        uchar4 t = tex2D<uchar4>(tex, (float)ii + 0.5f, (float)jj + 0.5f);
+        uchar4 t = tex2D<uchar4>(tex, (float)icur + 0.5f, (float)jcur + 0.5f);
         float wgt = wx * wy;
         acc0 = acc0 + wgt * (float)t.x;
         acc1 = acc1 + wgt * (float)t.y;
@@ -1303,28 +1388,24 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   scan_u32(a.path_slot_off, a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
            st, launches);
-  if (a.n_paths) {
-    k_list_build<false><<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    launches++;
-  }
+  // candidate lists: row counts (from path setup) -> row lists -> group counts -> group lists
+  scan_u32(a.row_count, a.row_off, nullptr, a.n_frames * (uint32_t)a.tiles_y, a.scan_tmp, &a.totals->n_rowent, a.caps.rows,
+           &a.totals->overflow, 16u, st, launches);
+  k_row_lists<<<(unsigned)std::min<uint32_t>(a.n_frames * (uint32_t)a.tiles_y, kNumSM * 8), kRowThreads, 0, st>>>(a);
+  launches++;
   scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
            launches);
+  k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);
   k_zero_slots<<<wide, T, 0, st>>>(a);
-  launches++;
-  if (a.n_paths) {
-    k_list_build<true><<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    k_list_sort_warp<<<(unsigned)std::min<uint32_t>((a.n_lists + 3) / 4, kNumSM * 16), kSortThreads, 0, st>>>(a);
-    k_list_sort<<<(unsigned)std::min<uint32_t>(a.n_lists, kNumSM * 8), kSortThreads, 0, st>>>(a);
-    launches += 3;
-  }
+  launches += 2;
   mark(3);
   if (a.n_seginst) {
-    k_flatten_emit<<<grid_for(a.n_seginst), T, 0, st>>>(a);
+    k_flatten_emit<<<grid_for(a.n_seginst), kEmitWarps * 32, 0, st>>>(a);
     launches++;
   }
   mark(4);
   if (a.n_seginst) {
-    k_bin<0><<<wide, T, 0, st>>>(a);
+    k_bin<0><<<wide, kBinWarps * 32, 0, st>>>(a);
     k_backdrop<<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
     k_backdrop_big<<<kNumSM * 4, T, 0, st>>>(a);
     launches += 3;
@@ -1335,7 +1416,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
            &a.totals->overflow, 4u, st, launches);
   mark(6);
   if (a.n_seginst) {
-    k_bin<1><<<wide, T, 0, st>>>(a);
+    k_bin<1><<<wide, kBinWarps * 32, 0, st>>>(a);
     launches++;
   }
   mark(7);

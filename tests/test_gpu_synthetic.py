@@ -137,3 +137,49 @@ def test_full_size_translation_equivariance(built_library):
     c = r.get_image(frame=1, premultiplied=True).data
     np.testing.assert_array_equal(c[16:, 32:], a[:-16, :-32])
     r.close()
+
+
+def test_streaming_renders_overlap_without_corruption(built_library):
+    """swfr_render_batch / swfr_read_frames_async streamed back to back (no sync in between, two host buffers):
+    every batch must come out exactly as when it is rendered alone and read synchronously."""
+    import torch
+
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import stage_array_from_numpy, stages_from_prims
+
+    W, H, N, F = 640, 360, 300, 6
+    r = sw.HeadlessRenderer(W, H)
+    r.set_option(capi.OPT_FRAMES_PER_PASS, 2)
+    r.set_option(capi.OPT_HOST_THREADS, 3)
+    for j, t in enumerate(synth.textures()):
+        r.register_bitmap(j, t)
+    batches = []
+    for k in range(3):
+        prims = []
+        for f in range(F):
+            fr = synth.SynthFrame(100 + k * F + f, N, W, H, 0.5)
+            prims.append(stage_array_from_numpy(fr.register(r), fr.matrices()))
+        batches.append(stages_from_prims(prims))
+    # reference: one batch at a time, synchronous reads
+    want = []
+    for arr, keep in batches:
+        r.render_stage_array(arr, F)
+        want.append(np.stack([r.get_image(frame=f, premultiplied=True).data.copy() for f in range(F)]))
+    assert not np.array_equal(want[0], want[1])
+    # streamed: 5 renders in flight back to back over 2 output buffers
+    fb = W * H * 4
+    out = [torch.zeros(F * fb, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    order = [0, 1, 2, 1, 0]
+    for i, k in enumerate(order):
+        r.render_stage_array(batches[k][0], F)
+        r.read_frames_async(0, F, out[i & 1].data_ptr())
+    r.sync()
+    np.testing.assert_array_equal(out[0].numpy().reshape(F, H, W, 4), want[order[4]])
+    np.testing.assert_array_equal(out[1].numpy().reshape(F, H, W, 4), want[order[3]])
+    # partial range + sync per step still works
+    r.render_stage_array(batches[2][0], F)
+    r.read_frames_async(1, 3, out[0].data_ptr())
+    r.sync()
+    np.testing.assert_array_equal(out[0].numpy()[: 3 * fb].reshape(3, H, W, 4), want[2][1:4])
+    r.close()
