@@ -222,6 +222,7 @@ __global__ void k_init(RenderArgs a) {
   if (i == 0) {
     a.totals->n_edges = a.totals->n_slots = a.totals->n_records = 0;
     a.totals->overflow = 0;
+    a.totals->overflow_late = 0;
     a.totals->error = 0;
     a.totals->work = 0;
     a.totals->n_list = 0;
@@ -737,7 +738,7 @@ __device__ __forceinline__ unsigned long long pack_record(int xa, int ya, int xb
 // processed independently of the others; crossings with tile columns are carried along the band.
 template <int MODE, bool SMALL>
 __device__ __forceinline__ void bin_band(const RenderArgs &a, int x0, int y0, int x1, int y1, int bx0, int by0, int bw,
-                                         uint32_t slot_base, int b) {
+                                         uint32_t slot_base, uint32_t rec_base, int b) {
   const int B = kTileFx;
   const bool horiz = y0 == y1;
   const bool down = y0 < y1;
@@ -793,9 +794,10 @@ __device__ __forceinline__ void bin_band(const RenderArgs &a, int x0, int y0, in
     if (MODE == 0) {
       atomicAdd(&a.slot_count[slot], 1u);
     } else {
-      // the counts of pass 0 double as cursors: they run back down to zero (order inside a slot is irrelevant,
-      // coverage accumulation is integer)
-      uint32_t pos = a.slot_off[slot] + atomicSub(&a.slot_count[slot], 1u) - 1u;
+      // slot_off holds the END of the slot's record range (relative to the path's base); the counts of pass 0
+      // double as cursors and run back down to zero (order inside a slot is irrelevant: coverage accumulation is
+      // integer)
+      uint32_t pos = rec_base + a.slot_off[slot] - atomicSub(&a.slot_count[slot], 1u);
       a.records[pos] = pack_record(ax - X0, ay - Yt, bx - X0, by - Yt, fs, fe);
     }
   }
@@ -809,8 +811,12 @@ constexpr int kBinWarps = 8;
 template <int MODE>
 __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
   if (a.totals->overflow) return;
+  if (MODE == 1 && a.totals->n_records > a.caps.records) {  // the record space allocated by k_slot_prefix does not fit
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&a.totals->overflow_late, 4u);
+    return;
+  }
   __shared__ int4 sh_edge[kBinWarps][32];
-  __shared__ uint4 sh_path[kBinWarps][32];  // xy0, bw | bh << 16, slot base, first band
+  __shared__ uint4 sh_path[kBinWarps][32];  // xy0, bw | first band << 16, slot base, record base
   const uint32_t n = a.totals->n_edges;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * kBinWarps * 32;
@@ -831,7 +837,8 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
         if (b_first <= b_last) {
           nb = b_last - b_first + 1;
           sh_edge[w][lane] = ed;
-          sh_path[w][lane] = make_uint4(rec.xy0, rec.wh, a.path_slot_off[pid], (uint32_t)b_first);
+          sh_path[w][lane] = make_uint4(rec.xy0, (uint32_t)bw | ((uint32_t)b_first << 16), a.path_slot_off[pid],
+                                        MODE == 1 ? a.path_rec_base[pid] : 0u);
         }
       }
     }
@@ -857,42 +864,28 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
       if (k0 + (int)lane < total) {
         const int4 ed = sh_edge[w][o];
         const uint4 pp = sh_path[w][o];
-        const int b = (int)pp.w + (k - first);
+        const int b = (int)(pp.y >> 16) + (k - first);
         const int bx0 = pp.x & 0xffff, by0 = pp.x >> 16, bw = pp.y & 0xffff;
         const bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
         if (small)
-          bin_band<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, b);
+          bin_band<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, pp.w, b);
         else
-          bin_band<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, b);
+          bin_band<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, pp.w, b);
       }
     }
     __syncwarp();
   }
 }
 
-// Prefix sum of the backdrop deltas along each tile row of each path grid.  Grids of up to kBackdropSmall slots:
-// one warp per path, a segmented (per row) scan over the flat grid, 32 slots per step, coalesced.  Larger grids:
-// one block per path, warps over rows (second kernel), so that a full-screen path is not a serial tail.
-__device__ __forceinline__ void backdrop_rows(int32_t *p, int bw, int row_begin, int row_end, int row_step, uint32_t lane) {
-  for (int row = row_begin; row < row_end; row += row_step) {
-    int32_t *q = p + row * bw;
-    int carry = 0;
-    for (int x0 = 0; x0 < bw; x0 += 32) {
-      int x = x0 + (int)lane;
-      int v = x < bw ? q[x] : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
-        if ((int)lane >= o) v += t;
-      }
-      v += carry;
-      if (x < bw) q[x] = v;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-    }
-  }
-}
-
-__global__ void k_backdrop(RenderArgs a) {
+// Per path instance, over the slots of its tile grid (row-major):
+//   * prefix sum of the backdrop deltas along each tile row (winding number at the left edge of every tile);
+//   * inclusive prefix sum of the record counts -> slot_off (END of each slot's record range, relative to the path),
+//     and one atomicAdd per path on totals.n_records for the path's base: record space is allocated path by path, so
+//     there is no global scan over the slot array (the placement of paths in the record buffer varies from run to run,
+//     the pixels do not: nothing depends on it).
+// Grids of up to kBackdropSmall slots: one warp per path, 32 slots per step, coalesced.  Larger grids: one block
+// per path (second kernel), so that a full-screen path is not a serial tail.
+__global__ void k_slot_prefix(RenderArgs a) {
   if (a.totals->overflow) return;
   uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -900,37 +893,88 @@ __global__ void k_backdrop(RenderArgs a) {
     uint32_t wh = a.path_rec[pid].wh;
     int bw = wh & 0xffff, bh = wh >> 16;
     const int n = bw * bh;
-    if (bw <= 1 || n > kBackdropSmall) continue;
-    int32_t *p = a.slot_backdrop + a.path_slot_off[pid];
+    if (n == 0) {
+      if (lane == 0) a.path_rec_base[pid] = 0;
+      continue;
+    }
+    if (n > kBackdropSmall) continue;
+    const uint32_t s0 = a.path_slot_off[pid];
+    int32_t *bd = a.slot_backdrop + s0;
+    const uint32_t *cnt = a.slot_count + s0;
+    uint32_t *end = a.slot_off + s0;
     int carry = 0, carry_row = -1;
+    uint32_t ccarry = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
       int i = i0 + (int)lane;
       bool ok = i < n;
-      int row = ok ? i / bw : -2;
-      int col = ok ? i - row * bw : 0;
-      int v = ok ? p[i] : 0;
+      uint32_t c = ok ? cnt[i] : 0u;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
-        if ((int)lane >= o && col >= o) v += t;
+        uint32_t t = __shfl_up_sync(0xffffffffu, c, o);
+        if ((int)lane >= o) c += t;
       }
-      if (row == carry_row) v += carry;
-      if (ok) p[i] = v;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-      carry_row = __shfl_sync(0xffffffffu, row, 31);
+      c += ccarry;
+      if (ok) end[i] = c;
+      ccarry = __shfl_sync(0xffffffffu, c, 31);
+      if (bw > 1) {
+        int row = ok ? i / bw : -2;
+        int col = ok ? i - row * bw : 0;
+        int v = ok ? bd[i] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, v, o);
+          if ((int)lane >= o && col >= o) v += t;
+        }
+        if (row == carry_row) v += carry;
+        if (ok) bd[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+        carry_row = __shfl_sync(0xffffffffu, row, 31);
+      }
     }
+    if (lane == 0) a.path_rec_base[pid] = ccarry ? atomicAdd(&a.totals->n_records, ccarry) : 0u;
   }
 }
 
-__global__ void k_backdrop_big(RenderArgs a) {
+__global__ void __launch_bounds__(256) k_slot_prefix_big(RenderArgs a) {
   if (a.totals->overflow) return;
+  __shared__ uint32_t sh[32];
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const uint32_t n_big = a.totals->n_big;
-  for (uint32_t i = blockIdx.x; i < n_big; i += gridDim.x) {
-    uint32_t pid = a.big_list[i];
-    uint32_t wh = a.path_rec[pid].wh;
-    int bw = wh & 0xffff, bh = wh >> 16;
-    backdrop_rows(a.slot_backdrop + a.path_slot_off[pid], bw, (int)w, bh, (int)nw, lane);
+  for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
+    const uint32_t pid = a.big_list[bi];
+    const uint32_t wh = a.path_rec[pid].wh;
+    const int bw = wh & 0xffff, bh = wh >> 16;
+    const uint32_t s0 = a.path_slot_off[pid];
+    // backdrop: warps over rows
+    for (int row = (int)w; row < bh; row += (int)nw) {
+      int32_t *q = a.slot_backdrop + s0 + row * bw;
+      int carry = 0;
+      for (int x0 = 0; x0 < bw; x0 += 32) {
+        int x = x0 + (int)lane;
+        int v = x < bw ? q[x] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, v, o);
+          if ((int)lane >= o) v += t;
+        }
+        v += carry;
+        if (x < bw) q[x] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    // record counts: block-wide inclusive prefix over the whole grid
+    const uint32_t n = (uint32_t)(bw * bh);
+    uint32_t carry = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+      const uint32_t i = i0 + threadIdx.x;
+      const uint32_t c = i < n ? a.slot_count[s0 + i] : 0u;
+      uint32_t tile_total;
+      const uint32_t ex = block_exclusive(c, sh, &tile_total);
+      if (i < n) a.slot_off[s0 + i] = carry + ex + c;
+      carry += tile_total;
+    }
+    if (threadIdx.x == 0) a.path_rec_base[pid] = carry ? atomicAdd(&a.totals->n_records, carry) : 0u;
+    __syncthreads();
   }
 }
 
@@ -1108,9 +1152,11 @@ __device__ __forceinline__ Probe probe_slot(const RenderArgs &a, uint32_t pid, b
   int bx0 = rc.x & 0xffff, by0 = rc.x >> 16, bw = rc.y & 0xffff, bh = rc.y >> 16;
   int lx = tx - bx0, ly = ty - by0;
   if (lx < 0 || ly < 0 || lx >= bw || ly >= bh) return pr;
-  uint32_t slot = __ldg(a.path_slot_off + pid) + (uint32_t)(ly * bw + lx);
-  pr.o0 = __ldg(a.slot_off + slot);
-  pr.o1 = __ldg(a.slot_off + slot + 1);
+  const uint32_t local = (uint32_t)(ly * bw + lx);
+  const uint32_t slot = __ldg(a.path_slot_off + pid) + local;
+  const uint32_t rec_base = __ldg(a.path_rec_base + pid);
+  pr.o0 = rec_base + (local ? __ldg(a.slot_off + slot - 1) : 0u);
+  pr.o1 = rec_base + __ldg(a.slot_off + slot);
   pr.bd = __ldg(a.slot_backdrop + slot);
   pr.info = rc.z;
   pr.color = rc.w;
@@ -1119,7 +1165,7 @@ __device__ __forceinline__ Probe probe_slot(const RenderArgs &a, uint32_t pid, b
 }
 
 __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
-  if (a.totals->overflow) return;
+  if (a.totals->overflow | a.totals->overflow_late) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1325,7 +1371,7 @@ __global__ void k_tile_counts(RenderArgs a, uint32_t frame, uint32_t *counts) {
     for (int y = 0; y < bh; y++)
       for (int x = 0; x < bw; x++) {
         uint32_t s = base + (uint32_t)(y * bw + x);
-        uint32_t c = a.slot_off[s + 1] - a.slot_off[s];
+        uint32_t c = a.slot_off[s] - (s > base ? a.slot_off[s - 1] : 0u);
         if (c) atomicAdd(&counts[(by0 + y) * a.tiles_x + bx0 + x], c);
       }
   }
@@ -1353,7 +1399,7 @@ static void scan_u32(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, 
 
 const char *stage_name(int i) {
   static const char *names[kNumStages] = {"flatten_count", "scan_edges",   "path_setup",  "flatten_emit",
-                                          "bin_count",     "scan_records", "bin_scatter", "fine"};
+                                          "bin_count",     "slot_prefix", "bin_scatter", "fine"};
   return (i >= 0 && i < kNumStages) ? names[i] : "?";
 }
 
@@ -1406,14 +1452,15 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   mark(4);
   if (a.n_seginst) {
     k_bin<0><<<wide, kBinWarps * 32, 0, st>>>(a);
-    k_backdrop<<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    k_backdrop_big<<<kNumSM * 4, T, 0, st>>>(a);
-    launches += 3;
+    launches++;
   }
   mark(5);
-  // records: slot_count -> slot_off (separate array so counts can be reused as scatter cursors)
-  scan_u32(a.slot_count, a.slot_off, &a.totals->n_slots, a.caps.slots, a.scan_tmp, &a.totals->n_records, a.caps.records,
-           &a.totals->overflow, 4u, st, launches);
+  // backdrop prefix + record allocation (slot_count -> slot_off, path_rec_base, totals.n_records)
+  if (a.n_paths) {
+    k_slot_prefix<<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
+    k_slot_prefix_big<<<kNumSM * 4, T, 0, st>>>(a);
+    launches += 2;
+  }
   mark(6);
   if (a.n_seginst) {
     k_bin<1><<<wide, kBinWarps * 32, 0, st>>>(a);

@@ -61,7 +61,8 @@ struct Totals {
   uint32_t n_list;    // candidate-list entries
   uint32_t n_big;     // path instances whose tile grid is larger than kBackdropSmall
   uint32_t n_rowent;  // row-list entries
-  uint32_t pad[3];
+  uint32_t overflow_late;  // bit2: the record space allocated after the count pass exceeds caps.records
+  uint32_t pad[2];
 };
 
 struct Caps {
@@ -87,11 +88,12 @@ struct RenderArgs {
   PathRec *path_rec;        // n_paths
   PaintInst *paint_inst;    // n_paths
   uint32_t *path_slot_off;  // n_paths + 1
+  uint32_t *path_rec_base;  // n_paths: first record of the path instance
   int4 *edges;              // caps.edges
   uint32_t *edge_pid;       // caps.edges: path instance of each edge
   uint32_t *slot_count;     // caps.slots (+1)
   int32_t *slot_backdrop;   // caps.slots
-  uint32_t *slot_off;       // caps.slots + 1
+  uint32_t *slot_off;       // caps.slots + 1: end of the slot's record range, relative to path_rec_base
   unsigned long long *records;  // caps.records
   uint32_t *frames;         // n_frames * width * height
   uint32_t *scan_tmp;       // >= 4096 words

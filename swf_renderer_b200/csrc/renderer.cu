@@ -135,9 +135,9 @@ struct swfr_renderer {
   std::vector<BitmapDev> h_bitmaps;
 
   // ---- working memory ----
-  DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_cursor, list_items, big_list;
-  Caps caps{0, 0, 0, 0};
+  DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop,
+      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_items, big_list, row_count, row_off, row_items;
+  Caps caps{0, 0, 0, 0, 0};
   PinnedBuf pin_totals;
   swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
   int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
@@ -412,6 +412,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   CK(r->path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
   CK(r->paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
   CK(r->path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
+  CK(r->path_rec_base.reserve(((size_t)max_paths + 1) * 4 + 256));
   CK(r->big_list.reserve((size_t)max_paths * 4 + 256));
   CK(r->scan_tmp.reserve(8192 * 4));
   CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
@@ -421,12 +422,16 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   want.slots = std::max<uint32_t>(want.slots, std::max<uint32_t>(1u << 16, max_paths * 32));
   want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
   want.list = std::max<uint32_t>(want.list, std::max<uint32_t>(1u << 16, max_paths * 12));
+  want.rows = std::max<uint32_t>(want.rows, std::max<uint32_t>(1u << 16, max_paths * 8));
   uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   size_t max_lists = (size_t)std::max<uint32_t>(1, r->frames_per_pass) * r->tiles_y * groups_x;
   for (const Pass &p : b.passes) max_lists = std::max(max_lists, (size_t)p.n_frames * r->tiles_y * groups_x);
   CK(r->list_off.reserve((max_lists + 1) * 4 + 256));
-  CK(r->list_cursor.reserve((max_lists + 1) * 4 + 256));
   CK(r->list_items.reserve((size_t)want.list * 4));
+  size_t max_rows = max_lists / groups_x;
+  CK(r->row_count.reserve((max_rows + 1) * 4 + 256));
+  CK(r->row_off.reserve((max_rows + 1) * 4 + 256));
+  CK(r->row_items.reserve((size_t)want.rows * 8));
   CK(r->edges.reserve((size_t)want.edges * 16));
   CK(r->edge_pid.reserve((size_t)want.edges * 4));
   CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
@@ -462,6 +467,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.path_rec = r->path_rec.as<PathRec>();
   a.paint_inst = r->paint_inst.as<PaintInst>();
   a.path_slot_off = r->path_slot_off.as<uint32_t>();
+  a.path_rec_base = r->path_rec_base.as<uint32_t>();
   a.edges = r->edges.as<int4>();
   a.edge_pid = r->edge_pid.as<uint32_t>();
   a.slot_count = r->slot_count.as<uint32_t>();
@@ -473,7 +479,9 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   a.n_lists = p.n_frames * r->tiles_y * a.groups_x;
   a.list_off = r->list_off.as<uint32_t>();
-  a.list_cursor = r->list_cursor.as<uint32_t>();
+  a.row_count = r->row_count.as<uint32_t>();
+  a.row_off = r->row_off.as<uint32_t>();
+  a.row_items = r->row_items.as<uint2>();
   a.list_items = r->list_items.as<uint32_t>();
   a.big_list = r->big_list.as<uint32_t>();
   a.totals = r->totals.as<Totals>() + pass_index;
@@ -549,7 +557,9 @@ int finish(swfr_renderer *r) {
       if (t.overflow & 2u) want.slots = std::max(want.slots, grow(t.n_slots));
       if (t.overflow & 4u) want.records = std::max(want.records, grow(t.n_records));
       if (t.overflow & 8u) want.list = std::max(want.list, grow(t.n_list));
+      if (t.overflow & 16u) want.rows = std::max(want.rows, grow(t.n_rowent));
       CK(r->list_items.reserve((size_t)want.list * 4));
+      CK(r->row_items.reserve((size_t)want.rows * 8));
       if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
       CK(r->edges.reserve((size_t)want.edges * 16));
       CK(r->edge_pid.reserve((size_t)want.edges * 4));
