@@ -222,7 +222,6 @@ __global__ void k_init(RenderArgs a) {
   if (i == 0) {
     a.totals->n_edges = a.totals->n_slots = a.totals->n_records = 0;
     a.totals->overflow = 0;
-    a.totals->overflow_late = 0;
     a.totals->error = 0;
     a.totals->work = 0;
     a.totals->n_list = 0;
@@ -506,9 +505,20 @@ __device__ uint32_t morph_solid(const uint8_t *c0, const uint8_t *c1, double r) 
   return solid_premul8(red, g, b, ch[3]);
 }
 
-__global__ void k_path_setup(RenderArgs a) {
+constexpr int kMaxTileRows = 1024;  // frames up to 16384 px high
+
+__global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
+  // candidate lists, step 0: how many path instances touch each tile row of the frame.  Counted in shared memory
+  // for the frame of the block's first path (a block of consecutive paths rarely spans two frames; the others go
+  // straight to global memory), then flushed with one atomic per non-empty row.
+  __shared__ uint32_t sh_rows[kMaxTileRows];
   uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < a.n_paths; pid += stride) {
+  for (uint32_t pid0 = blockIdx.x * blockDim.x; pid0 < a.n_paths; pid0 += stride) {
+  for (int y = threadIdx.x; y < a.tiles_y; y += blockDim.x) sh_rows[y] = 0;
+  const uint32_t block_frame = a.items[find_owner(a.item_path_off, a.n_items, pid0)].frame;
+  __syncthreads();
+  const uint32_t pid = pid0 + threadIdx.x;
+  if (pid < a.n_paths) {
     uint32_t it = find_owner(a.item_path_off, a.n_items, pid);
     const DrawItem &item = a.items[it];
     const DefPaint &dp = a.def_paints[item.paint_first + (pid - a.item_path_off[it])];
@@ -603,11 +613,19 @@ __global__ void k_path_setup(RenderArgs a) {
     a.path_rec[pid] = rec;
     a.path_slot_off[pid] = (uint32_t)(bw * bh);
     if (bw > 1 && bw * bh > kBackdropSmall) a.big_list[atomicAdd(&a.totals->n_big, 1u)] = pid;
-    // candidate lists, step 0: how many path instances touch each tile row of the frame
     if (bw > 0) {
-      uint32_t *rc = a.row_count + item.frame * (uint32_t)a.tiles_y + (uint32_t)by0;
-      for (int y = 0; y < bh; y++) atomicAdd(rc + y, 1u);
+      if (item.frame == block_frame) {
+        for (int y = 0; y < bh; y++) atomicAdd(&sh_rows[by0 + y], 1u);
+      } else {
+        uint32_t *rc = a.row_count + item.frame * (uint32_t)a.tiles_y + (uint32_t)by0;
+        for (int y = 0; y < bh; y++) atomicAdd(rc + y, 1u);
+      }
     }
+  }
+  __syncthreads();
+  for (int y = threadIdx.x; y < a.tiles_y; y += blockDim.x)
+    if (sh_rows[y]) atomicAdd(a.row_count + block_frame * (uint32_t)a.tiles_y + (uint32_t)y, sh_rows[y]);
+  __syncthreads();
   }
 }
 
@@ -811,10 +829,6 @@ constexpr int kBinWarps = 8;
 template <int MODE>
 __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
   if (a.totals->overflow) return;
-  if (MODE == 1 && a.totals->n_records > a.caps.records) {  // the record space allocated by k_slot_prefix does not fit
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&a.totals->overflow_late, 4u);
-    return;
-  }
   __shared__ int4 sh_edge[kBinWarps][32];
   __shared__ uint4 sh_path[kBinWarps][32];  // xy0, bw | first band << 16, slot base, record base
   const uint32_t n = a.totals->n_edges;
@@ -879,10 +893,9 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
 
 // Per path instance, over the slots of its tile grid (row-major):
 //   * prefix sum of the backdrop deltas along each tile row (winding number at the left edge of every tile);
-//   * inclusive prefix sum of the record counts -> slot_off (END of each slot's record range, relative to the path),
-//     and one atomicAdd per path on totals.n_records for the path's base: record space is allocated path by path, so
-//     there is no global scan over the slot array (the placement of paths in the record buffer varies from run to run,
-//     the pixels do not: nothing depends on it).
+//   * inclusive prefix sum of the record counts -> slot_off (END of each slot's record range, relative to the path)
+//     and the path's total -> path_rec_base, which a scan over the PATHS then turns into the path's first record:
+//     record space is allocated path by path, so there is no global scan over the (much longer) slot array.
 // Grids of up to kBackdropSmall slots: one warp per path, 32 slots per step, coalesced.  Larger grids: one block
 // per path (second kernel), so that a full-screen path is not a serial tail.
 __global__ void k_slot_prefix(RenderArgs a) {
@@ -904,34 +917,47 @@ __global__ void k_slot_prefix(RenderArgs a) {
     uint32_t *end = a.slot_off + s0;
     int carry = 0, carry_row = -1;
     uint32_t ccarry = 0;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-      int i = i0 + (int)lane;
-      bool ok = i < n;
-      uint32_t c = ok ? cnt[i] : 0u;
+    for (int i0 = 0; i0 < n; i0 += 128) {
+      // four steps' worth of loads in flight before the (serial) scans
+      uint32_t c4[4];
+      int v4[4];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, c, o);
-        if ((int)lane >= o) c += t;
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + 32 * u + (int)lane;
+        c4[u] = i < n ? cnt[i] : 0u;
+        v4[u] = (i < n && bw > 1) ? bd[i] : 0;
       }
-      c += ccarry;
-      if (ok) end[i] = c;
-      ccarry = __shfl_sync(0xffffffffu, c, 31);
-      if (bw > 1) {
-        int row = ok ? i / bw : -2;
-        int col = ok ? i - row * bw : 0;
-        int v = ok ? bd[i] : 0;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + 32 * u + (int)lane;
+        if (i0 + 32 * u >= n) break;
+        bool ok = i < n;
+        uint32_t c = c4[u];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          int t = __shfl_up_sync(0xffffffffu, v, o);
-          if ((int)lane >= o && col >= o) v += t;
+          uint32_t t = __shfl_up_sync(0xffffffffu, c, o);
+          if ((int)lane >= o) c += t;
         }
-        if (row == carry_row) v += carry;
-        if (ok) bd[i] = v;
-        carry = __shfl_sync(0xffffffffu, v, 31);
-        carry_row = __shfl_sync(0xffffffffu, row, 31);
+        c += ccarry;
+        if (ok) end[i] = c;
+        ccarry = __shfl_sync(0xffffffffu, c, 31);
+        if (bw > 1) {
+          int row = ok ? i / bw : -2;
+          int col = ok ? i - row * bw : 0;
+          int v = v4[u];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, v, o);
+            if ((int)lane >= o && col >= o) v += t;
+          }
+          if (row == carry_row) v += carry;
+          if (ok) bd[i] = v;
+          carry = __shfl_sync(0xffffffffu, v, 31);
+          carry_row = __shfl_sync(0xffffffffu, row, 31);
+        }
       }
     }
-    if (lane == 0) a.path_rec_base[pid] = ccarry ? atomicAdd(&a.totals->n_records, ccarry) : 0u;
+    if (lane == 0) a.path_rec_base[pid] = ccarry;  // total; turned into the base by a scan over the paths
   }
 }
 
@@ -962,18 +988,24 @@ __global__ void __launch_bounds__(256) k_slot_prefix_big(RenderArgs a) {
         carry = __shfl_sync(0xffffffffu, v, 31);
       }
     }
-    // record counts: block-wide inclusive prefix over the whole grid
+    // record counts: block-wide inclusive prefix over the whole grid, 4 slots per thread and step
     const uint32_t n = (uint32_t)(bw * bh);
     uint32_t carry = 0;
-    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
-      const uint32_t i = i0 + threadIdx.x;
-      const uint32_t c = i < n ? a.slot_count[s0 + i] : 0u;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x * 4) {
+      const uint32_t i = i0 + threadIdx.x * 4;
+      uint32_t c[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) c[k] = i + k < n ? a.slot_count[s0 + i + k] : 0u;
       uint32_t tile_total;
-      const uint32_t ex = block_exclusive(c, sh, &tile_total);
-      if (i < n) a.slot_off[s0 + i] = carry + ex + c;
+      uint32_t run = carry + block_exclusive(c[0] + c[1] + c[2] + c[3], sh, &tile_total);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        run += c[k];
+        if (i + k < n) a.slot_off[s0 + i + k] = run;
+      }
       carry += tile_total;
     }
-    if (threadIdx.x == 0) a.path_rec_base[pid] = carry ? atomicAdd(&a.totals->n_records, carry) : 0u;
+    if (threadIdx.x == 0) a.path_rec_base[pid] = carry;
     __syncthreads();
   }
 }
@@ -1165,7 +1197,7 @@ __device__ __forceinline__ Probe probe_slot(const RenderArgs &a, uint32_t pid, b
 }
 
 __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
-  if (a.totals->overflow | a.totals->overflow_late) return;
+  if (a.totals->overflow) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1461,6 +1493,8 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
     k_slot_prefix_big<<<kNumSM * 4, T, 0, st>>>(a);
     launches += 2;
   }
+  scan_u32(a.path_rec_base, a.path_rec_base, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_records, a.caps.records,
+           &a.totals->overflow, 4u, st, launches);
   mark(6);
   if (a.n_seginst) {
     k_bin<1><<<wide, kBinWarps * 32, 0, st>>>(a);

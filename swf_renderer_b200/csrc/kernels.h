@@ -61,8 +61,7 @@ struct Totals {
   uint32_t n_list;    // candidate-list entries
   uint32_t n_big;     // path instances whose tile grid is larger than kBackdropSmall
   uint32_t n_rowent;  // row-list entries
-  uint32_t overflow_late;  // bit2: the record space allocated after the count pass exceeds caps.records
-  uint32_t pad[2];
+  uint32_t pad[3];
 };
 
 struct Caps {

@@ -575,7 +575,7 @@ int finish(swfr_renderer *r) {
       r->stats.kernel_launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
       CK(cudaMemcpyAsync(&r->last_totals[i], r->totals.as<Totals>() + i, sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
       CK(cudaStreamSynchronize(r->stream));
-    }
+      }
   }
   r->pending = false;
   if (rerun) {  // frames copied out before the re-run were incomplete: copy them again
