@@ -227,8 +227,11 @@ __global__ void k_init(RenderArgs a) {
     a.totals->n_list = 0;
     a.totals->n_big = 0;
     a.totals->n_rowent = 0;
+    a.totals->n_stage_blocks = 0;
+    a.totals->overflow_stage = 0;
   }
   for (uint32_t l = i; l < a.n_frames * (uint32_t)a.tiles_y; l += stride) a.row_count[l] = 0;
+  for (uint32_t l = i; l < a.caps.stage / kStageBlock; l += stride) a.stage_used[l] = 0;
   for (uint32_t p = i; p < a.n_paths; p += stride) {
     a.path_bbox[4 * p + 0] = INT_MAX;
     a.path_bbox[4 * p + 1] = INT_MAX;
@@ -750,90 +753,105 @@ __device__ __forceinline__ unsigned long long pack_record(int xa, int ya, int xb
          ((unsigned long long)yb << 39) | ((unsigned long long)fs << 52) | ((unsigned long long)fe << 53);
 }
 
-// Bins the part of one edge that lies in tile row (band) `b` of its path's grid.  MODE 0 counts records and posts
-// backdrop deltas, MODE 1 scatters the tile-clipped records.  The crossings with the band's top and bottom lines come
+// The part of one edge that lies in tile row (band) `b` of its path's grid: the band-clipped sub-edge, the slots of
+// the band's row and the range of tile columns it touches.  The crossings with the band's top and bottom lines come
 // straight from the edge's end points (x0 + round((Y - y0) (x1 - x0) / (y1 - y0))), so every band of an edge can be
-// processed independently of the others; crossings with tile columns are carried along the band.
-template <int MODE, bool SMALL>
-__device__ __forceinline__ void bin_band(const RenderArgs &a, int x0, int y0, int x1, int y1, int bx0, int by0, int bw,
-                                         uint32_t slot_base, uint32_t rec_base, int b) {
+// processed independently of the others.  Also posts the backdrop deltas of the band.
+struct BandPiece {
+  int xs, ys, xe, ye;  // sub-edge, in edge direction
+  int c0, c1;          // tile columns touched inside the grid (c0 > c1: none)
+  uint32_t row_base;   // slot of column bx0 in this band
+  int Yt;
+};
+
+template <bool SMALL>
+__device__ __forceinline__ BandPiece band_setup(const RenderArgs &a, int x0, int y0, int x1, int y1, int bx0, int by0,
+                                                int bw, uint32_t slot_base, int b) {
   const int B = kTileFx;
+  BandPiece p;
   const bool horiz = y0 == y1;
   const bool down = y0 < y1;
   const int ylo = min(y0, y1), yhi = max(y0, y1);
   const int Yt = b * B, Yb = Yt + B;
-  int xs, ys, xe, ye;
   if (horiz) {
-    xs = x0, ys = y0, xe = x1, ye = y1;
+    p.xs = x0, p.ys = y0, p.xe = x1, p.ye = y1;
   } else {
     const int yu = max(ylo, Yt), yl = min(yhi, Yb);
     const int xu = (ylo >= Yt) ? (down ? x0 : x1) : x0 + muldiv<SMALL>(Yt - y0, x1 - x0, y1 - y0);
     const int xl = (yhi <= Yb) ? (down ? x1 : x0) : x0 + muldiv<SMALL>(Yb - y0, x1 - x0, y1 - y0);
     if (down) {
-      xs = xu, ys = yu, xe = xl, ye = yl;
+      p.xs = xu, p.ys = yu, p.xe = xl, p.ye = yl;
     } else {
-      xs = xl, ys = yl, xe = xu, ye = yu;
+      p.xs = xl, p.ys = yl, p.xe = xu, p.ye = yu;
     }
   }
-  const uint32_t row_base = slot_base + (uint32_t)((b - by0) * bw);
-  if (MODE == 0) {
-    if (ys == Yt) {
-      int lx = max((xs >> 12) + 1 - bx0, 0);
-      if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], 1);
-    }
-    if (ye == Yt) {
-      int lx = max((xe >> 12) + 1 - bx0, 0);
-      if (lx < bw) atomicAdd(&a.slot_backdrop[row_base + lx], -1);
-    }
+  p.Yt = Yt;
+  p.row_base = slot_base + (uint32_t)((b - by0) * bw);
+  if (p.ys == Yt) {
+    int lx = max((p.xs >> 12) + 1 - bx0, 0);
+    if (lx < bw) atomicAdd(&a.slot_backdrop[p.row_base + lx], 1);
   }
-  const int xlo = min(xs, xe), xhi = max(xs, xe);
-  const int c0 = max(xlo >> 12, bx0), c1 = min(xhi >> 12, bx0 + bw - 1);
-  if (c0 > c1) return;
-  const bool right = xs < xe;
-  // y where the sub-edge crosses the left boundary of the current tile (when it reaches further left)
-  int y_left = 0;
-  if (xlo < c0 * B) y_left = ys + muldiv<SMALL>(c0 * B - xs, ye - ys, xe - xs);
-  for (int t = c0; t <= c1; t++) {
-    const int X0 = t * B, X1 = X0 + B;
-    const bool clip_l = xlo < X0, clip_r = xhi > X1;
-    int y_right = 0;  // also needed by the next tile when the sub-edge ends exactly on the boundary
-    if (clip_r || t < c1) y_right = ys + muldiv<SMALL>(X1 - xs, ye - ys, xe - xs);
-    int ax, ay, bx, by, fs = 0, fe = 0;
-    if (right) {
-      ax = clip_l ? X0 : xs, ay = clip_l ? y_left : ys, fs = clip_l;
-      bx = clip_r ? X1 : xe, by = clip_r ? y_right : ye;
-    } else {
-      ax = clip_r ? X1 : xs, ay = clip_r ? y_right : ys;
-      bx = clip_l ? X0 : xe, by = clip_l ? y_left : ye, fe = clip_l;
-    }
-    y_left = y_right;
-    if (ay == by && !fs && !fe) continue;
-    const uint32_t slot = row_base + (uint32_t)(t - bx0);
-    if (MODE == 0) {
-      atomicAdd(&a.slot_count[slot], 1u);
-    } else {
-      // slot_off holds the END of the slot's record range (relative to the path's base); the counts of pass 0
-      // double as cursors and run back down to zero (order inside a slot is irrelevant: coverage accumulation is
-      // integer)
-      uint32_t pos = rec_base + a.slot_off[slot] - atomicSub(&a.slot_count[slot], 1u);
-      a.records[pos] = pack_record(ax - X0, ay - Yt, bx - X0, by - Yt, fs, fe);
-    }
+  if (p.ye == Yt) {
+    int lx = max((p.xe >> 12) + 1 - bx0, 0);
+    if (lx < bw) atomicAdd(&a.slot_backdrop[p.row_base + lx], -1);
   }
+  const int xlo = min(p.xs, p.xe), xhi = max(p.xs, p.xe);
+  p.c0 = max(xlo >> 12, bx0);
+  p.c1 = min(xhi >> 12, bx0 + bw - 1);
+  return p;
 }
 
-// One warp takes 32 consecutive edges, counts the bands each of them touches inside its path's grid, and then
-// spreads the (edge, band) pairs evenly over its lanes (warp prefix sum + search), so that a 64 px edge crossing
-// five bands does not leave 31 lanes idle.
+constexpr uint32_t kStageInvalid = 0xffffffffu;
+
+// One tile column `t` of a band piece: the tile-clipped record (or an invalid marker when the clipped piece is a
+// point).  The crossings with the tile's left and right boundary lines come straight from the band piece
+// (ys + round((X - xs) (ye - ys) / (xe - xs))), so every column can be processed independently of the others.
+template <bool SMALL>
+__device__ __forceinline__ bool column_record(int xs, int ys, int xe, int ye, int Yt, int t, unsigned long long &rc) {
+  const int B = kTileFx;
+  const int xlo = min(xs, xe), xhi = max(xs, xe);
+  const bool right = xs < xe;
+  const int X0 = t * B, X1 = X0 + B;
+  const bool clip_l = xlo < X0, clip_r = xhi > X1;
+  int y_left = 0, y_right = 0;
+  if (clip_l) y_left = ys + muldiv<SMALL>(X0 - xs, ye - ys, xe - xs);
+  if (clip_r) y_right = ys + muldiv<SMALL>(X1 - xs, ye - ys, xe - xs);
+  int ax, ay, bx, by, fs = 0, fe = 0;
+  if (right) {
+    ax = clip_l ? X0 : xs, ay = clip_l ? y_left : ys, fs = clip_l;
+    bx = clip_r ? X1 : xe, by = clip_r ? y_right : ye;
+  } else {
+    ax = clip_r ? X1 : xs, ay = clip_r ? y_right : ys;
+    bx = clip_l ? X0 : xe, by = clip_l ? y_left : ye, fe = clip_l;
+  }
+  rc = pack_record(ax - X0, ay - Yt, bx - X0, by - Yt, fs, fe);
+  return !(ay == by && !fs && !fe);
+}
+
+// K2, pass 1 of 2.  Two levels of warp-cooperative expansion keep all lanes busy although edges touch different
+// numbers of tiles:
+//   level 1 - a warp takes 32 consecutive edges, counts the bands (tile rows) each of them touches inside its path's
+//             grid and spreads the (edge, band) pairs evenly over its lanes (warp prefix sum + search); every lane
+//             clips its band piece, posts the backdrop deltas and counts the tile columns the piece touches;
+//   level 2 - the (piece, column) pairs of the round are spread over the lanes the same way; every lane clips ONE
+//             record, counts it in its slot and writes it to the warp's staging block (consecutive lanes write
+//             consecutive 16-byte entries; one global atomic per kStageBlock entries).
+// Pass 2 (k_scatter) moves the staged records to their slots once the offsets are known, without touching the
+// geometry again.
 constexpr int kBinWarps = 8;
 
-template <int MODE>
 __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
   if (a.totals->overflow) return;
   __shared__ int4 sh_edge[kBinWarps][32];
-  __shared__ uint4 sh_path[kBinWarps][32];  // xy0, bw | first band << 16, slot base, record base
+  __shared__ uint4 sh_path[kBinWarps][32];   // xy0, bw | first band << 16, slot base, path instance
+  __shared__ int4 sh_piece[kBinWarps][32];   // band piece xs, ys, xe, ye
+  __shared__ uint4 sh_pmeta[kBinWarps][32];  // first column, slot of that column, band top, path instance | small << 31
   const uint32_t n = a.totals->n_edges;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * kBinWarps * 32;
+  const uint32_t cap_blocks = a.caps.stage / kStageBlock;
+  uint32_t blk = 0, blk_used = kStageBlock;  // current staging block of this warp (none yet)
+  bool have_blk = false, dead = false;
   for (uint32_t base = (blockIdx.x * kBinWarps + w) * 32; base < n; base += stride) {
     const uint32_t e = base + lane;
     int nb = 0;
@@ -851,8 +869,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
         if (b_first <= b_last) {
           nb = b_last - b_first + 1;
           sh_edge[w][lane] = ed;
-          sh_path[w][lane] = make_uint4(rec.xy0, (uint32_t)bw | ((uint32_t)b_first << 16), a.path_slot_off[pid],
-                                        MODE == 1 ? a.path_rec_base[pid] : 0u);
+          sh_path[w][lane] = make_uint4(rec.xy0, (uint32_t)bw | ((uint32_t)b_first << 16), a.path_slot_off[pid], pid);
         }
       }
     }
@@ -866,28 +883,115 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
     const int excl = incl - nb;
     __syncwarp();
     for (int k0 = 0; k0 < total; k0 += 32) {
+      // ---- level 1: lane <-> (edge, band) ----
       const int k = min(k0 + (int)lane, total - 1);
-      // owner = the last lane whose first item is <= k (lanes without items share their successor's start)
-      int o = 0;
+      int o = 0;  // owner = the last lane whose first item is <= k (lanes without items share their successor's start)
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1) {
         int v = __shfl_sync(0xffffffffu, excl, o + step);
         if (v <= k) o += step;
       }
       const int first = __shfl_sync(0xffffffffu, excl, o);
+      uint32_t nc = 0;
       if (k0 + (int)lane < total) {
         const int4 ed = sh_edge[w][o];
         const uint4 pp = sh_path[w][o];
-        const int b = (int)(pp.y >> 16) + (k - first);
         const int bx0 = pp.x & 0xffff, by0 = pp.x >> 16, bw = pp.y & 0xffff;
         const bool small = max(abs(ed.z - ed.x), abs(ed.w - ed.y)) <= kMaxLenFx;
-        if (small)
-          bin_band<MODE, true>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, pp.w, b);
-        else
-          bin_band<MODE, false>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, pp.w, b);
+        const int b = (int)(pp.y >> 16) + (k - first);
+        const BandPiece piece = small ? band_setup<true>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, b)
+                                      : band_setup<false>(a, ed.x, ed.y, ed.z, ed.w, bx0, by0, bw, pp.z, b);
+        if (piece.c1 >= piece.c0) {
+          nc = (uint32_t)(piece.c1 - piece.c0 + 1);
+          sh_piece[w][lane] = make_int4(piece.xs, piece.ys, piece.xe, piece.ye);
+          sh_pmeta[w][lane] = make_uint4((uint32_t)piece.c0, piece.row_base + (uint32_t)(piece.c0 - bx0), (uint32_t)piece.Yt,
+                                         pp.w | (small ? 0x80000000u : 0u));
+        }
       }
+      uint32_t cincl = nc;
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, cincl, o2);
+        if ((int)lane >= o2) cincl += t;
+      }
+      const uint32_t ctotal = __shfl_sync(0xffffffffu, cincl, 31);
+      if (ctotal == 0) continue;
+      const uint32_t cexcl = cincl - nc;
+      // ---- staging space for this round: one entry per (piece, column) ----
+      const uint32_t rem = kStageBlock - blk_used;  // room left in the current block
+      const uint32_t old_pos = blk * kStageBlock + blk_used;
+      uint32_t new_pos = 0;
+      if (ctotal > rem) {  // continue in freshly allocated block(s): one atomic for all of them
+        const uint32_t need = ctotal - rem, nblk = (need + kStageBlock - 1) / kStageBlock;
+        uint32_t first_blk = 0;
+        if (lane == 0) first_blk = atomicAdd(&a.totals->n_stage_blocks, nblk);
+        first_blk = __shfl_sync(0xffffffffu, first_blk, 0);
+        if (first_blk + nblk > cap_blocks) {
+          if (lane == 0) atomicOr(&a.totals->overflow_stage, 1u);
+          dead = true;
+        }
+        if (!dead && lane == 0) {
+          if (have_blk) a.stage_used[blk] = kStageBlock;
+          for (uint32_t q = 0; q + 1 < nblk; q++) a.stage_used[first_blk + q] = kStageBlock;
+        }
+        new_pos = first_blk * kStageBlock;
+        blk = first_blk + nblk - 1;
+        blk_used = need - (nblk - 1) * kStageBlock;
+        have_blk = true;
+      } else {
+        blk_used += ctotal;
+      }
+      __syncwarp();
+      // ---- level 2: lane <-> (piece, column) ----
+      for (uint32_t i0 = 0; i0 < ctotal; i0 += 32) {
+        const uint32_t idx = min(i0 + lane, ctotal - 1);
+        int o2 = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          uint32_t v = __shfl_sync(0xffffffffu, cexcl, o2 + step);
+          if (v <= idx) o2 += step;
+        }
+        const uint32_t cfirst = __shfl_sync(0xffffffffu, cexcl, o2);
+        if (i0 + lane < ctotal) {
+          const int4 pc = sh_piece[w][o2];
+          const uint4 pm = sh_pmeta[w][o2];
+          const uint32_t j = idx - cfirst;
+          unsigned long long rc;
+          const bool keep = (pm.w >> 31) ? column_record<true>(pc.x, pc.y, pc.z, pc.w, (int)pm.z, (int)(pm.x + j), rc)
+                                         : column_record<false>(pc.x, pc.y, pc.z, pc.w, (int)pm.z, (int)(pm.x + j), rc);
+          const uint32_t slot = pm.y + j;
+          if (keep) atomicAdd(&a.slot_count[slot], 1u);
+          if (!dead) {
+            // streaming store: staging is written once here and read once by k_scatter
+            const uint32_t pos = idx < rem ? old_pos + idx : new_pos + (idx - rem);
+            __stcs(a.stage + pos, make_uint4((uint32_t)rc, (uint32_t)(rc >> 32), keep ? slot : kStageInvalid, pm.w & 0x7fffffffu));
+          }
+        }
+      }
+      __syncwarp();
     }
     __syncwarp();
+  }
+  if (have_blk && !dead && lane == 0) a.stage_used[blk] = blk_used;
+}
+
+// K2, pass 2 of 2: staged records -> their slots.  slot_off holds the END of the slot's record range (relative to the
+// path's base); the counts of pass 1 double as cursors and run back down to zero (order inside a slot is irrelevant:
+// coverage accumulation is integer).
+__global__ void k_scatter(RenderArgs a) {
+  if (a.totals->overflow) return;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nblk = min(a.totals->n_stage_blocks, a.caps.stage / kStageBlock);
+  for (uint32_t b = warp; b < nblk; b += nwarps) {
+    const uint32_t used = a.stage_used[b];
+    const uint4 *st = a.stage + (size_t)b * kStageBlock;
+    for (uint32_t i = lane; i < used; i += 32) {
+      const uint4 e = __ldcs(st + i);
+      if (e.z == kStageInvalid) continue;
+      const uint32_t pos = a.path_rec_base[e.w] + a.slot_off[e.z] - atomicSub(&a.slot_count[e.z], 1u);
+      a.records[pos] = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+    }
   }
 }
 
@@ -1196,8 +1300,92 @@ __device__ __forceinline__ Probe probe_slot(const RenderArgs &a, uint32_t pid, b
   return pr;
 }
 
-__global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
-  if (a.totals->overflow) return;
+// 8-bit coverage masks m[0..7] of this lane's 8 pixels (row = lane & 15, columns (lane >> 4) * 8 ..) for one slot:
+// stages the slot's records [o0, o1) into the warp's 16x16 Q16 signed-area accumulator (shared-memory integer
+// atomics of prefix differences; crossings of the tile's left boundary go to a 17-entry column), then every lane
+// prefix-sums its 8 accumulators, applies the backdrop and the non-zero rule min(|sum|, 1), and clears what it read.
+__device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, uint32_t o1, int bd, int *acc, int *cross,
+                                              uint32_t lane, uint32_t m[8]) {
+  const int row = lane & 15, half = lane >> 4;
+  const uint32_t nrec = o1 - o0;
+  bool any_cross = false;
+  if (nrec >= 16) {
+    // many records: one lane per record, rows in a loop
+    for (uint32_t k = lane; k < nrec; k += 32) {
+      unsigned long long rc = __ldg(a.records + o0 + k);
+      int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff),
+          yb = (int)((rc >> 39) & 0x1fff);
+      int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
+      if (fs | fe) {
+        int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
+        int r0 = min(yc >> 8, 15);
+        int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
+        atomicAdd(&cross[r0], sgn * hq);
+        atomicAdd(&cross[r0 + 1], sgn * (65536 - hq));
+        any_cross = true;
+      }
+      if (ya != yb) {
+        int ylo = min(ya, yb), yhi = max(ya, yb);
+        for (int r = ylo >> 8; r <= ((yhi - 1) >> 8); r++) accumulate_row(xa, ya, xb, yb, r, acc + r * kAccStride);
+      }
+    }
+  } else {
+    // few records: one lane per (record, row)
+    for (uint32_t k = lane; k < nrec * 16; k += 32) {
+      unsigned long long rc = __ldg(a.records + o0 + (k >> 4));
+      int r = (int)(k & 15);
+      int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff),
+          yb = (int)((rc >> 39) & 0x1fff);
+      int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
+      if (fs | fe) {
+        int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
+        int r0 = min(yc >> 8, 15);
+        if (r == r0) {  // one lane per record posts the crossing term
+          int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
+          atomicAdd(&cross[r0], sgn * hq);
+          atomicAdd(&cross[r0 + 1], sgn * (65536 - hq));
+        }
+        any_cross = true;
+      }
+      if (ya != yb) accumulate_row(xa, ya, xb, yb, r, acc + r * kAccStride);
+    }
+  }
+  any_cross = __any_sync(0xffffffffu, any_cross);
+  __syncwarp();
+  // row prefix: 8 accumulators of this lane, carry from the left half
+  int v[8];
+  int4 q0 = *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8);
+  int4 q1 = *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8 + 4);
+  v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w, v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
+#pragma unroll
+  for (int i = 1; i < 8; i++) v[i] += v[i - 1];
+  int left = __shfl_sync(0xffffffffu, v[7], lane & 15);
+  int basev = bd * 65536 + (half ? left : 0);
+  if (any_cross) {
+    int cr = cross[lane & 15];
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, cr, o, 16);
+      if ((int)(lane & 15) >= o) cr += t;
+    }
+    basev += cr;
+  }
+  __syncwarp();
+  *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8) = make_int4(0, 0, 0, 0);
+  *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8 + 4) = make_int4(0, 0, 0, 0);
+  if (any_cross && lane < 20) cross[lane] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int sm = v[i] + basev;
+    sm = sm < 0 ? -sm : sm;
+    sm = min(sm, 65536);
+    m[i] = ((uint32_t)sm * 255u + 32768u) >> 16;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a) {
+  if (a.totals->overflow | a.totals->overflow_stage) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1216,31 +1404,82 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
     if (w >= total) break;
     uint32_t frame = w / tiles, tile = w - frame * tiles;
     int ty = (int)(tile / (uint32_t)a.tiles_x), tx = (int)(tile - (uint32_t)ty * a.tiles_x);
+    const int X0 = tx * kTile + half * 8, Y = ty * kTile + row;
     // candidates: the paint-ordered list of this tile's (row, column group)
     const uint32_t li = (frame * (uint32_t)a.tiles_y + (uint32_t)ty) * a.groups_x + (uint32_t)tx / kGroupTiles;
     const uint32_t p_begin = __ldg(a.list_off + li), p_end = __ldg(a.list_off + li + 1);
 
-    // ---- pass 1: the last opaque full-tile cover hides everything painted before it ----
+    // ---- pass 1, back to front, coverage of OPAQUE paints only: exact occlusion culling per pixel ----
+    // A pixel that an opaque paint covers completely (mask 255) shows nothing of what was painted before:
+    // need[i] = list position (relative to p_begin, saturated to 16 bits) of the last such path for pixel i, 0 if
+    // there is none.  The walk stops as soon as every pixel of the tile has one (an opaque full-tile cover does that
+    // at once).  Pass 2 starts at the smallest need[] and skips, per pixel, every path before need[i].
+    uint32_t need01 = 0, need23 = 0, need45 = 0, need67 = 0;  // 8 x 16 bits
+    uint32_t open = 0;  // bit i: pixel i has no opaque cover yet (pixels outside the frame never count)
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (Y < a.height && X0 + i < a.width) open |= 1u << i;
     uint32_t start = p_begin;
-    for (uint32_t hi = p_end; hi > p_begin;) {
-      uint32_t lo = hi - p_begin >= 32 ? hi - 32 : p_begin;
-      uint32_t idx = lo + lane;
-      uint32_t pid = idx < hi ? __ldg(a.list_items + idx) : 0u;
-      Probe pr = probe_slot(a, pid, idx < hi, tx, ty);
-      bool cover = pr.hit && pr.o1 == pr.o0 && ((pr.info >> 8) & 1u);
-      uint32_t mask = __ballot_sync(0xffffffffu, cover);
-      if (mask) {
-        start = lo + (31 - __clz(mask));
-        break;
+    {
+      bool all_done = __all_sync(0xffffffffu, open == 0);
+      for (uint32_t hi = p_end; hi > p_begin && !all_done;) {
+        uint32_t lo = hi - p_begin >= 32 ? hi - 32 : p_begin;
+        uint32_t idx = lo + lane;
+        uint32_t pid = idx < hi ? __ldg(a.list_items + idx) : 0u;
+        Probe pr = probe_slot(a, pid, idx < hi, tx, ty);
+        uint32_t mask = __ballot_sync(0xffffffffu, pr.hit && ((pr.info >> 8) & 1u));
+        while (mask && !all_done) {
+          int src_lane = 31 - __clz(mask);
+          mask &= ~(1u << src_lane);
+          uint32_t o0 = __shfl_sync(0xffffffffu, pr.o0, src_lane);
+          uint32_t o1 = __shfl_sync(0xffffffffu, pr.o1, src_lane);
+          int bd = __shfl_sync(0xffffffffu, pr.bd, src_lane);
+          const uint32_t rel = min(lo + (uint32_t)src_lane - p_begin, 65535u);
+          uint32_t cov = 0xffu;  // bit i: pixel i is covered completely
+          if (o1 != o0) {
+            uint32_t m[8];
+            slot_coverage(a, o0, o1, bd, acc, cross, lane, m);
+            cov = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) cov |= (m[i] == 255u ? 1u : 0u) << i;
+          }
+          const uint32_t fresh = cov & open;
+          if (fresh) {
+            if (fresh & 0x01u) need01 = (need01 & 0xffff0000u) | rel;
+            if (fresh & 0x02u) need01 = (need01 & 0x0000ffffu) | (rel << 16);
+            if (fresh & 0x04u) need23 = (need23 & 0xffff0000u) | rel;
+            if (fresh & 0x08u) need23 = (need23 & 0x0000ffffu) | (rel << 16);
+            if (fresh & 0x10u) need45 = (need45 & 0xffff0000u) | rel;
+            if (fresh & 0x20u) need45 = (need45 & 0x0000ffffu) | (rel << 16);
+            if (fresh & 0x40u) need67 = (need67 & 0xffff0000u) | rel;
+            if (fresh & 0x80u) need67 = (need67 & 0x0000ffffu) | (rel << 16);
+            open &= ~fresh;
+          }
+          all_done = __all_sync(0xffffffffu, open == 0);
+        }
+        hi = lo;
       }
-      hi = lo;
+      // first list position any pixel still needs (pixels outside the frame do not count)
+      uint32_t mn = 0xffffffffu;
+      if (Y < a.height) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (X0 + i < a.width) {
+            const uint32_t nd = ((i & 1) ? ((i < 2 ? need01 : i < 4 ? need23 : i < 6 ? need45 : need67) >> 16)
+                                         : ((i < 2 ? need01 : i < 4 ? need23 : i < 6 ? need45 : need67) & 0xffffu));
+            mn = min(mn, nd);
+          }
+        }
+      }
+      mn = __reduce_min_sync(0xffffffffu, mn);
+      start = mn == 0xffffffffu ? p_end : p_begin + mn;
+      if (mn == 65535u) start = p_begin + 65535u;  // saturated: everything from there on is needed anyway
     }
 
-    // ---- pass 2: composite in paint order ----
+    // ---- pass 2, front to back... in paint order: composite ----
     uint32_t px[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) px[i] = 0;
-    const int X0 = tx * kTile + half * 8, Y = ty * kTile + row;
     for (uint32_t base = start; base < p_end; base += 32) {
       uint32_t idx = base + lane;
       uint32_t pid = idx < p_end ? __ldg(a.list_items + idx) : 0u;
@@ -1249,6 +1488,18 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
       while (mask) {
         int src_lane = __ffs(mask) - 1;
         mask &= mask - 1;
+        // pixels of this lane that still show this path (list position >= need[i])
+        const uint32_t rel = min(base + (uint32_t)src_lane - p_begin, 65535u);
+        uint32_t vis = 0;
+        vis |= (rel >= (need01 & 0xffffu) ? 1u : 0u) << 0;
+        vis |= (rel >= (need01 >> 16) ? 1u : 0u) << 1;
+        vis |= (rel >= (need23 & 0xffffu) ? 1u : 0u) << 2;
+        vis |= (rel >= (need23 >> 16) ? 1u : 0u) << 3;
+        vis |= (rel >= (need45 & 0xffffu) ? 1u : 0u) << 4;
+        vis |= (rel >= (need45 >> 16) ? 1u : 0u) << 5;
+        vis |= (rel >= (need67 & 0xffffu) ? 1u : 0u) << 6;
+        vis |= (rel >= (need67 >> 16) ? 1u : 0u) << 7;
+        if (!__any_sync(0xffffffffu, vis != 0)) continue;  // hidden in every pixel of the tile
         uint32_t o0 = __shfl_sync(0xffffffffu, pr.o0, src_lane);
         uint32_t o1 = __shfl_sync(0xffffffffu, pr.o1, src_lane);
         int bd = __shfl_sync(0xffffffffu, pr.bd, src_lane);
@@ -1261,82 +1512,11 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
 #pragma unroll
           for (int i = 0; i < 8; i++) m[i] = 255u;
         } else {
-          uint32_t nrec = o1 - o0;
-          bool any_cross = false;
-          if (nrec >= 16) {
-            // many records: one lane per record, rows in a loop
-            for (uint32_t k = lane; k < nrec; k += 32) {
-              unsigned long long rc = __ldg(a.records + o0 + k);
-              int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff),
-                  yb = (int)((rc >> 39) & 0x1fff);
-              int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
-              if (fs | fe) {
-                int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
-                int r0 = min(yc >> 8, 15);
-                int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
-                atomicAdd(&cross[r0], sgn * hq);
-                atomicAdd(&cross[r0 + 1], sgn * (65536 - hq));
-                any_cross = true;
-              }
-              if (ya != yb) {
-                int ylo = min(ya, yb), yhi = max(ya, yb);
-                for (int r = ylo >> 8; r <= ((yhi - 1) >> 8); r++) accumulate_row(xa, ya, xb, yb, r, acc + r * kAccStride);
-              }
-            }
-          } else {
-            // few records: one lane per (record, row)
-            for (uint32_t k = lane; k < nrec * 16; k += 32) {
-              unsigned long long rc = __ldg(a.records + o0 + (k >> 4));
-              int r = (int)(k & 15);
-              int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff),
-                  yb = (int)((rc >> 39) & 0x1fff);
-              int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
-              if (fs | fe) {
-                int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
-                int r0 = min(yc >> 8, 15);
-                if (r == r0) {  // one lane per record posts the crossing term
-                  int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
-                  atomicAdd(&cross[r0], sgn * hq);
-                  atomicAdd(&cross[r0 + 1], sgn * (65536 - hq));
-                }
-                any_cross = true;
-              }
-              if (ya != yb) accumulate_row(xa, ya, xb, yb, r, acc + r * kAccStride);
-            }
-          }
-          any_cross = __any_sync(0xffffffffu, any_cross);
-          __syncwarp();
-          // row prefix: 8 accumulators of this lane, carry from the left half
-          int v[8];
-          int4 q0 = *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8);
-          int4 q1 = *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8 + 4);
-          v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w, v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
-#pragma unroll
-          for (int i = 1; i < 8; i++) v[i] += v[i - 1];
-          int left = __shfl_sync(0xffffffffu, v[7], lane & 15);
-          int basev = bd * 65536 + (half ? left : 0);
-          if (any_cross) {
-            int cr = cross[lane & 15];
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-              int t = __shfl_up_sync(0xffffffffu, cr, o, 16);
-              if ((lane & 15) >= o) cr += t;
-            }
-            basev += cr;
-          }
-          __syncwarp();
-          *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8) = make_int4(0, 0, 0, 0);
-          *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8 + 4) = make_int4(0, 0, 0, 0);
-          if (any_cross && lane < 20) cross[lane] = 0;
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            int s = v[i] + basev;
-            s = s < 0 ? -s : s;
-            s = min(s, 65536);
-            m[i] = ((uint32_t)s * 255u + 32768u) >> 16;
-          }
-          __syncwarp();
+          slot_coverage(a, o0, o1, bd, acc, cross, lane, m);
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (!((vis >> i) & 1u)) m[i] = 0;
         // ---- paint + blend ----
         if (type == PAINT_SOLID) {
 #pragma unroll
@@ -1483,7 +1663,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   mark(4);
   if (a.n_seginst) {
-    k_bin<0><<<wide, kBinWarps * 32, 0, st>>>(a);
+    k_bin<<<wide, kBinWarps * 32, 0, st>>>(a);
     launches++;
   }
   mark(5);
@@ -1497,7 +1677,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
            &a.totals->overflow, 4u, st, launches);
   mark(6);
   if (a.n_seginst) {
-    k_bin<1><<<wide, kBinWarps * 32, 0, st>>>(a);
+    k_scatter<<<wide, T, 0, st>>>(a);
     launches++;
   }
   mark(7);

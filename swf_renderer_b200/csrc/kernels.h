@@ -14,6 +14,7 @@ constexpr int kTileFx = 4096;      // 16 px in 1/256 px
 constexpr int kMaxLenFx = 16384;   // flattened edges span at most 64 px per axis
 constexpr int kNumSM = 148;        // B200
 constexpr int kGroupTiles = 8;     // tile columns per candidate list (128 px)
+constexpr int kStageBlock = 256;   // staging entries per block (blocks are private to one warp of the binning pass)
 constexpr int kBackdropSmall = 1024;  // grids up to this many slots get their backdrop prefix from one warp
 
 // One draw item after host flattening of the stage: 48 bytes.
@@ -61,11 +62,13 @@ struct Totals {
   uint32_t n_list;    // candidate-list entries
   uint32_t n_big;     // path instances whose tile grid is larger than kBackdropSmall
   uint32_t n_rowent;  // row-list entries
-  uint32_t pad[3];
+  uint32_t n_stage_blocks;  // staging blocks handed out by the binning pass
+  uint32_t overflow_stage;  // the staging buffer was too small (found while binning, after the scans)
+  uint32_t pad[1];
 };
 
 struct Caps {
-  uint32_t edges, slots, records, list, rows;
+  uint32_t edges, slots, records, list, rows, stage;  // stage: entries, a multiple of the staging block size
 };
 
 // Everything a render launch needs (device pointers unless noted).
@@ -94,6 +97,8 @@ struct RenderArgs {
   int32_t *slot_backdrop;   // caps.slots
   uint32_t *slot_off;       // caps.slots + 1: end of the slot's record range, relative to path_rec_base
   unsigned long long *records;  // caps.records
+  uint4 *stage;             // caps.stage: (record lo, record hi, slot, path instance) in binning order
+  uint32_t *stage_used;     // caps.stage / 256: entries used in each staging block
   uint32_t *frames;         // n_frames * width * height
   uint32_t *scan_tmp;       // >= 4096 words
   // candidate lists: for every (frame, tile row, group of kGroupTiles tile columns) the path instances whose

@@ -136,8 +136,8 @@ struct swfr_renderer {
 
   // ---- working memory ----
   DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_items, big_list, row_count, row_off, row_items;
-  Caps caps{0, 0, 0, 0, 0};
+      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used;
+  Caps caps{0, 0, 0, 0, 0, 0};
   PinnedBuf pin_totals;
   swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
   int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
@@ -423,6 +423,12 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
   want.list = std::max<uint32_t>(want.list, std::max<uint32_t>(1u << 16, max_paths * 12));
   want.rows = std::max<uint32_t>(want.rows, std::max<uint32_t>(1u << 16, max_paths * 8));
+  // staging: the records, plus one partly filled block per binning warp (at most kNumSM * 16 * 8 warps, one per 32 edges)
+  {
+    uint64_t warps = std::min<uint64_t>((uint64_t)kNumSM * 16 * 8, (uint64_t)want.edges / 32 + 1);
+    uint64_t st = (uint64_t)want.records + want.records / 4 + warps * kStageBlock + 65535u;
+    want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(st & ~255ull, 0xffffff00ull));
+  }
   uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   size_t max_lists = (size_t)std::max<uint32_t>(1, r->frames_per_pass) * r->tiles_y * groups_x;
   for (const Pass &p : b.passes) max_lists = std::max(max_lists, (size_t)p.n_frames * r->tiles_y * groups_x);
@@ -438,6 +444,8 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   CK(r->slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
   CK(r->slot_off.reserve(((size_t)want.slots + 1) * 4));
   CK(r->records.reserve((size_t)want.records * 8));
+  CK(r->stage.reserve((size_t)want.stage * 16));
+  CK(r->stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
   r->caps = want;
   return SWFR_OK;
 }
@@ -474,6 +482,8 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.slot_backdrop = r->slot_backdrop.as<int32_t>();
   a.slot_off = r->slot_off.as<uint32_t>();
   a.records = r->records.as<unsigned long long>();
+  a.stage = r->stage.as<uint4>();
+  a.stage_used = r->stage_used.as<uint32_t>();
   a.frames = r->frames.as<uint32_t>() + (size_t)p.f0 * r->width * r->height;
   a.scan_tmp = r->scan_tmp.as<uint32_t>();
   a.groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
@@ -548,8 +558,8 @@ int finish(swfr_renderer *r) {
   bool rerun = false;
   for (size_t i = 0; i < np; i++) {
     int guard = 0;
-    while (r->last_totals[i].overflow) {
-      if (++guard > 6) return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
+    while (r->last_totals[i].overflow | r->last_totals[i].overflow_stage) {
+      if (++guard > 8) return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
       const Totals &t = r->last_totals[i];
       Caps want = r->caps;
       auto grow = [](uint32_t need) { return (uint32_t)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0xfffffff0ull); };
@@ -561,6 +571,13 @@ int finish(swfr_renderer *r) {
       CK(r->list_items.reserve((size_t)want.list * 4));
       CK(r->row_items.reserve((size_t)want.rows * 8));
       if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
+      if (t.overflow_stage) {
+        uint64_t need = ((uint64_t)t.n_stage_blocks + t.n_stage_blocks / 8 + 64) * 256;
+        want.stage = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want.stage, need), 0xffffff00ull);
+      }
+      want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
+      CK(r->stage.reserve((size_t)want.stage * 16));
+      CK(r->stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
       CK(r->edges.reserve((size_t)want.edges * 16));
       CK(r->edge_pid.reserve((size_t)want.edges * 4));
       CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
