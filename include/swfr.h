@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SWFR_ABI_VERSION 1
+#define SWFR_ABI_VERSION 2
 
 typedef enum swfr_status {
   SWFR_OK = 0,
@@ -158,9 +158,12 @@ typedef struct swfr_display_primitive {
   uint32_t id;     /* ShapeId / MorphShapeId returned by swfr_register_* */
   float matrix[6]; /* Matrix2D: [scale_x, scale_y, rotate_skew0, rotate_skew1, translate_x, translate_y];
                       x' = m0*x + m3*y + m4, y' = m2*x + m1*y + m5 (twips) */
-  uint16_t ratio;  /* MorphRatio: 0 = start, 65535 = end */
-  uint16_t reserved;
+  uint16_t ratio;  /* MorphRatio (rs/src/stage.rs:28-34): 0 = start, 65535 = end; the lerp factor is ratio / 65535 */
+  uint16_t flags;  /* SWFR_PRIM_RATIO_F32: ratio_f replaces ratio */
+  float ratio_f;   /* the TypeScript renderer's MorphShape.ratio, a number in 0..1 (ts/src/lib/display/morph-shape.ts:5-10,
+                      canvas-renderer.ts:190-205); lets a caller ask for exactly 0.5 */
 } swfr_display_primitive;
+#define SWFR_PRIM_RATIO_F32 1u
 
 typedef struct swfr_stage {
   swfr_rgba8 background_color; /* carried; the reference TS renderer ignores it (canvas-renderer.ts:70-72) */

@@ -64,6 +64,8 @@ typedef struct {
   int32_t def;
   float m[6];     /* Matrix2D order: scale_x, scale_y, rotate_skew0, rotate_skew1, tx, ty  (rs/src/stage.rs:12-20) */
   uint16_t ratio; /* MorphRatio (rs/src/stage.rs:28-34) */
+  uint16_t use_ratio_f; /* != 0: ratio_f (the TypeScript renderer's number in 0..1, display/morph-shape.ts) replaces ratio */
+  float ratio_f;
 } swfo_item;
 
 typedef struct {
@@ -609,7 +611,7 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
     double m0[6], m[6];
     for (int i = 0; i < 6; i++) m0[i] = (double)item->m[i];
     ctm_from_matrix(m0, m);
-    double ratio = (double)item->ratio / 65535.0;
+    double ratio = item->use_ratio_f ? (double)item->ratio_f : (double)item->ratio / 65535.0;
     for (int lp = 0; lp < def->n_path; lp++, path_inst++) {
       /* ---- flatten this path's segments ---- */
       size_t ne = 0;

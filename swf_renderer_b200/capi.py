@@ -20,6 +20,7 @@ SPREAD_PAD, SPREAD_REFLECT, SPREAD_REPEAT = 0, 1, 2
 COLOR_SRGB, COLOR_LINEAR_RGB = 0, 1
 RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
 PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
+PRIM_RATIO_F32 = 1
 OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS = 1, 2, 3, 4
 
 
@@ -125,7 +126,8 @@ class DisplayPrimitive(C.Structure):
         ("id", C.c_uint32),
         ("matrix", C.c_float * 6),
         ("ratio", C.c_uint16),
-        ("reserved", C.c_uint16),
+        ("flags", C.c_uint16),
+        ("ratio_f", C.c_float),
     ]
 
 

@@ -337,6 +337,13 @@ int compile_definition(const swfr_define_shape *tag, bool morph, CompiledDef &ou
         // stroke geometry depends on the ratio; it is expanded per draw (see renderer).  A stroke whose
         // colour is fully transparent in both states composites nothing.
         if (cp.line.fill.color.a != 0 || cp.line.fill.morph_color.a != 0) out.has_visible_morph_stroke = true;
+        MorphLine ml;
+        ml.commands = cp.commands;
+        ml.w0 = (double)cp.line.width;
+        ml.w1 = (double)cp.line.morph_width;
+        memcpy(ml.color0, &cp.line.fill.color, 4);
+        memcpy(ml.color1, &cp.line.fill.morph_color, 4);
+        out.morph_lines.push_back(std::move(ml));
         continue;
       }
       if (cp.line.width > 0) width_state = (double)cp.line.width;

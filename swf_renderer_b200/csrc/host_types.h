@@ -65,6 +65,14 @@ struct CompiledPath {
   std::vector<swfr_color_stop> stops;  // owned copy of the gradient stops
 };
 
+// A line path of a morph shape: its outline depends on the ratio (lerped path, lerped width, round caps and joins;
+// canvas-renderer.ts:252-266), so it is expanded per draw, not at registration.
+struct MorphLine {
+  std::vector<Command> commands;  // start + end state
+  double w0 = 0, w1 = 0;          // width in twips, start / end
+  uint8_t color0[4] = {0, 0, 0, 0}, color1[4] = {0, 0, 0, 0};
+};
+
 struct CompiledDef {
   bool is_morph = false;
   std::vector<CompiledPath> paths;       // reference order: per layer fills then lines
@@ -73,6 +81,8 @@ struct CompiledDef {
   std::vector<DefPaint> paints;          // one per emitted device path
   std::vector<std::vector<float>> luts;  // ramps referenced by paints[].lut (local indices)
   bool has_visible_morph_stroke = false;
+  std::vector<MorphLine> morph_lines;    // every line path of a morph shape, in paint order (also invisible ones:
+                                         // a zero width keeps the previous one, canvas-renderer.ts:253-256)
 };
 
 // Compiles records into ordered style paths and the device segment/paint form.

@@ -24,9 +24,16 @@ struct DrawItem {
   uint32_t paint_first; // first DefPaint of the definition
   uint32_t path_off;    // first path instance of this item
   uint32_t frame;       // frame index within the batch
-  uint16_t ratio;
-  uint16_t is_morph;
-  uint32_t pad;
+  uint16_t ratio;       // MorphRatio (rs/src/stage.rs:28-34): ratio / 65535
+  uint16_t kind;        // ITEM_STATIC / ITEM_MORPH / ITEM_DYNAMIC, | ITEM_RATIO_F32 when ratio_f32 replaces ratio
+  float ratio_f32;      // the TypeScript renderer's ratio (a number in 0..1, morph-shape.ts:5-10)
+};
+enum : uint16_t {
+  ITEM_STATIC = 0,   // segments in the static store, paints in the definition paint store
+  ITEM_MORPH = 1,    // start/end segments in the morph store
+  ITEM_DYNAMIC = 2,  // segments and paints in the batch's own stores (morph-shape strokes expanded for this draw)
+  ITEM_KIND_MASK = 0xff,
+  ITEM_RATIO_F32 = 0x100
 };
 
 // Per path instance, read by binning and by the fine kernel: 16 bytes.
@@ -82,6 +89,8 @@ struct RenderArgs {
   const SegStatic *segs_static;
   const SegMorph *segs_morph;
   const DefPaint *def_paints;
+  const SegStatic *segs_dynamic;   // per batch (ITEM_DYNAMIC)
+  const DefPaint *paints_dynamic;  // per batch (ITEM_DYNAMIC)
   const float *ramps;
   const BitmapDev *bitmaps;
   uint32_t *seg_edge_off;   // n_seginst + 1 (piece counts, then exclusive scan)

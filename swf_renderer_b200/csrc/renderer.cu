@@ -103,7 +103,9 @@ struct swfr_batch {
   std::vector<Pass> passes;
   PinnedArr<DrawItem> items;
   PinnedArr<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
-  DevBuf d_items, d_seg_off, d_path_off, d_frame_off;
+  PinnedArr<SegStatic> dyn_segs;                     // outlines of morph-shape strokes expanded for this batch's draws
+  PinnedArr<DefPaint> dyn_paints;
+  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints;
   bool resident = false;
   uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
   cudaEvent_t uploaded = nullptr;  // recorded on the upload stream after the H2D copies
@@ -127,7 +129,7 @@ struct swfr_renderer {
   std::vector<DefPaint> h_paints;
   std::vector<float> h_ramps;
   std::vector<DefEntry> shape_defs, morph_defs;
-  std::vector<uint8_t> morph_has_stroke;
+  std::vector<std::shared_ptr<std::vector<MorphLine>>> morph_strokes;  // non-null: the morph shape has visible strokes
   std::vector<std::unique_ptr<CompiledDef>> shape_dbg, morph_dbg;
   DevBuf d_static, d_morph, d_paints, d_ramps, d_bitmaps;
   size_t up_static = 0, up_morph = 0, up_paints = 0, up_ramps = 0;  // elements already uploaded
@@ -217,10 +219,57 @@ int flush_store(swfr_renderer *r) {
   return SWFR_OK;
 }
 
+static inline double lerp_host(double start, double end, double r) {  // canvas-renderer.ts:24-26
+  double a = end * r;
+  double b = 1.0 - r;
+  double c = start * b;
+  return a + c;
+}
+
+// Outlines of the line paths of a morph shape at ratio r (canvas-renderer.ts:252-266: lerped path and width, round
+// caps and joins, a zero width keeps the previous one), as a transient static definition: one solid paint (its
+// colour still morphs on the device) and its fill segments per visible line.
+static void expand_morph_strokes(const std::vector<MorphLine> &lines, double r, std::vector<SegStatic> &segs,
+                                 std::vector<DefPaint> &paints) {
+  double width_state = 1.0;
+  std::vector<Command> cmds;
+  std::vector<StrokeSeg> ss;
+  for (const MorphLine &ml : lines) {
+    double w = lerp_host(ml.w0, ml.w1, r);
+    if (w > 0) width_state = w;
+    double al = lerp_host(ml.color0[3] / 255.0, ml.color1[3] / 255.0, r);
+    if (al <= 0) continue;  // composites nothing
+    cmds.clear();
+    for (const Command &c : ml.commands) {
+      Command o;
+      o.type = c.type;
+      for (int k = 0; k < 4; k++) o.s[k] = o.e[k] = lerp_host(c.s[k], c.e[k], r);
+      cmds.push_back(o);
+    }
+    ss.clear();
+    stroke_commands(cmds, width_state, true, ss);
+    uint32_t path = (uint32_t)paints.size();
+    DefPaint p{};
+    p.type = PAINT_SOLID;
+    p.lut = -1;
+    memcpy(p.color0, ml.color0, 4);
+    memcpy(p.color1, ml.color1, 4);
+    p.flags |= PF_COLOR_MORPH;
+    paints.push_back(p);
+    for (const StrokeSeg &sg : ss) {
+      SegStatic g;
+      memcpy(g.p, sg.p, sizeof g.p);
+      g.path_flags = path | (sg.curve ? 0x80000000u : 0u);
+      segs.push_back(g);
+    }
+  }
+}
+
 // Flattens stages into draw items (reference: CanvasRenderer.renderStage / drawDisplayObject,
 // ts/src/lib/renderers/canvas-renderer.ts:69-94) and splits them into passes.  Two sweeps over the stages, both
-// parallel over frames: (1) validate ids and count segment / path instances per frame, (2) after a prefix over the
-// frames of each pass, write the draw items and their offsets straight into the batch's pinned arrays.
+// parallel over frames: (1) validate ids, count segment / path instances per frame and expand the strokes of morph
+// shapes for their ratio, (2) after a prefix over the frames of each pass, write the draw items and their offsets
+// straight into the batch's pinned arrays.
 int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_batch &b) {
   b.n_frames = n;
   b.passes.clear();
@@ -233,15 +282,21 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
       return fail(r, SWFR_ERR_INVALID_ARGUMENT, "stage.display_root is NULL");
     total_prims += stages[f].n_primitives;
   }
-  if (total_prims > 0xfffffff0ull) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "too many display primitives");
+  if (total_prims > 0x7ffffff0ull) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "too many display primitives");
   uint32_t nt = r->host_threads ? r->host_threads : std::min<uint32_t>(8, std::max(1u, std::thread::hardware_concurrency()));
   nt = std::max<uint32_t>(1, std::min<uint32_t>(nt, n));
   if (total_prims < 20000) nt = 1;
 
+  struct DynItem {  // stroke outlines of one morph primitive
+    uint32_t prim, seg_at, seg_count, paint_at, paint_count;
+  };
   struct FrameSum {
-    uint64_t seg = 0, path = 0;
+    uint64_t seg = 0, path = 0, items = 0;
     int err = SWFR_OK;
     uint32_t bad_id = 0;
+    std::vector<DynItem> dyn;
+    std::vector<SegStatic> dyn_segs;
+    std::vector<DefPaint> dyn_paints;
   };
   std::vector<FrameSum> sums(n);
   auto lookup = [&](const swfr_display_primitive &pr, int &err) -> const DefEntry * {
@@ -257,14 +312,13 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         err = SWFR_ERR_INVALID_ID;
         return nullptr;
       }
-      if (r->morph_has_stroke[pr.id]) {
-        err = SWFR_ERR_UNSUPPORTED_STYLE;
-        return nullptr;
-      }
       return &r->morph_defs[pr.id];
     }
     err = SWFR_ERR_INVALID_ARGUMENT;
     return nullptr;
+  };
+  auto prim_ratio = [](const swfr_display_primitive &pr) -> double {
+    return (pr.flags & SWFR_PRIM_RATIO_F32) ? (double)pr.ratio_f : (double)pr.ratio / 65535.0;
   };
   auto run = [&](auto &&fn) {
     if (nt == 1) {
@@ -281,32 +335,47 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
       FrameSum &s = sums[f];
       const swfr_stage &st = stages[f];
       for (uint32_t i = 0; i < st.n_primitives; i++) {
+        const swfr_display_primitive &pr = st.display_root[i];
         int err = SWFR_OK;
-        const DefEntry *de = lookup(st.display_root[i], err);
+        const DefEntry *de = lookup(pr, err);
         if (!de) {
           s.err = err;
-          s.bad_id = st.display_root[i].id;
+          s.bad_id = pr.id;
           break;
         }
         s.seg += de->seg_count;
         s.path += de->path_count;
+        s.items += 1;
+        if (pr.kind == SWFR_PRIM_MORPH_SHAPE && r->morph_strokes[pr.id]) {
+          DynItem d;
+          d.prim = i;
+          d.seg_at = (uint32_t)s.dyn_segs.size();
+          d.paint_at = (uint32_t)s.dyn_paints.size();
+          expand_morph_strokes(*r->morph_strokes[pr.id], prim_ratio(pr), s.dyn_segs, s.dyn_paints);
+          d.seg_count = (uint32_t)s.dyn_segs.size() - d.seg_at;
+          d.paint_count = (uint32_t)s.dyn_paints.size() - d.paint_at;
+          if (d.paint_count) {
+            s.dyn.push_back(d);
+            s.seg += d.seg_count;
+            s.path += d.paint_count;
+            s.items += 1;
+          }
+        }
       }
     }
   });
   for (uint32_t f = 0; f < n; f++) {
     if (sums[f].err == SWFR_ERR_INVALID_ID) return fail(r, SWFR_ERR_INVALID_ID, "unknown shape id " + std::to_string(sums[f].bad_id));
-    if (sums[f].err == SWFR_ERR_UNSUPPORTED_STYLE)
-      return fail(r, SWFR_ERR_UNSUPPORTED_STYLE, "morph shapes with visible strokes are not supported yet");
     if (sums[f].err != SWFR_OK) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown display primitive kind");
   }
 
   // pass layout + per-frame bases
   struct FrameBase {
-    size_t item_at, seg_off_at, path_off_at, frame_off_at;
+    size_t item_at, seg_off_at, path_off_at, frame_off_at, dyn_seg_at, dyn_paint_at;
     uint32_t seg0, path0;
   };
   std::vector<FrameBase> base(n);
-  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0;
+  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0, dyn_seg_at = 0, dyn_paint_at = 0;
   for (uint32_t f0 = 0; f0 < n; f0 += fpp) {
     Pass p;
     p.f0 = f0;
@@ -319,12 +388,14 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     size_t it_run = 0;
     for (uint32_t f = f0; f < f0 + p.n_frames; f++) {
       base[f] = FrameBase{items_at + it_run, seg_off_at + it_run, path_off_at + it_run, frame_off_at + (f - f0),
-                          (uint32_t)seg_run, (uint32_t)path_run};
+                          dyn_seg_at,        dyn_paint_at,        (uint32_t)seg_run,    (uint32_t)path_run};
       seg_run += sums[f].seg;
       path_run += sums[f].path;
-      it_run += stages[f].n_primitives;
+      it_run += sums[f].items;
+      dyn_seg_at += sums[f].dyn_segs.size();
+      dyn_paint_at += sums[f].dyn_paints.size();
     }
-    if (seg_run > 0xfffffff0ull || path_run > 0xfffffff0ull)
+    if (seg_run > 0xfffffff0ull || path_run > 0xfffffff0ull || it_run > 0xfffffff0ull)
       return fail(r, SWFR_ERR_INVALID_ARGUMENT, "a pass exceeds 2^32 segment instances; lower SWFR_OPT_FRAMES_PER_PASS");
     p.n_items = (uint32_t)it_run;
     p.n_seginst = (uint32_t)seg_run;
@@ -333,15 +404,18 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     seg_off_at += it_run + 1;
     path_off_at += it_run + 1;
     frame_off_at += p.n_frames + 1;
-    b.n_prims += p.n_items;
     b.n_seginst += seg_run;
     b.n_paths += path_run;
     b.passes.push_back(p);
   }
+  if (dyn_seg_at > 0xfffffff0ull) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "too many stroke segments in one batch");
+  b.n_prims = total_prims;
   CK(b.items.resize(items_at));
   CK(b.seg_off.resize(seg_off_at));
   CK(b.path_off.resize(path_off_at));
   CK(b.frame_off.resize(frame_off_at));
+  CK(b.dyn_segs.resize(dyn_seg_at));
+  CK(b.dyn_paints.resize(dyn_paint_at));
   for (const Pass &p : b.passes) {  // closing entries of each pass
     b.seg_off[p.seg_off_at + p.n_items] = p.n_seginst;
     b.path_off[p.path_off_at + p.n_items] = p.n_paths;
@@ -351,11 +425,16 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     for (uint32_t f = t; f < n; f += nt) {
       const swfr_stage &st = stages[f];
       const FrameBase &fb = base[f];
+      const FrameSum &fs = sums[f];
       DrawItem *items = b.items.data() + fb.item_at;
       uint32_t *so = b.seg_off.data() + fb.seg_off_at, *po = b.path_off.data() + fb.path_off_at;
       uint32_t seg_run = fb.seg0, path_run = fb.path0;
       b.frame_off[fb.frame_off_at] = path_run;
       const uint32_t local_frame = f % fpp;
+      if (!fs.dyn_segs.empty()) memcpy(b.dyn_segs.data() + fb.dyn_seg_at, fs.dyn_segs.data(), fs.dyn_segs.size() * sizeof(SegStatic));
+      if (!fs.dyn_paints.empty())
+        memcpy(b.dyn_paints.data() + fb.dyn_paint_at, fs.dyn_paints.data(), fs.dyn_paints.size() * sizeof(DefPaint));
+      size_t k = 0, next_dyn = 0;
       for (uint32_t i = 0; i < st.n_primitives; i++) {
         const swfr_display_primitive &pr = st.display_root[i];
         int err = SWFR_OK;
@@ -367,13 +446,27 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         it.path_off = path_run;
         it.frame = local_frame;
         it.ratio = pr.ratio;
-        it.is_morph = (uint16_t)de->is_morph;
-        it.pad = 0;
-        items[i] = it;
-        so[i] = seg_run;
-        po[i] = path_run;
+        it.kind = (uint16_t)((de->is_morph ? ITEM_MORPH : ITEM_STATIC) | ((pr.flags & SWFR_PRIM_RATIO_F32) ? ITEM_RATIO_F32 : 0));
+        it.ratio_f32 = pr.ratio_f;
+        items[k] = it;
+        so[k] = seg_run;
+        po[k] = path_run;
+        k++;
         seg_run += de->seg_count;
         path_run += de->path_count;
+        if (next_dyn < fs.dyn.size() && fs.dyn[next_dyn].prim == i) {  // the primitive's strokes, painted after its fills
+          const DynItem &d = fs.dyn[next_dyn++];
+          it.seg_first = (uint32_t)(fb.dyn_seg_at + d.seg_at);
+          it.paint_first = (uint32_t)(fb.dyn_paint_at + d.paint_at);
+          it.path_off = path_run;
+          it.kind = (uint16_t)(ITEM_DYNAMIC | ((pr.flags & SWFR_PRIM_RATIO_F32) ? ITEM_RATIO_F32 : 0));
+          items[k] = it;
+          so[k] = seg_run;
+          po[k] = path_run;
+          k++;
+          seg_run += d.seg_count;
+          path_run += d.paint_count;
+        }
       }
     }
   });
@@ -395,6 +488,11 @@ int upload_batch(swfr_renderer *r, swfr_batch &b) {
   if (b.path_off.bytes()) CK(cudaMemcpyAsync(b.d_path_off.p, b.path_off.data(), b.path_off.bytes(), cudaMemcpyHostToDevice, st));
   if (b.frame_off.bytes())
     CK(cudaMemcpyAsync(b.d_frame_off.p, b.frame_off.data(), b.frame_off.bytes(), cudaMemcpyHostToDevice, st));
+  CK(b.d_dyn_segs.reserve(std::max<size_t>(b.dyn_segs.bytes(), 256)));
+  CK(b.d_dyn_paints.reserve(std::max<size_t>(b.dyn_paints.bytes(), 256)));
+  if (b.dyn_segs.bytes()) CK(cudaMemcpyAsync(b.d_dyn_segs.p, b.dyn_segs.data(), b.dyn_segs.bytes(), cudaMemcpyHostToDevice, st));
+  if (b.dyn_paints.bytes())
+    CK(cudaMemcpyAsync(b.d_dyn_paints.p, b.dyn_paints.data(), b.dyn_paints.bytes(), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(b.uploaded, st));
   b.resident = true;
   return SWFR_OK;
@@ -467,6 +565,8 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.segs_static = r->d_static.as<SegStatic>();
   a.segs_morph = r->d_morph.as<SegMorph>();
   a.def_paints = r->d_paints.as<DefPaint>();
+  a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
+  a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
   a.ramps = r->d_ramps.as<float>();
   a.bitmaps = r->d_bitmaps.as<BitmapDev>();
   a.seg_edge_off = r->seg_edge_off.as<uint32_t>();
@@ -655,7 +755,9 @@ int register_def(swfr_renderer *r, const swfr_define_shape *tag, bool morph, uin
     r->h_morph.insert(r->h_morph.end(), def->segs.begin(), def->segs.end());
     *out_id = (uint32_t)r->morph_defs.size();
     r->morph_defs.push_back(de);
-    r->morph_has_stroke.push_back(def->has_visible_morph_stroke ? 1 : 0);
+    r->morph_strokes.push_back(def->has_visible_morph_stroke
+                                   ? std::make_shared<std::vector<MorphLine>>(std::move(def->morph_lines))
+                                   : nullptr);
     r->morph_dbg.push_back(r->retain_compiled ? std::move(def) : nullptr);
   } else {
     de.seg_first = (uint32_t)r->h_static.size();

@@ -52,6 +52,7 @@ class StoredMorphShape:  # DisplayPrimitive::MorphShape
     id: int
     matrix: Matrix2D = field(default_factory=Matrix2D)
     ratio: int = 0  # MorphRatio(u16): 0 = start, 65535 = end
+    ratio_f: Optional[float] = None  # the TypeScript renderer's ratio (0..1, float32); replaces `ratio` when set
 
 
 DisplayPrimitive = Union[StoredShape, StoredMorphShape]
@@ -88,6 +89,9 @@ def _stage_arrays(stages: Sequence[Stage]):
             if isinstance(p, StoredMorphShape):
                 prims[j].kind = capi.PRIM_MORPH_SHAPE
                 prims[j].ratio = int(p.ratio)
+                if p.ratio_f is not None:
+                    prims[j].flags = capi.PRIM_RATIO_F32
+                    prims[j].ratio_f = float(p.ratio_f)
             else:
                 prims[j].kind = capi.PRIM_SHAPE
         keep.append(prims)

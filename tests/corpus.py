@@ -84,10 +84,11 @@ class Scene:
             self.frames.append([])
         self.frames[frame].append(("shape", idx, list(matrix), 0))
 
-    def draw_morph(self, idx, matrix, ratio, frame=0):
+    def draw_morph(self, idx, matrix, ratio, frame=0, ratio_f=None):
+        """ratio: MorphRatio(u16); ratio_f (optional): the TypeScript renderer's float ratio, replaces it."""
         while len(self.frames) <= frame:
             self.frames.append([])
-        self.frames[frame].append(("morph", idx, list(matrix), int(ratio)))
+        self.frames[frame].append(("morph", idx, list(matrix), int(ratio) if ratio_f is None else (int(ratio), float(ratio_f))))
 
 
 def render_oracle(scene: Scene, frame=0, want_debug=False):
@@ -105,7 +106,10 @@ def render_oracle(scene: Scene, frame=0, want_debug=False):
         else:
             if idx not in morph_compiled:
                 morph_compiled[idx] = cs.compile_morph_shape(scene.morphs[idx])
-            raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio)
+            if isinstance(ratio, tuple):
+                raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio[0], ratio[1])
+            else:
+                raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio)
     return raster.render_scene(b.scene(scene.width, scene.height), want_debug)
 
 
@@ -124,6 +128,8 @@ def make_product(scene: Scene):
         for kind, idx, m, ratio in items:
             if kind == "shape":
                 st.display_root.append(sw.StoredShape(shape_ids[idx], sw.Matrix2D(m)))
+            elif isinstance(ratio, tuple):
+                st.display_root.append(sw.StoredMorphShape(morph_ids[idx], sw.Matrix2D(m), ratio[0], ratio[1]))
             else:
                 st.display_root.append(sw.StoredMorphShape(morph_ids[idx], sw.Matrix2D(m), ratio))
         stages.append(st)

@@ -121,3 +121,77 @@ def test_unknown_bitmap_is_an_error(built_library):
         r.sync()
     assert e.value.status == -2  # BitmapNotFound
     r.close()
+
+
+def _morph_with_visible_strokes(width0=60, width1=140, color0=(0, 0, 0, 255), color1=(200, 30, 30, 128)):
+    """The corpus morph shape with its (invisible) line style made visible: lerped width, lerped colour."""
+    import copy
+
+    tag = copy.deepcopy(corpus.load_ast(corpus.MORPH_SAMPLE))
+    for styles_key in ("initial_styles",):
+        for ls in tag["shape"][styles_key]["line"]:
+            ls["width"], ls["morph_width"] = width0, width1
+            ls["fill"] = {"type": "solid",
+                          "color": dict(zip("rgba", color0)), "morph_color": dict(zip("rgba", color1))}
+    return tag
+
+
+@pytest.mark.parametrize("ratio", [0, 1, 16384, 32768, 50000, 65535])
+def test_morph_shape_with_visible_strokes(built_library, ratio):
+    """morph lines are stroked per draw at the item's ratio (lerped path and width, round caps and
+    joins, canvas-renderer.ts:252-266) and painted after the fills - bit-exact against the oracle, which models
+    the same expansion (parity unpinned against the reference: its corpus has no visible morph stroke)."""
+    tag = _morph_with_visible_strokes()
+    w, h, m = corpus.fixture_canvas(tag)
+    sc = corpus.Scene(w + 16, h + 16)
+    m = [1.0, 1.0, 0.0, 0.0, m[4] + 160.0, m[5] + 160.0]
+    sc.draw_morph(sc.add_morph(tag), m, ratio)
+    ref, info = corpus.render_oracle(sc, want_debug=True)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    edges, epath = r.debug_edges(0)
+    np.testing.assert_array_equal(edges, info["edges"])
+    np.testing.assert_array_equal(epath, info["edge_path"])
+    np.testing.assert_array_equal(r.debug_tile_counts(0), info["tile_counts"])
+    st = r.stats()
+    assert st["n_primitives"] == 1 and st["n_path_instances"] >= 2
+    r.close()
+    bad = (out != ref).any(axis=2)
+    assert not bad.any(), "%d px differ" % bad.sum()
+    plain = corpus.Scene(sc.width, sc.height)
+    plain.draw_morph(plain.add_morph(corpus.load_ast(corpus.MORPH_SAMPLE)), m, ratio)
+    assert (corpus.render_oracle(plain) != ref).any()  # the stroke is really visible
+
+
+def test_morph_strokes_in_a_batched_sweep_and_float_ratio(built_library):
+    """Strokes expanded per frame inside one batch (threads of the stage flattener included), and the TypeScript
+    renderer's float ratio (0.5 exactly instead of 32768 / 65535)."""
+    from swf_renderer_b200 import capi
+
+    tag = _morph_with_visible_strokes(40, 100, (10, 20, 30, 255), (250, 240, 0, 255))
+    w, h, m = corpus.fixture_canvas(tag)
+    sc = corpus.Scene(w, h)
+    idx = sc.add_morph(tag)
+    plain = sc.add_morph(corpus.load_ast(corpus.MORPH_SAMPLE))
+    ratios = [0, 8192, 30000, 65535]
+    for f, rt in enumerate(ratios):
+        sc.draw_morph(plain, m, rt, frame=f)
+        sc.draw_morph(idx, m, rt, frame=f)
+        sc.draw_morph(plain, [0.5, 0.5, 0.0, 0.0, m[4] * 0.5, m[5] * 0.5], 65535 - rt, frame=f)
+    sc.draw_morph(idx, m, 0, frame=len(ratios), ratio_f=0.5)
+    sc.draw_morph(idx, m, 0, frame=len(ratios) + 1, ratio_f=0.25)
+    r, stages = corpus.make_product(sc)
+    r.set_option(capi.OPT_FRAMES_PER_PASS, 4)
+    r.render_batch(stages)
+    for f in range(len(stages)):
+        out = r.get_image(frame=f, premultiplied=True).data
+        ref = corpus.render_oracle(sc, frame=f)
+        assert np.array_equal(out, ref), "frame %d differs in %d px" % (f, (out != ref).any(axis=2).sum())
+    r.close()
+    # ratio 0.5 as a float is not MorphRatio 32768 (= 0.500008): the two renderings differ somewhere
+    a = corpus.Scene(w, h)
+    a.draw_morph(a.add_morph(tag), m, 0, ratio_f=0.5)
+    b = corpus.Scene(w, h)
+    b.draw_morph(b.add_morph(tag), m, 32768)
+    assert a.frames != b.frames

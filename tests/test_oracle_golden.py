@@ -113,3 +113,20 @@ def test_gradient_ramp_endpoints():
     np.testing.assert_allclose(lut[0], [1, 0, 0, 1])
     np.testing.assert_allclose(lut[256], [0, 0, 1, 0.5])
     np.testing.assert_allclose(lut[128], [0.5, 0, 0.5, 0.75], atol=1e-6)
+
+
+def test_render_morph_golden_at_float_ratio_one_half():
+    """The reference test renders ratio 0.5 (a JS number; golden 32768.png = 0.5 * 65536,
+    node-canvas-renderer.spec.ts:86-131).  The oracle accepts that float directly."""
+    import compare
+    from oracle import compile_shape as cs
+    from oracle import raster
+
+    tag = corpus.load_ast(corpus.MORPH_SAMPLE)
+    w, h, m = corpus.fixture_canvas(tag)
+    b = raster._Builder({})
+    raster.add_morph_shape_item(b, cs.compile_morph_shape(tag), m, 0, 0.5)
+    out = raster.render_scene(b.scene(w, h))
+    gold = compare.premultiply_png(corpus.load_golden_png(corpus.MORPH_SAMPLE, "32768.png"))
+    st = compare.stats(out, gold)
+    assert st["interior_max"] <= 8 and st["psnr"] >= 50.0, st
