@@ -171,6 +171,42 @@ typedef struct swfr_stage {
   const swfr_display_primitive *display_root;
 } swfr_stage;
 
+/* ---- display tree (ts/src/lib/display/) ---------------------------------------------------------- */
+
+/* DisplayObjectType (ts/src/lib/display/display-object-type.ts:1-5), same order */
+typedef enum swfr_display_object_type {
+  SWFR_DISPLAY_CONTAINER = 0,
+  SWFR_DISPLAY_MORPH_SHAPE = 1,
+  SWFR_DISPLAY_SHAPE = 2
+} swfr_display_object_type;
+
+/* DisplayObject = DisplayObjectContainer | MorphShape | Shape.  The reference embeds the definition tag and
+ * compiles it on first use (canvas-renderer.ts:96-112); here definitions are registered first and referenced by id. */
+typedef struct swfr_display_object {
+  uint32_t type;           /* swfr_display_object_type */
+  uint32_t id;             /* ShapeId / MorphShapeId (shapes and morph shapes) */
+  uint8_t has_matrix;      /* `matrix?: Matrix` */
+  swfr_swf_matrix matrix;  /* swf-tree Matrix: Sfixed16P16 epsilons + twips */
+  float ratio;             /* MorphShape.ratio, a number in 0..1 */
+  uint32_t n_children;     /* containers */
+  const struct swfr_display_object *children;
+} swfr_display_object;
+
+/* Stage (ts/src/lib/display/stage.ts:7-18): size in pixels, root children */
+typedef struct swfr_display_stage {
+  uint8_t has_background_color;
+  swfr_rgba8 background_color;
+  uint32_t width, height;
+  uint32_t n_children;
+  const swfr_display_object *children;
+} swfr_display_stage;
+
+/* renderStage / drawDisplayObject / drawContainer (canvas-renderer.ts:69-94, 131-145): depth-first walk in paint
+ * order; a container's matrix applies to everything below it (save / applyMatrix / restore).  Matrices are composed
+ * in FP64 like Cairo's CTM and rounded to the Rust API's f32 Matrix2D at the leaves; morph primitives carry the
+ * float ratio (SWFR_PRIM_RATIO_F32).  Host only.  Writes up to `cap` primitives, *n = the number needed. */
+int swfr_flatten_display_stage(const swfr_display_stage *stage, swfr_display_primitive *out, uint32_t cap, uint32_t *n);
+
 /* ---- lifecycle -------------------------------------------------------------------------------------- */
 
 /* Creates a renderer with a width x height RGBA8 viewport on CUDA device `device`, with its own stream. */
@@ -190,7 +226,11 @@ typedef enum swfr_option {
   SWFR_OPT_RETAIN_COMPILED = 1,
   SWFR_OPT_FRAMES_PER_PASS = 2,
   SWFR_OPT_PROFILE = 3,
-  SWFR_OPT_HOST_THREADS = 4
+  SWFR_OPT_HOST_THREADS = 4,
+  SWFR_OPT_CLEAR_TO_BACKGROUND = 5 /* 0 (default): frames start transparent and Stage.background_color is ignored, like
+                                      the TypeScript renderer and the headless Rust renderer (canvas-renderer.ts:70-72,
+                                      headless_renderer.rs:611-615); 1: frames start from the opaque background colour,
+                                      like the windowed Rust renderer (gfx_renderer.rs:292-301) */
 } swfr_option;
 int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value);
 
@@ -235,6 +275,21 @@ int swfr_read_image(swfr_renderer *r, uint32_t frame, uint8_t *dst, size_t strid
 int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uint8_t *dst);
 /* Device pointer of frame 0 of the last render (premultiplied RGBA8, frames width*height*4 bytes apart). */
 int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n_frames);
+
+/* Renderer.render(stage) of the TypeScript API (ts/src/lib/renderer.ts:4-8, canvas-renderer.ts:61-78): flattens the
+ * display tree and renders it into frame 0 (n trees into frames 0..n-1).  stage.width / height must equal the
+ * renderer's viewport. */
+int swfr_render_display_stage(swfr_renderer *r, const swfr_display_stage *stage);
+int swfr_render_display_stages(swfr_renderer *r, const swfr_display_stage *stages, uint32_t n);
+
+/* ---- image files (host only) -------------------------------------------------------------------------- */
+
+/* write_pam (rs/src/pam.rs:3-34) / imageDataToPam (ts/src/lib/image-data-to-pam.ts:8-30): "P7" header + tight RGBA
+ * rows.  Pass out = NULL to query the size; *n = bytes needed / written. */
+int swfr_write_pam(const uint8_t *rgba, uint32_t width, uint32_t height, size_t stride, uint8_t *out, uint64_t cap, uint64_t *n);
+/* canvas.toBuffer("image/png") of the reference test (node-canvas-renderer.spec.ts:134-147): 8-bit RGBA PNG of
+ * straight-alpha pixels (swfr_read_image with premultiplied = 0). */
+int swfr_write_png(const uint8_t *rgba, uint32_t width, uint32_t height, size_t stride, uint8_t *out, uint64_t cap, uint64_t *n);
 
 /* ---- statistics of the last render (after swfr_sync) ------------------------------------------------ */
 

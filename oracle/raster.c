@@ -81,6 +81,8 @@ typedef struct {
   const swfo_segment *segs;
   const swfo_paint *paints;
   const swfo_bitmap *bitmaps;
+  uint32_t background; /* premultiplied RGBA8 every pixel starts from: 0 = clearRect (canvas-renderer.ts:70-72, the
+                          default), or the opaque stage colour like the windowed Rust renderer (gfx_renderer.rs:292-301) */
 } swfo_scene;
 
 /* optional debug taps (may be NULL) */
@@ -596,6 +598,8 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
   const int tiles_x = (W + SWFO_TILE - 1) / SWFO_TILE, tiles_y = (H + SWFO_TILE - 1) / SWFO_TILE;
   uint32_t *fb = (uint32_t *)calloc((size_t)W * H, 4); /* clearRect => transparent black (canvas-renderer.ts:70-71) */
   if (!fb) return -1;
+  if (sc->background)
+    for (size_t i = 0; i < (size_t)W * H; i++) fb[i] = sc->background;
   if (dbg) {
     dbg->n_edges = 0;
     dbg->n_records = 0;

@@ -79,6 +79,7 @@ class Scene(C.Structure):
         ("segs", C.POINTER(Segment)),
         ("paints", C.POINTER(Paint)),
         ("bitmaps", C.POINTER(Bitmap)),
+        ("background", C.c_uint32),
     ]
 
 
@@ -239,7 +240,8 @@ class _Builder:
     def add_item(self, def_index, matrix, ratio=0, ratio_f=None):
         self.items.append((def_index, matrix, ratio, ratio_f))
 
-    def scene(self, width, height):
+    def scene(self, width, height, background=None):
+        """background: None = transparent clear (the TypeScript renderer), or (r, g, b) = opaque stage colour."""
         segs = (Segment * max(1, len(self.segs)))()
         for i, (s6, e6, is_curve, path) in enumerate(self.segs):
             segs[i].s[:] = s6
@@ -264,6 +266,8 @@ class _Builder:
             bitmaps[i].rgba = pm.ctypes.data_as(C.POINTER(C.c_uint8))
         sc = Scene()
         sc.width, sc.height, sc.n_items = width, height, len(self.items)
+        if background is not None:
+            sc.background = int(background[0]) | (int(background[1]) << 8) | (int(background[2]) << 16) | (255 << 24)
         sc.items, sc.defs, sc.segs, sc.paints, sc.bitmaps = items, defs, segs, paints, bitmaps
         self.keep.extend([segs, paints, defs, items, bitmaps])
         return sc

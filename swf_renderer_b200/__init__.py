@@ -15,3 +15,4 @@ from .renderer import (  # noqa: F401
     compile_tag,
     decode_x_swf_bmp,
 )
+from . import display  # noqa: F401,E402  (mirror of the TypeScript display tree / Renderer interface)

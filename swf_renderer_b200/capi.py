@@ -21,7 +21,7 @@ COLOR_SRGB, COLOR_LINEAR_RGB = 0, 1
 RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
 PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
 PRIM_RATIO_F32 = 1
-OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS = 1, 2, 3, 4
+OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS, OPT_CLEAR_TO_BACKGROUND = 1, 2, 3, 4, 5
 
 
 class Rgba8(C.Structure):
@@ -139,6 +139,35 @@ class Stage(C.Structure):
     ]
 
 
+class DisplayObject(C.Structure):
+    pass
+
+
+DisplayObject._fields_ = [
+    ("type", C.c_uint32),
+    ("id", C.c_uint32),
+    ("has_matrix", C.c_uint8),
+    ("matrix", SwfMatrix),
+    ("ratio", C.c_float),
+    ("n_children", C.c_uint32),
+    ("children", C.POINTER(DisplayObject)),
+]
+
+
+class DisplayStage(C.Structure):
+    _fields_ = [
+        ("has_background_color", C.c_uint8),
+        ("background_color", Rgba8),
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+        ("n_children", C.c_uint32),
+        ("children", C.POINTER(DisplayObject)),
+    ]
+
+
+DISPLAY_CONTAINER, DISPLAY_MORPH_SHAPE, DISPLAY_SHAPE = 0, 1, 2
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("n_primitives", C.c_uint64),
@@ -173,6 +202,20 @@ PROTOTYPES = {
     ),
     "swfr_render": (C.c_int, [C.c_void_p, C.POINTER(Stage)]),
     "swfr_render_batch": (C.c_int, [C.c_void_p, C.POINTER(Stage), C.c_uint32]),
+    "swfr_flatten_display_stage": (
+        C.c_int,
+        [C.POINTER(DisplayStage), C.POINTER(DisplayPrimitive), C.c_uint32, C.POINTER(C.c_uint32)],
+    ),
+    "swfr_render_display_stage": (C.c_int, [C.c_void_p, C.POINTER(DisplayStage)]),
+    "swfr_render_display_stages": (C.c_int, [C.c_void_p, C.POINTER(DisplayStage), C.c_uint32]),
+    "swfr_write_pam": (
+        C.c_int,
+        [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)],
+    ),
+    "swfr_write_png": (
+        C.c_int,
+        [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)],
+    ),
     "swfr_batch_create": (C.c_int, [C.c_void_p, C.POINTER(Stage), C.c_uint32, C.POINTER(C.c_void_p)]),
     "swfr_batch_render": (C.c_int, [C.c_void_p, C.c_void_p]),
     "swfr_batch_destroy": (None, [C.c_void_p, C.c_void_p]),

@@ -1435,8 +1435,9 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
 
     // ---- pass 2: composite in paint order ----
     uint32_t px[8];
+    const uint32_t bg = __ldg(a.frame_bg + frame);
 #pragma unroll
-    for (int i = 0; i < 8; i++) px[i] = 0;
+    for (int i = 0; i < 8; i++) px[i] = bg;
     for (uint32_t base = start; base < p_end; base += 32) {
       uint32_t idx = base + lane;
       uint32_t pid = idx < p_end ? __ldg(a.list_items + idx) : 0u;

@@ -86,6 +86,7 @@ struct RenderArgs {
   const uint32_t *item_seg_off;   // n_items + 1
   const uint32_t *item_path_off;  // n_items + 1
   const uint32_t *frame_path_off; // n_frames + 1
+  const uint32_t *frame_bg;       // n_frames: premultiplied RGBA8 every pixel of the frame starts from
   const SegStatic *segs_static;
   const SegMorph *segs_morph;
   const DefPaint *def_paints;

@@ -103,9 +103,10 @@ struct swfr_batch {
   std::vector<Pass> passes;
   PinnedArr<DrawItem> items;
   PinnedArr<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
+  PinnedArr<uint32_t> frame_bg;                      // per frame: premultiplied RGBA8 the frame starts from
   PinnedArr<SegStatic> dyn_segs;                     // outlines of morph-shape strokes expanded for this batch's draws
   PinnedArr<DefPaint> dyn_paints;
-  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints;
+  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints, d_frame_bg;
   bool resident = false;
   uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
   cudaEvent_t uploaded = nullptr;  // recorded on the upload stream after the H2D copies
@@ -144,6 +145,7 @@ struct swfr_renderer {
   swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
   int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
   uint32_t host_threads = 0;    // stage flattening threads (0 = min(8, hardware))
+  bool clear_to_background = false;
   cudaStream_t up_stream = nullptr;
 
   // ---- last render ----
@@ -416,6 +418,12 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   CK(b.frame_off.resize(frame_off_at));
   CK(b.dyn_segs.resize(dyn_seg_at));
   CK(b.dyn_paints.resize(dyn_paint_at));
+  CK(b.frame_bg.resize(n));
+  for (uint32_t f = 0; f < n; f++) {
+    const swfr_rgba8 &c = stages[f].background_color;
+    // gfx_renderer.rs:292-301: clear colour (r, g, b, 1.0); otherwise transparent black (canvas-renderer.ts:70-72)
+    b.frame_bg[f] = r->clear_to_background ? ((uint32_t)c.r | ((uint32_t)c.g << 8) | ((uint32_t)c.b << 16) | 0xff000000u) : 0u;
+  }
   for (const Pass &p : b.passes) {  // closing entries of each pass
     b.seg_off[p.seg_off_at + p.n_items] = p.n_seginst;
     b.path_off[p.path_off_at + p.n_items] = p.n_paths;
@@ -488,6 +496,8 @@ int upload_batch(swfr_renderer *r, swfr_batch &b) {
   if (b.path_off.bytes()) CK(cudaMemcpyAsync(b.d_path_off.p, b.path_off.data(), b.path_off.bytes(), cudaMemcpyHostToDevice, st));
   if (b.frame_off.bytes())
     CK(cudaMemcpyAsync(b.d_frame_off.p, b.frame_off.data(), b.frame_off.bytes(), cudaMemcpyHostToDevice, st));
+  CK(b.d_frame_bg.reserve(std::max<size_t>(b.frame_bg.bytes(), 256)));
+  if (b.frame_bg.bytes()) CK(cudaMemcpyAsync(b.d_frame_bg.p, b.frame_bg.data(), b.frame_bg.bytes(), cudaMemcpyHostToDevice, st));
   CK(b.d_dyn_segs.reserve(std::max<size_t>(b.dyn_segs.bytes(), 256)));
   CK(b.d_dyn_paints.reserve(std::max<size_t>(b.dyn_paints.bytes(), 256)));
   if (b.dyn_segs.bytes()) CK(cudaMemcpyAsync(b.d_dyn_segs.p, b.dyn_segs.data(), b.dyn_segs.bytes(), cudaMemcpyHostToDevice, st));
@@ -565,6 +575,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.segs_static = r->d_static.as<SegStatic>();
   a.segs_morph = r->d_morph.as<SegMorph>();
   a.def_paints = r->d_paints.as<DefPaint>();
+  a.frame_bg = b.d_frame_bg.as<uint32_t>() + p.f0;
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
   a.ramps = r->d_ramps.as<float>();
@@ -863,6 +874,7 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
     case 2: r->frames_per_pass = (uint32_t)std::max<uint64_t>(1, value); return SWFR_OK;
     case 3: r->profile = value != 0; return SWFR_OK;
     case 4: r->host_threads = (uint32_t)std::min<uint64_t>(value, 256); return SWFR_OK;
+    case 5: r->clear_to_background = value != 0; return SWFR_OK;
     default: return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown option");
   }
 }
@@ -972,6 +984,32 @@ int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n) {
 }
 
 int swfr_render(swfr_renderer *r, const swfr_stage *stage) { return swfr_render_batch(r, stage, 1); }
+
+int swfr_render_display_stages(swfr_renderer *r, const swfr_display_stage *stages, uint32_t n) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!stages || n == 0) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
+  std::vector<std::vector<swfr_display_primitive>> prims(n);
+  std::vector<swfr_stage> flat(n);
+  for (uint32_t f = 0; f < n; f++) {
+    const swfr_display_stage &ds = stages[f];
+    if (ds.width != r->width || ds.height != r->height)
+      return fail(r, SWFR_ERR_INVALID_ARGUMENT, "stage size differs from the renderer's viewport");
+    uint32_t count = 0;
+    int rc = swfr_flatten_display_stage(&ds, nullptr, 0, &count);
+    if (rc != SWFR_OK) return fail(r, rc, "UnexpectedDisplayObjectType");
+    prims[f].resize(std::max<uint32_t>(count, 1));
+    rc = swfr_flatten_display_stage(&ds, prims[f].data(), count, &count);
+    if (rc != SWFR_OK) return fail(r, rc, "UnexpectedDisplayObjectType");
+    flat[f].background_color = ds.has_background_color ? ds.background_color : swfr_rgba8{0, 0, 0, 0};
+    flat[f].n_primitives = count;
+    flat[f].display_root = prims[f].data();
+  }
+  return swfr_render_batch(r, flat.data(), n);
+}
+
+int swfr_render_display_stage(swfr_renderer *r, const swfr_display_stage *stage) {
+  return swfr_render_display_stages(r, stage, 1);
+}
 
 int swfr_batch_create(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_batch **out) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
