@@ -242,6 +242,9 @@ def run_ours(a):
     r.set_option(capi.OPT_RETAIN_COMPILED, 0)
     if a.frames_per_pass:
         r.set_option(capi.OPT_FRAMES_PER_PASS, a.frames_per_pass)
+    # stage-flattening threads: the box's cores are shared by the ranks of the node
+    cores = max(1, len(os.sched_getaffinity(0)))
+    r.set_option(capi.OPT_HOST_THREADS, max(1, min(8, cores // max(world, 1))))
 
     # ---- inputs: textures, definitions, stages (host arrays) ----
     for i, t in enumerate(synth.textures()):

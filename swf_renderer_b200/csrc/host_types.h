@@ -103,5 +103,8 @@ void build_ramp(const swfr_color_stop *stops, uint32_t n, bool linear_rgb, bool 
 
 // image/x-swf-bmp format 3 -> straight RGBA8.  Returns a swfr_status.
 int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, uint32_t *w, uint32_t *h, std::string &err);
+// The host half alone: header check + zlib inflate -> colour table (3 bytes x colors) followed by padded index rows.
+int inflate_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &inflated, uint32_t *w, uint32_t *h, uint32_t *colors,
+                    uint32_t *padded, std::string &err);
 
 }  // namespace swfr

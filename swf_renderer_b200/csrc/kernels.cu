@@ -1506,13 +1506,39 @@ __global__ void k_unpremultiply(const uint32_t *__restrict__ src, uint32_t *__re
   }
 }
 
-__global__ void k_premultiply(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint64_t n) {
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t p = src[i], al = p >> 24;
-    uint32_t r = ((p & 255) * al + 127u) / 255u, g = (((p >> 8) & 255) * al + 127u) / 255u,
-             b = (((p >> 16) & 255) * al + 127u) / 255u;
+// Straight RGBA8 rows (`stride` bytes apart) -> tight premultiplied 8-bit (what a Canvas stores); *translucent is set
+// when any alpha is below 255.
+__global__ void k_premultiply(const uint8_t *__restrict__ src, size_t stride, uint32_t w, uint32_t h, uint32_t *__restrict__ dst,
+                              uint32_t *translucent) {
+  const uint64_t n = (uint64_t)w * h, step = (uint64_t)gridDim.x * blockDim.x;
+  bool any = false;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (uint64_t)y * w);
+    const uint8_t *s = src + (size_t)y * stride + 4 * (size_t)x;
+    const uint32_t al = s[3];
+    const uint32_t r = (s[0] * al + 127u) / 255u, g = (s[1] * al + 127u) / 255u, b = (s[2] * al + 127u) / 255u;
     dst[i] = r | (g << 8) | (b << 16) | (al << 24);
+    any |= al != 255u;
+  }
+  if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(translucent, 1u);
+}
+
+// image/x-swf-bmp format 3 after inflate (decode-x-swf-bmp.ts:17-39): `colors` RGB triplets, then rows of 8-bit
+// colour indices padded to a multiple of 4 bytes -> tight opaque RGBA8 (premultiplied == straight at alpha 255); an
+// index past the table is opaque black (decode-x-swf-bmp.ts:35-36).
+__global__ void k_xswfbmp_expand(const uint8_t *__restrict__ inflated, uint32_t colors, uint32_t w, uint32_t h, uint32_t padded,
+                                 uint32_t *__restrict__ dst) {
+  __shared__ uint32_t table[256];
+  for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x)
+    table[c] = c < colors ? ((uint32_t)inflated[3 * c] | ((uint32_t)inflated[3 * c + 1] << 8) | ((uint32_t)inflated[3 * c + 2] << 16) |
+                             0xff000000u)
+                          : 0xff000000u;
+  __syncthreads();
+  const uint8_t *idx = inflated + 3 * (size_t)colors;
+  const uint64_t n = (uint64_t)w * h, step = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (uint64_t)y * w);
+    dst[i] = table[idx[(size_t)y * padded + x]];
   }
 }
 
@@ -1633,8 +1659,13 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
 void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t st) {
   k_unpremultiply<<<kNumSM * 8, 256, 0, st>>>(src, dst, n_px);
 }
-void launch_premultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t st) {
-  k_premultiply<<<kNumSM * 8, 256, 0, st>>>(src, dst, n_px);
+void launch_premultiply(const uint8_t *src, size_t stride, uint32_t w, uint32_t h, uint32_t *dst, uint32_t *translucent,
+                        cudaStream_t st) {
+  k_premultiply<<<kNumSM * 8, 256, 0, st>>>(src, stride, w, h, dst, translucent);
+}
+void launch_xswfbmp_expand(const uint8_t *inflated, uint32_t colors, uint32_t w, uint32_t h, uint32_t padded, uint32_t *dst,
+                           cudaStream_t st) {
+  k_xswfbmp_expand<<<kNumSM * 8, 256, 0, st>>>(inflated, colors, w, h, padded, dst);
 }
 void launch_tile_counts(const RenderArgs &a, uint32_t frame, uint32_t *counts, cudaStream_t st) {
   k_tile_counts<<<kNumSM * 2, 256, 0, st>>>(a, frame, counts);

@@ -133,7 +133,10 @@ const char *stage_name(int i);
 int launch_render(const RenderArgs &a, cudaStream_t stream, cudaEvent_t *ev = nullptr);
 
 void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
-void launch_premultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
+void launch_premultiply(const uint8_t *src, size_t stride, uint32_t w, uint32_t h, uint32_t *dst, uint32_t *translucent,
+                        cudaStream_t stream);
+void launch_xswfbmp_expand(const uint8_t *inflated, uint32_t colors, uint32_t w, uint32_t h, uint32_t padded, uint32_t *dst,
+                           cudaStream_t stream);
 void launch_tile_counts(const RenderArgs &a, uint32_t frame, uint32_t *counts, cudaStream_t stream);
 
 }  // namespace swfr

@@ -139,7 +139,7 @@ struct swfr_renderer {
 
   // ---- working memory ----
   DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used;
+      slot_off, records, frames, scan_tmp, totals, scratch, scratch2, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used;
   Caps caps{0, 0, 0, 0, 0, 0};
   PinnedBuf pin_totals;
   swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
@@ -886,39 +886,18 @@ int swfr_register_morph_shape(swfr_renderer *r, const swfr_define_shape *tag, ui
   return register_def(r, tag, true, out_id);
 }
 
-int swfr_register_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, const uint8_t *rgba, size_t stride) {
-  if (!r) return SWFR_ERR_INVALID_HANDLE;
-  if (!rgba || w == 0 || h == 0 || stride < (size_t)w * 4) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad bitmap");
-  cudaSetDevice(r->device);
-  int rc = finish(r);
-  if (rc != SWFR_OK) return rc;
-  rc = flush_store(r);
-  if (rc != SWFR_OK) return rc;
-  if (r->bitmaps.empty()) {
-    r->bitmaps.resize(65536);
-    r->h_bitmaps.resize(65536);
-  }
-  // straight -> premultiplied 8-bit (what a Canvas stores), then into a 2D array behind a texture object
-  std::vector<uint8_t> pm((size_t)w * h * 4);
-  bool opaque = true;
-  for (uint32_t y = 0; y < h; y++)
-    for (uint32_t x = 0; x < w; x++) {
-      const uint8_t *s = rgba + (size_t)y * stride + 4 * x;
-      uint8_t *d = &pm[4 * ((size_t)y * w + x)];
-      uint32_t a = s[3];
-      d[0] = (uint8_t)((s[0] * a + 127u) / 255u);
-      d[1] = (uint8_t)((s[1] * a + 127u) / 255u);
-      d[2] = (uint8_t)((s[2] * a + 127u) / 255u);
-      d[3] = (uint8_t)a;
-      if (a != 255) opaque = false;
-    }
+namespace {
+
+// Installs a tight premultiplied RGBA8 image that already sits in device memory (r->scratch) as bitmap `id`:
+// 2D array + point-sampling texture object + table entry.
+int install_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, bool opaque) {
   BitmapRes &res = r->bitmaps[id];
   if (res.tex) cudaDestroyTextureObject(res.tex);
   if (res.arr) cudaFreeArray(res.arr);
   res = BitmapRes{};
   cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
   CK(cudaMallocArray(&res.arr, &cd, w, h));
-  CK(cudaMemcpy2DToArray(res.arr, 0, 0, pm.data(), (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2DToArrayAsync(res.arr, 0, 0, r->scratch.p, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, r->stream));
   cudaResourceDesc rd{};
   rd.resType = cudaResourceTypeArray;
   rd.res.array.array = res.arr;
@@ -941,15 +920,59 @@ int swfr_register_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, 
   return SWFR_OK;
 }
 
+int begin_bitmap(swfr_renderer *r) {
+  cudaSetDevice(r->device);
+  int rc = finish(r);
+  if (rc != SWFR_OK) return rc;
+  rc = flush_store(r);
+  if (rc != SWFR_OK) return rc;
+  if (r->bitmaps.empty()) {
+    r->bitmaps.resize(65536);
+    r->h_bitmaps.resize(65536);
+  }
+  return SWFR_OK;
+}
+
+}  // namespace
+
+// Straight RGBA8 from the host: uploaded as it is, premultiplied on the device (what a Canvas stores).
+int swfr_register_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, const uint8_t *rgba, size_t stride) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!rgba || w == 0 || h == 0 || stride < (size_t)w * 4) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad bitmap");
+  int rc = begin_bitmap(r);
+  if (rc != SWFR_OK) return rc;
+  const size_t src_bytes = (size_t)(h - 1) * stride + (size_t)w * 4, dst_bytes = (size_t)w * h * 4;
+  CK(r->scratch.reserve(dst_bytes));
+  CK(r->scratch2.reserve(src_bytes + 16));
+  uint32_t *flag = reinterpret_cast<uint32_t *>((char *)r->scratch2.p + ((src_bytes + 3) & ~(size_t)3));
+  CK(cudaMemcpyAsync(r->scratch2.p, rgba, src_bytes, cudaMemcpyHostToDevice, r->stream));
+  CK(cudaMemsetAsync(flag, 0, 4, r->stream));
+  launch_premultiply(r->scratch2.as<uint8_t>(), stride, w, h, r->scratch.as<uint32_t>(), flag, r->stream);
+  uint32_t translucent = 0;
+  CK(cudaMemcpyAsync(&translucent, flag, 4, cudaMemcpyDeviceToHost, r->stream));
+  CK(cudaStreamSynchronize(r->stream));
+  return install_bitmap(r, id, w, h, translucent == 0);
+}
+
+// DefineBitmap image/x-swf-bmp: zlib inflate on the host (a serial bit stream), colour-table expansion on the device
+// (one byte per pixel crosses PCIe instead of four).
 int swfr_register_bitmap_xswfbmp(swfr_renderer *r, uint16_t id, const uint8_t *data, size_t len) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (!data) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL data");
-  std::vector<uint8_t> rgba;
-  uint32_t w = 0, h = 0;
+  std::vector<uint8_t> inflated;
+  uint32_t w = 0, h = 0, colors = 0, padded = 0;
   std::string err;
-  int rc = decode_xswfbmp(data, len, rgba, &w, &h, err);
+  int rc = inflate_xswfbmp(data, len, inflated, &w, &h, &colors, &padded, err);
   if (rc != SWFR_OK) return fail(r, rc, err);
-  return swfr_register_bitmap(r, id, w, h, rgba.data(), (size_t)w * 4);
+  if (w == 0 || h == 0) return fail(r, SWFR_ERR_MALFORMED, "x-swf-bmp: empty image");
+  rc = begin_bitmap(r);
+  if (rc != SWFR_OK) return rc;
+  CK(r->scratch.reserve((size_t)w * h * 4));
+  CK(r->scratch2.reserve(inflated.size()));
+  CK(cudaMemcpyAsync(r->scratch2.p, inflated.data(), inflated.size(), cudaMemcpyHostToDevice, r->stream));
+  launch_xswfbmp_expand(r->scratch2.as<uint8_t>(), colors, w, h, padded, r->scratch.as<uint32_t>(), r->stream);
+  CK(cudaStreamSynchronize(r->stream));  // `inflated` is pageable host memory
+  return install_bitmap(r, id, w, h, true);
 }
 
 int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t cap, uint32_t *w, uint32_t *h) {

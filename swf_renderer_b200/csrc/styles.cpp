@@ -59,7 +59,8 @@ void build_ramp(const swfr_color_stop *stops_in, uint32_t n, bool linear_rgb, bo
   if (all_opaque) *all_opaque = opaque;
 }
 
-int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, uint32_t *w, uint32_t *h, std::string &err) {
+int inflate_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &src, uint32_t *w, uint32_t *h, uint32_t *colors,
+                    uint32_t *padded_out, std::string &err) {
   if (len < 6) {
     err = "x-swf-bmp: truncated header";
     return SWFR_ERR_MALFORMED;
@@ -73,7 +74,7 @@ int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, 
   uint32_t color_count = (uint32_t)data[5] + 1;
   size_t table = 3 * (size_t)color_count;
   size_t need = table + (size_t)padded * height;
-  std::vector<uint8_t> src(need);
+  src.resize(need);
   uLongf got = (uLongf)need;
   int zr = uncompress(src.data(), &got, data + 6, (uLong)(len - 6));
   if (zr != Z_OK && zr != Z_BUF_ERROR) {
@@ -84,6 +85,19 @@ int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, 
     err = "x-swf-bmp: pixel data is truncated";
     return SWFR_ERR_MALFORMED;
   }
+  *w = width;
+  *h = height;
+  *colors = color_count;
+  *padded_out = padded;
+  return SWFR_OK;
+}
+
+int decode_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &rgba, uint32_t *w, uint32_t *h, std::string &err) {
+  std::vector<uint8_t> src;
+  uint32_t width = 0, height = 0, color_count = 0, padded = 0;
+  int rc = inflate_xswfbmp(data, len, src, &width, &height, &color_count, &padded, err);
+  if (rc != SWFR_OK) return rc;
+  size_t table = 3 * (size_t)color_count;
   rgba.resize((size_t)width * height * 4);
   for (uint32_t y = 0; y < height; y++) {
     for (uint32_t x = 0; x < width; x++) {

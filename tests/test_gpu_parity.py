@@ -195,3 +195,53 @@ def test_morph_strokes_in_a_batched_sweep_and_float_ratio(built_library):
     b = corpus.Scene(w, h)
     b.draw_morph(b.add_morph(tag), m, 32768)
     assert a.frames != b.frames
+
+
+def test_xswfbmp_expanded_on_the_device(built_library):
+    """Renderer.addBitmap(tag) - the colour table of image/x-swf-bmp is expanded by a kernel: the render
+    must equal the one whose bitmap was decoded on the host by the oracle; an index past the table is opaque black
+    (decode-x-swf-bmp.ts:35-36); rows are padded to 4 bytes."""
+    import zlib
+
+    import swf_renderer_b200 as sw
+
+    sc = corpus.corpus_scene("textured-shapes/homestuck-beta-4", ["bitmap/homestuck-beta-3"])
+    ref = corpus.render_oracle(sc)
+    r = sw.HeadlessRenderer(sc.width, sc.height)
+    r.add_bitmap(corpus.load_bitmap_ast("bitmap/homestuck-beta-3"))
+    sid = r.register_shape(sc.shapes[0])
+    r.render(sw.Stage([sw.StoredShape(sid, sw.Matrix2D(sc.frames[0][0][2]))]))
+    out = r.get_image(premultiplied=True).data
+    r.close()
+    np.testing.assert_array_equal(out, ref)
+
+    # synthetic 5 x 3 image (rows padded to 8 bytes), 2 colours, some indices out of range
+    w, h, colors = 5, 3, [(255, 0, 0), (0, 128, 255)]
+    idx = np.array([[0, 1, 2, 1, 0], [1, 1, 0, 255, 7], [0, 0, 1, 1, 1]], dtype=np.uint8)
+    rows = np.zeros((h, 8), dtype=np.uint8)
+    rows[:, :w] = idx
+    raw = bytes(c for col in colors for c in col) + rows.tobytes()
+    data = bytes([3, w & 255, w >> 8, h & 255, h >> 8, len(colors) - 1]) + zlib.compress(raw)
+    want = np.zeros((h, w, 4), dtype=np.uint8)
+    for y in range(h):
+        for x in range(w):
+            c = colors[idx[y, x]] if idx[y, x] < len(colors) else (0, 0, 0)
+            want[y, x] = (*c, 255)
+    np.testing.assert_array_equal(sw.decode_x_swf_bmp(data), want)  # host decoder
+    # through the device path: fill a rectangle with the bitmap at 1 texel = 1 px, unsmoothed positions at texel centres
+    tag = {
+        "type": "define-shape", "id": 1, "bounds": {"x_min": 0, "x_max": w * 20, "y_min": 0, "y_max": h * 20},
+        "shape": {"initial_styles": {"fill": [{"type": "bitmap", "bitmap_id": 9, "repeating": False, "smoothed": False,
+                                               "matrix": {"scale_x": 20 * 65536, "scale_y": 20 * 65536, "rotate_skew0": 0,
+                                                          "rotate_skew1": 0, "translate_x": 0, "translate_y": 0}}], "line": []},
+                  "records": [{"type": "style-change", "move_to": {"x": 0, "y": 0}, "right_fill": 1},
+                              {"type": "edge", "delta": {"x": w * 20, "y": 0}}, {"type": "edge", "delta": {"x": 0, "y": h * 20}},
+                              {"type": "edge", "delta": {"x": -w * 20, "y": 0}}, {"type": "edge", "delta": {"x": 0, "y": -h * 20}}]},
+    }
+    r = sw.HeadlessRenderer(w, h)
+    r._check(r._lib.swfr_register_bitmap_xswfbmp(r._h, 9, data, len(data)))
+    sid = r.register_shape(tag)
+    r.render(sw.Stage([sw.StoredShape(sid)]))
+    out = r.get_image(premultiplied=True).data
+    r.close()
+    np.testing.assert_array_equal(out, want)
