@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames-per-pass", type=int, default=0, help="0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--uhd-frames", type=int, default=16,
+                    help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
     return ap.parse_args()
 
 
@@ -371,6 +373,50 @@ def run_ours(a):
         r.sync()
     e2e_serial_ms = (time.perf_counter() - t0) / n_serial * 1e3
 
+    # ---- secondary: the same stream at 3840x2160 (BASELINE metric "at 1080p/4K"), device-resident stages ----
+    uhd = None
+    if a.uhd_frames > 0:
+        UW, UH = 3840, 2160
+        batch.close()
+        ru = sw.HeadlessRenderer(UW, UH, device=local, cuda_stream=stream.cuda_stream)
+        ru.set_option(capi.OPT_RETAIN_COMPILED, 0)
+        ru.set_option(capi.OPT_FRAMES_PER_PASS, 8)
+        for i, t in enumerate(synth.textures()):
+            ru.register_bitmap(i, t)
+        prims_u = []
+        for f in range(a.uhd_frames):
+            fr = synth.SynthFrame(rank * a.uhd_frames + f, a.shapes, UW, UH, 2.0)
+            prims_u.append(stage_array_from_numpy(fr.register(ru), fr.matrices()))
+        bu = ru.create_batch(stages_from_prims(prims_u))
+        for _ in range(3):
+            bu.render()
+        ru.sync()
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_u = max(3, min(a.steps, 10))
+        u0.record(stream)
+        for _ in range(n_u):
+            bu.render()
+        u1.record(stream)
+        ru.sync()
+        barrier()
+        ums = max_over_ranks(u0.elapsed_time(u1))
+        su = ru.stats()
+        uhd = {
+            "resolution": [UW, UH],
+            "frames_per_step_per_gpu": a.uhd_frames,
+            "shapes_per_frame": a.shapes,
+            "steps": n_u,
+            "ms_per_step": ums / n_u,
+            "value": world * a.uhd_frames * UW * UH * n_u / (ums / 1e3) / 1e6,
+            "unit": UNIT,
+            "shapes_per_s": world * a.uhd_frames * a.shapes * n_u / (ums / 1e3),
+            "n_records": su["n_records"],
+        }
+        bu.close()
+        ru.close()
+        batch = None
+
     if rank == 0:
         line = {
             "metric": METRIC,
@@ -404,10 +450,13 @@ def run_ours(a):
             "roofline": roofline,
             "per_step": {k: stats[k] for k in ("n_primitives", "n_segments", "n_edges", "n_slots", "n_records", "retries")},
         }
+        if uhd is not None:
+            line["uhd"] = uhd
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(a)
         print(json.dumps(line), flush=True)
-    batch.close()
+    if batch is not None:
+        batch.close()
     r.close()
     if world > 1:
         dist.destroy_process_group()
