@@ -227,6 +227,8 @@ typedef enum swfr_option {
   SWFR_OPT_FRAMES_PER_PASS = 2,
   SWFR_OPT_PROFILE = 3,
   SWFR_OPT_HOST_THREADS = 4,
+  SWFR_OPT_DEBUG_TINY_ARENA = 6,   /* tests only: working arrays start at a few hundred entries, so every render has to
+                                      grow them and re-run (swfr_stats.retries > 0) */
   SWFR_OPT_CLEAR_TO_BACKGROUND = 5 /* 0 (default): frames start transparent and Stage.background_color is ignored, like
                                       the TypeScript renderer and the headless Rust renderer (canvas-renderer.ts:70-72,
                                       headless_renderer.rs:611-615); 1: frames start from the opaque background colour,

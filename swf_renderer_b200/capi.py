@@ -22,6 +22,7 @@ RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
 PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
 PRIM_RATIO_F32 = 1
 OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS, OPT_CLEAR_TO_BACKGROUND = 1, 2, 3, 4, 5
+OPT_DEBUG_TINY_ARENA = 6
 
 
 class Rgba8(C.Structure):

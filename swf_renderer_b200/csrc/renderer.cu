@@ -146,6 +146,7 @@ struct swfr_renderer {
   int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
   uint32_t host_threads = 0;    // stage flattening threads (0 = min(8, hardware))
   bool clear_to_background = false;
+  bool tiny_arena = false;  // debug: start every working array at a few hundred entries so that growth + re-run is exercised
   cudaStream_t up_stream = nullptr;
 
   // ---- last render ----
@@ -526,6 +527,14 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
   CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
   Caps want = r->caps;
+  if (r->tiny_arena) {  // SWFR_OPT_DEBUG_TINY_ARENA: no heuristics, every array has to grow through finish()
+    want.edges = std::max<uint32_t>(want.edges, 512);
+    want.slots = std::max<uint32_t>(want.slots, 512);
+    want.records = std::max<uint32_t>(want.records, 512);
+    want.list = std::max<uint32_t>(want.list, 512);
+    want.rows = std::max<uint32_t>(want.rows, 512);
+    want.stage = std::max<uint32_t>(want.stage, 1024);
+  } else {
   want.edges = std::max<uint32_t>(want.edges, std::max<uint32_t>(1u << 16, max_seg * 4));
   want.slots = std::max<uint32_t>(want.slots, std::max<uint32_t>(1u << 16, max_paths * 32));
   want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
@@ -536,6 +545,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     uint64_t warps = std::min<uint64_t>((uint64_t)kNumSM * 16 * 8, (uint64_t)want.edges / 32 + 1);
     uint64_t st = (uint64_t)want.records + want.records / 4 + warps * kStageBlock + 65535u;
     want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(st & ~255ull, 0xffffff00ull));
+  }
   }
   uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   size_t max_lists = (size_t)std::max<uint32_t>(1, r->frames_per_pass) * r->tiles_y * groups_x;
@@ -670,7 +680,7 @@ int finish(swfr_renderer *r) {
   for (size_t i = 0; i < np; i++) {
     int guard = 0;
     while (r->last_totals[i].overflow | r->last_totals[i].overflow_stage) {
-      if (++guard > 8) return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
+      if (++guard > 12) return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
       const Totals &t = r->last_totals[i];
       Caps want = r->caps;
       auto grow = [](uint32_t need) { return (uint32_t)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0xfffffff0ull); };
@@ -686,7 +696,8 @@ int finish(swfr_renderer *r) {
         uint64_t need = ((uint64_t)t.n_stage_blocks + t.n_stage_blocks / 8 + 64) * 256;
         want.stage = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want.stage, need), 0xffffff00ull);
       }
-      want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
+      if (!r->tiny_arena)
+        want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
       CK(r->stage.reserve((size_t)want.stage * 16));
       CK(r->stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
       CK(r->edges.reserve((size_t)want.edges * 16));
@@ -875,6 +886,10 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
     case 3: r->profile = value != 0; return SWFR_OK;
     case 4: r->host_threads = (uint32_t)std::min<uint64_t>(value, 256); return SWFR_OK;
     case 5: r->clear_to_background = value != 0; return SWFR_OK;
+    case 6:
+      r->tiny_arena = value != 0;
+      if (r->tiny_arena) r->caps = Caps{0, 0, 0, 0, 0, 0};
+      return SWFR_OK;
     default: return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown option");
   }
 }

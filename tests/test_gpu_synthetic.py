@@ -183,3 +183,50 @@ def test_streaming_renders_overlap_without_corruption(built_library):
     r.sync()
     np.testing.assert_array_equal(out[0].numpy()[: 3 * fb].reshape(3, H, W, 4), want[2][1:4])
     r.close()
+
+
+def test_working_memory_growth_and_rerun(built_library):
+    """SWFR_OPT_DEBUG_TINY_ARENA: every working array (edges, slots, records, lists, rows, staging) starts far too
+    small, so the render overflows stage after stage, the host grows the arena and re-runs the pass - the result must
+    be the oracle's, also for a batch whose frames were being copied out while a pass was re-run."""
+    import torch
+
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import stage_array_from_numpy, stages_from_prims
+
+    sc = _scene(11, 300, 640, 360, 0.5)
+    ref = corpus.render_oracle(sc)
+    r, stages = corpus.make_product(sc)
+    r.set_option(capi.OPT_DEBUG_TINY_ARENA, 1)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    st = r.stats()
+    assert st["retries"] >= 3, st
+    np.testing.assert_array_equal(out, ref)
+    r.render(stages[0])  # second time: the arena is large enough now
+    assert r.stats()["retries"] == 0
+    np.testing.assert_array_equal(r.get_image(premultiplied=True).data, ref)
+    r.close()
+
+    # streamed batch with async read-back while passes overflow and are re-run
+    W, H, N, F = 320, 200, 150, 4
+    r = sw.HeadlessRenderer(W, H)
+    for j, t in enumerate(synth.textures()):
+        r.register_bitmap(j, t)
+    prims, want = [], []
+    for f in range(F):
+        fr = synth.SynthFrame(300 + f, N, W, H, 0.5)
+        prims.append(stage_array_from_numpy(fr.register(r), fr.matrices()))
+    arr, keep = stages_from_prims(prims)
+    r.set_option(capi.OPT_FRAMES_PER_PASS, 2)
+    r.render_stage_array(arr, F)
+    want = np.stack([r.get_image(frame=f, premultiplied=True).data.copy() for f in range(F)])
+    r.set_option(capi.OPT_DEBUG_TINY_ARENA, 1)
+    buf = torch.zeros(F * W * H * 4, dtype=torch.uint8, pin_memory=True)
+    r.render_stage_array(arr, F)
+    r.read_frames_async(0, F, buf.data_ptr())
+    r.sync()
+    assert r.stats()["retries"] >= 3
+    np.testing.assert_array_equal(buf.numpy().reshape(F, H, W, 4), want)
+    r.close()
