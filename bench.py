@@ -448,7 +448,8 @@ def run_ours(a):
             },
             "gpu_launches": launches,
             "roofline": roofline,
-            "per_step": {k: stats[k] for k in ("n_primitives", "n_segments", "n_edges", "n_slots", "n_records", "retries")},
+            "per_step": {k: stats[k] for k in ("n_primitives", "n_segments", "n_edges", "n_slots", "n_records", "fine_slots",
+                                                "fine_records", "retries")},
         }
         if uhd is not None:
             line["uhd"] = uhd

@@ -227,6 +227,12 @@ typedef enum swfr_option {
   SWFR_OPT_FRAMES_PER_PASS = 2,
   SWFR_OPT_PROFILE = 3,
   SWFR_OPT_HOST_THREADS = 4,
+  SWFR_OPT_OCCLUSION_CHUNKS = 7,   /* depth chunks for occlusion culling: the items of a frame are binned in this many
+                                      ranges from the top (last painted) down, and geometry under an opaque full-tile
+                                      cover found by an upper chunk is skipped.  0 (default): automatic (5 for frames
+                                      of >= 1024 items, else 1); 1: no culling - every edge and record is produced, which
+                                      the swfr_debug_edges / swfr_debug_tile_counts taps need; up to 8.  Pixels are
+                                      identical for every setting */
   SWFR_OPT_DEBUG_TINY_ARENA = 6,   /* tests only: working arrays start at a few hundred entries, so every render has to
                                       grow them and re-run (swfr_stats.retries > 0) */
   SWFR_OPT_CLEAR_TO_BACKGROUND = 5 /* 0 (default): frames start transparent and Stage.background_color is ignored, like
@@ -298,6 +304,8 @@ int swfr_write_png(const uint8_t *rgba, uint32_t width, uint32_t height, size_t 
 typedef struct swfr_stats {
   uint64_t n_primitives, n_path_instances, n_segments, n_edges, n_slots, n_records, n_tiles;
   uint64_t algorithmic_bytes; /* B_seg + B_draw + 2*8*E_tile + 4*W*H per frame, summed */
+  uint64_t fine_slots;        /* (path, tile) slots the coverage kernel composited (after occlusion culling) */
+  uint64_t fine_records;      /* binned records it read; n_records - fine_records were binned but hidden */
   uint32_t kernel_launches;   /* kernels launched by the last swfr_*render* call */
   uint32_t retries;           /* re-runs caused by working-memory growth */
 } swfr_stats;

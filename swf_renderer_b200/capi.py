@@ -23,6 +23,7 @@ PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
 PRIM_RATIO_F32 = 1
 OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS, OPT_CLEAR_TO_BACKGROUND = 1, 2, 3, 4, 5
 OPT_DEBUG_TINY_ARENA = 6
+OPT_OCCLUSION_CHUNKS = 7
 
 
 class Rgba8(C.Structure):
@@ -179,6 +180,8 @@ class Stats(C.Structure):
         ("n_records", C.c_uint64),
         ("n_tiles", C.c_uint64),
         ("algorithmic_bytes", C.c_uint64),
+        ("fine_slots", C.c_uint64),
+        ("fine_records", C.c_uint64),
         ("kernel_launches", C.c_uint32),
         ("retries", C.c_uint32),
     ]

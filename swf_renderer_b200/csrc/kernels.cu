@@ -221,6 +221,21 @@ __device__ __forceinline__ void load_segment(const RenderArgs &a, const ItemRegs
   }
 }
 
+// Depth chunks: items [chunk_first(c, f), chunk_first(c + 1, f)) of frame f belong to chunk c (pass-relative indices).
+__device__ __forceinline__ uint32_t chunk_first(const RenderArgs &a, uint32_t c, uint32_t frame) {
+  return __ldg(a.chunk_items + c * a.n_frames + frame);
+}
+
+// Path instance of segment `local` of a draw item (without transforming the segment).
+__device__ __forceinline__ uint32_t segment_pid(const RenderArgs &a, const ItemRegs &item, uint32_t local) {
+  uint32_t pf;
+  if (item.kind == ITEM_MORPH)
+    pf = __ldg(&a.segs_morph[item.seg_first + local].path_flags);
+  else
+    pf = __ldg(&(item.kind == ITEM_DYNAMIC ? a.segs_dynamic : a.segs_static)[item.seg_first + local].path_flags);
+  return item.path_off + (pf & 0x7fffffffu);
+}
+
 __global__ void k_init(RenderArgs a) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t stride = gridDim.x * blockDim.x;
@@ -231,12 +246,17 @@ __global__ void k_init(RenderArgs a) {
     a.totals->work = 0;
     a.totals->n_list = 0;
     a.totals->n_big = 0;
+    a.totals->n_big_chunk = 0;
     a.totals->n_rowent = 0;
     a.totals->n_stage_blocks = 0;
     a.totals->overflow_stage = 0;
+    a.totals->fine_hits = 0;
+    a.totals->fine_records = 0;
   }
   for (uint32_t l = i; l < a.n_frames * (uint32_t)a.tiles_y; l += stride) a.row_count[l] = 0;
   for (uint32_t l = i; l < a.caps.stage / kStageBlock; l += stride) a.stage_used[l] = 0;
+  for (uint32_t l = i; l < a.n_frames * (uint32_t)(a.tiles_x * a.tiles_y); l += stride) a.tile_cover[l] = 0;
+  for (uint32_t l = i; l < a.n_items; l += stride) a.item_alive[l] = 0;
   for (uint32_t p = i; p < a.n_paths; p += stride) {
     a.path_bbox[4 * p + 0] = INT_MAX;
     a.path_bbox[4 * p + 1] = INT_MAX;
@@ -279,36 +299,134 @@ __global__ void k_flatten_count(RenderArgs a) {
   }
 }
 
+// Occlusion culling, per depth chunk (chunks are processed from the top one down).  tile_cover[tile] = 1 + the highest
+// path instance found so far that covers the tile completely and opaquely (0 = none); every such path belongs to a
+// chunk above the one being processed, so for the paths of this chunk "covered" is simply tile_cover != 0.
+// k_cover_sat builds, per frame, the summed-area table of OPEN (uncovered) tiles, (tiles_x + 1) x (tiles_y + 1)
+// entries with a zero first row and column: one block per frame, row prefixes then column prefixes.
+__global__ void __launch_bounds__(256) k_cover_sat(RenderArgs a) {
+  if (a.totals->overflow) return;
+  const uint32_t frame = blockIdx.x;
+  if (frame == 0 && threadIdx.x == 0) a.totals->n_big_chunk = 0;  // the list of the chunk about to be processed
+  const int tx = a.tiles_x, ty = a.tiles_y, sw = tx + 1;
+  const uint32_t *cover = a.tile_cover + frame * (uint32_t)(tx * ty);
+  uint32_t *sat = a.cover_sat + (size_t)frame * (size_t)sw * (size_t)(ty + 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int x = threadIdx.x; x < sw; x += blockDim.x) sat[x] = 0;
+  for (int y = w; y < ty; y += nw) {  // row prefixes: one warp per row, 32 tiles per step
+    uint32_t *row = sat + (size_t)(y + 1) * sw;
+    if (lane == 0) row[0] = 0;
+    uint32_t carry = 0;
+    for (int x0 = 0; x0 < tx; x0 += 32) {
+      const int x = x0 + lane;
+      uint32_t v = (x < tx && cover[y * tx + x] == 0) ? 1u : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      v += carry;
+      if (x < tx) row[x + 1] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  for (int x = threadIdx.x + 1; x < sw; x += blockDim.x) {  // column prefixes: coalesced across threads
+    uint32_t run = 0;
+    for (int y = 1; y <= ty; y++) {
+      run += sat[(size_t)y * sw + x];
+      sat[(size_t)y * sw + x] = run;
+    }
+  }
+}
+
+// A path of this chunk is still alive when at least one tile of its bbox is open (one summed-area query).  Alive paths
+// get their slots cleared here (one warp per path, coalesced); dead paths are not flattened, not binned, get no
+// records, and their slots are never read (k_fine checks path_alive first).
+__global__ void k_path_alive(RenderArgs a, uint32_t c) {
+  if (a.totals->overflow) return;
+  const uint32_t frame = blockIdx.y;
+  const uint32_t i0 = chunk_first(a, c, frame), i1 = chunk_first(a, c + 1, frame);
+  const uint32_t p0 = __ldg(a.item_path_off + i0), p1 = __ldg(a.item_path_off + i1);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int sw = a.tiles_x + 1;
+  const uint32_t *sat = a.cover_sat + (size_t)frame * (size_t)sw * (size_t)(a.tiles_y + 1);
+  for (uint32_t pid = p0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); pid < p1; pid += nwarps) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));
+    const int bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
+    bool alive = bw > 0;
+    if (alive && c + 1 != a.n_chunks) {  // nothing has been binned above the top chunk
+      const uint32_t open = __ldg(sat + (size_t)(by0 + bh) * sw + bx0 + bw) - __ldg(sat + (size_t)by0 * sw + bx0 + bw) -
+                            __ldg(sat + (size_t)(by0 + bh) * sw + bx0) + __ldg(sat + (size_t)by0 * sw + bx0);
+      alive = open != 0;
+    }
+    if (lane == 0) {
+      a.path_alive[pid] = alive ? 1u : 0u;
+      a.path_rec_base[pid] = 0;
+      if (alive) {
+        a.item_alive[a.path_item[pid]] = 1u;
+        if (bw * bh > kBackdropSmall) {  // large tile grids are scanned by whole blocks: this chunk's list, and all of them
+          a.big_chunk[atomicAdd(&a.totals->n_big_chunk, 1u)] = pid;
+          a.big_list[atomicAdd(&a.totals->n_big, 1u)] = pid;
+        }
+      }
+    }
+    if (alive) {
+      const uint32_t s0 = a.path_slot_off[pid], n = (uint32_t)(bw * bh);
+      for (uint32_t i = lane; i < n; i += 32) {
+        a.slot_count[s0 + i] = 0;
+        a.slot_backdrop[s0 + i] = 0;
+      }
+    }
+  }
+}
+
 // Emits the flattened edges (16 bytes of geometry + the path instance index).  One warp takes 32 consecutive segment
 // instances (their edges are contiguous in the output), and spreads the pieces of all of them evenly over its lanes:
 // lane k computes the END point of piece k; the start point is the neighbour lane's end point, the segment's first
 // control point, or the last point of the previous round.  Stores are coalesced 16-byte writes.
 constexpr int kEmitWarps = 8;
 
-__global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
   __shared__ int sh_p[kEmitWarps][32][6];
   __shared__ double sh_inv[kEmitWarps][32];
   __shared__ uint32_t sh_pid[kEmitWarps][32];  // path instance | curve << 31
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * kEmitWarps * 32;
-  for (uint32_t base = (blockIdx.x * kEmitWarps + w) * 32; base < a.n_seginst; base += stride) {
+  // segment instances of depth chunk c in frame blockIdx.y
+  const uint32_t s_begin = __ldg(a.item_seg_off + chunk_first(a, c, blockIdx.y));
+  const uint32_t s_end = __ldg(a.item_seg_off + chunk_first(a, c + 1, blockIdx.y));
+  for (uint32_t base = s_begin + (blockIdx.x * kEmitWarps + w) * 32; base < s_end; base += stride) {
     const uint32_t j = base + lane;
     int n = 0;
     uint32_t off = 0;
-    if (j < a.n_seginst) {
+    if (j < s_end) {
       const uint32_t it = a.seg_item[j];
-      const ItemRegs item = load_item(a, it);
-      int p[6];
-      bool curve;
-      uint32_t pid;
-      load_segment(a, item, j - __ldg(a.item_seg_off + it), p, curve, pid);
-      off = a.seg_edge_off[j];
-      n = (int)(a.seg_edge_off[j + 1] - off);
+      bool visible = __ldg(a.item_alive + it) != 0;  // no path of the draw item is visible: skip it at once
+      uint32_t local = 0;
+      if (visible) {
+        local = j - __ldg(a.item_seg_off + it);
+        ItemRegs head;  // the three fields segment_pid needs; the matrix is loaded for visible paths only
+        head.seg_first = __ldg(&a.items[it].seg_first);
+        head.path_off = __ldg(&a.items[it].path_off);
+        head.kind = __ldg(&a.items[it].kind) & ITEM_KIND_MASK;
+        visible = __ldg(a.path_alive + segment_pid(a, head, local)) != 0;
+      }
+      if (visible) {  // hidden paths emit nothing (their edges stay marked ~0)
+        const ItemRegs item = load_item(a, it);
+        int p[6];
+        bool curve;
+        uint32_t pid;
+        load_segment(a, item, local, p, curve, pid);
+        off = a.seg_edge_off[j];
+        n = (int)(a.seg_edge_off[j + 1] - off);
 #pragma unroll
-      for (int k = 0; k < 6; k++) sh_p[w][lane][k] = p[k];
-      sh_inv[w][lane] = piece_inv2den(curve, n);
-      sh_pid[w][lane] = pid | (curve ? 0x80000000u : 0u);
+        for (int k = 0; k < 6; k++) sh_p[w][lane][k] = p[k];
+        sh_inv[w][lane] = piece_inv2den(curve, n);
+        sh_pid[w][lane] = pid | (curve ? 0x80000000u : 0u);
+      }
     }
     int incl = n;
 #pragma unroll
@@ -318,7 +436,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a) 
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int excl = incl - n;
-    const uint32_t off0 = __shfl_sync(0xffffffffu, off, 0);  // edges of this warp's segments start here
     __syncwarp();
     int carry_x = 0, carry_y = 0;
     for (int k0 = 0; k0 < total; k0 += 32) {
@@ -331,6 +448,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a) 
       }
       const int first = __shfl_sync(0xffffffffu, excl, o);
       const int n_o = __shfl_sync(0xffffffffu, n, o);
+      const uint32_t off_o = __shfl_sync(0xffffffffu, off, o);  // first edge of the owner's segment
       const int i = k - first + 1;  // 1..n_o
       int p[6];
 #pragma unroll
@@ -349,8 +467,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a) 
       carry_x = __shfl_sync(0xffffffffu, qx, 31);
       carry_y = __shfl_sync(0xffffffffu, qy, 31);
       if (k0 + (int)lane < total) {
-        a.edges[off0 + (uint32_t)k] = make_int4(px, py, qx, qy);
-        a.edge_pid[off0 + (uint32_t)k] = pc & 0x7fffffffu;
+        a.edges[off_o + (uint32_t)(i - 1)] = make_int4(px, py, qx, qy);
+        a.edge_pid[off_o + (uint32_t)(i - 1)] = pc & 0x7fffffffu;
       }
     }
     __syncwarp();
@@ -618,10 +736,10 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
     if (!valid) bw = bh = 0;
     rec.xy0 = (uint32_t)bx0 | ((uint32_t)by0 << 16);
     rec.wh = (uint32_t)bw | ((uint32_t)bh << 16);
-    rec.info = dp.type | (flags << 8);
+    rec.info = dp.type | (flags << 8) | (item.frame << 16);  // frames per pass < 65536
     a.path_rec[pid] = rec;
     a.path_slot_off[pid] = (uint32_t)(bw * bh);
-    if (bw > 1 && bw * bh > kBackdropSmall) a.big_list[atomicAdd(&a.totals->n_big, 1u)] = pid;
+    a.path_item[pid] = it;
     if (bw > 0) {
       if (item.frame == block_frame) {
         for (int y = 0; y < bh; y++) atomicAdd(&sh_rows[by0 + y], 1u);
@@ -720,14 +838,13 @@ __global__ void k_group_lists(RenderArgs a) {
   }
 }
 
-__global__ void k_zero_slots(RenderArgs a) {
+// Marks every edge as "not emitted" (edge_pid = ~0): with occlusion culling only the geometry of paths that are still
+// visible somewhere is emitted and binned.  (The slots of those paths are cleared by k_path_alive.)
+__global__ void k_clear_edges(RenderArgs a) {
   if (a.totals->overflow) return;
-  uint32_t n = a.totals->n_slots;
   uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    a.slot_count[i] = 0;
-    a.slot_backdrop[i] = 0;
-  }
+  uint32_t ne = a.totals->n_edges;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += stride) a.edge_pid[i] = 0xffffffffu;
 }
 
 // ======================================================================================================
@@ -807,7 +924,6 @@ __device__ __forceinline__ BandPiece band_setup(const RenderArgs &a, int x0, int
   return p;
 }
 
-constexpr uint32_t kStageInvalid = 0xffffffffu;
 
 // One tile column `t` of a band piece: the tile-clipped record (or an invalid marker when the clipped piece is a
 // point).  The crossings with the tile's left and right boundary lines come straight from the band piece
@@ -846,36 +962,42 @@ __device__ __forceinline__ bool column_record(int xs, int ys, int xe, int ye, in
 // geometry again.
 constexpr int kBinWarps = 8;
 
-__global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
+__global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
   __shared__ int4 sh_edge[kBinWarps][32];
   __shared__ uint4 sh_path[kBinWarps][32];   // xy0, bw | first band << 16, slot base, path instance
   __shared__ int4 sh_piece[kBinWarps][32];   // band piece xs, ys, xe, ye
-  __shared__ uint4 sh_pmeta[kBinWarps][32];  // first column, slot of that column, band top, path instance | small << 31
-  const uint32_t n = a.totals->n_edges;
+  __shared__ uint4 sh_pmeta[kBinWarps][32];  // first column, slot of that column, band row, path instance | small << 31
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * kBinWarps * 32;
   const uint32_t cap_blocks = a.caps.stage / kStageBlock;
+  // edges of depth chunk c in frame blockIdx.y (segments, hence edges, are stored in item order)
+  const uint32_t frame = blockIdx.y;
+  const uint32_t e_begin = a.seg_edge_off[__ldg(a.item_seg_off + chunk_first(a, c, frame))];
+  const uint32_t e_end = a.seg_edge_off[__ldg(a.item_seg_off + chunk_first(a, c + 1, frame))];
+  const uint32_t *cover = a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y);
   uint32_t blk = 0, blk_used = kStageBlock;  // current staging block of this warp (none yet)
-  bool have_blk = false, dead = false;
-  for (uint32_t base = (blockIdx.x * kBinWarps + w) * 32; base < n; base += stride) {
+  bool have_blk = false, stage_full = false;
+  for (uint32_t base = e_begin + (blockIdx.x * kBinWarps + w) * 32; base < e_end; base += stride) {
     const uint32_t e = base + lane;
     int nb = 0;
-    if (e < n) {
-      const int4 ed = a.edges[e];
+    if (e < e_end) {
       const uint32_t pid = a.edge_pid[e];
-      const PathRec rec = a.path_rec[pid];
-      const int bw = rec.wh & 0xffff, bh = rec.wh >> 16, by0 = rec.xy0 >> 16;
-      if (bw) {
-        const int ylo = min(ed.y, ed.w), yhi = max(ed.y, ed.w);
-        int b_first = ylo >> 12, b_last = (ed.y == ed.w) ? b_first : (yhi - 1) >> 12;
-        // rows outside the path's grid are outside the viewport (the bbox covers every edge of the path)
-        b_first = max(b_first, by0);
-        b_last = min(b_last, by0 + bh - 1);
-        if (b_first <= b_last) {
-          nb = b_last - b_first + 1;
-          sh_edge[w][lane] = ed;
-          sh_path[w][lane] = make_uint4(rec.xy0, (uint32_t)bw | ((uint32_t)b_first << 16), a.path_slot_off[pid], pid);
+      if (pid != 0xffffffffu) {  // ~0: the edge was not emitted (its path is hidden)
+        const int4 ed = a.edges[e];
+        const PathRec rec = a.path_rec[pid];
+        const int bw = rec.wh & 0xffff, bh = rec.wh >> 16, by0 = rec.xy0 >> 16;
+        if (bw) {
+          const int ylo = min(ed.y, ed.w), yhi = max(ed.y, ed.w);
+          int b_first = ylo >> 12, b_last = (ed.y == ed.w) ? b_first : (yhi - 1) >> 12;
+          // rows outside the path's grid are outside the viewport (the bbox covers every edge of the path)
+          b_first = max(b_first, by0);
+          b_last = min(b_last, by0 + bh - 1);
+          if (b_first <= b_last) {
+            nb = b_last - b_first + 1;
+            sh_edge[w][lane] = ed;
+            sh_path[w][lane] = make_uint4(rec.xy0, (uint32_t)bw | ((uint32_t)b_first << 16), a.path_slot_off[pid], pid);
+          }
         }
       }
     }
@@ -910,7 +1032,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
         if (piece.c1 >= piece.c0) {
           nc = (uint32_t)(piece.c1 - piece.c0 + 1);
           sh_piece[w][lane] = make_int4(piece.xs, piece.ys, piece.xe, piece.ye);
-          sh_pmeta[w][lane] = make_uint4((uint32_t)piece.c0, piece.row_base + (uint32_t)(piece.c0 - bx0), (uint32_t)piece.Yt,
+          sh_pmeta[w][lane] = make_uint4((uint32_t)piece.c0, piece.row_base + (uint32_t)(piece.c0 - bx0), (uint32_t)b,
                                          pp.w | (small ? 0x80000000u : 0u));
         }
       }
@@ -923,30 +1045,6 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
       const uint32_t ctotal = __shfl_sync(0xffffffffu, cincl, 31);
       if (ctotal == 0) continue;
       const uint32_t cexcl = cincl - nc;
-      // ---- staging space for this round: one entry per (piece, column) ----
-      const uint32_t rem = kStageBlock - blk_used;  // room left in the current block
-      const uint32_t old_pos = blk * kStageBlock + blk_used;
-      uint32_t new_pos = 0;
-      if (ctotal > rem) {  // continue in freshly allocated block(s): one atomic for all of them
-        const uint32_t need = ctotal - rem, nblk = (need + kStageBlock - 1) / kStageBlock;
-        uint32_t first_blk = 0;
-        if (lane == 0) first_blk = atomicAdd(&a.totals->n_stage_blocks, nblk);
-        first_blk = __shfl_sync(0xffffffffu, first_blk, 0);
-        if (first_blk + nblk > cap_blocks) {
-          if (lane == 0) atomicOr(&a.totals->overflow_stage, 1u);
-          dead = true;
-        }
-        if (!dead && lane == 0) {
-          if (have_blk) a.stage_used[blk] = kStageBlock;
-          for (uint32_t q = 0; q + 1 < nblk; q++) a.stage_used[first_blk + q] = kStageBlock;
-        }
-        new_pos = first_blk * kStageBlock;
-        blk = first_blk + nblk - 1;
-        blk_used = need - (nblk - 1) * kStageBlock;
-        have_blk = true;
-      } else {
-        blk_used += ctotal;
-      }
       __syncwarp();
       // ---- level 2: lane <-> (piece, column) ----
       for (uint32_t i0 = 0; i0 < ctotal; i0 += 32) {
@@ -958,34 +1056,59 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a) {
           if (v <= idx) o2 += step;
         }
         const uint32_t cfirst = __shfl_sync(0xffffffffu, cexcl, o2);
+        bool keep = false;
+        unsigned long long rc = 0;
+        uint32_t slot = 0, pid = 0;
         if (i0 + lane < ctotal) {
-          const int4 pc = sh_piece[w][o2];
           const uint4 pm = sh_pmeta[w][o2];
           const uint32_t j = idx - cfirst;
-          unsigned long long rc;
-          const bool keep = (pm.w >> 31) ? column_record<true>(pc.x, pc.y, pc.z, pc.w, (int)pm.z, (int)(pm.x + j), rc)
-                                         : column_record<false>(pc.x, pc.y, pc.z, pc.w, (int)pm.z, (int)(pm.x + j), rc);
-          const uint32_t slot = pm.y + j;
-          if (keep) atomicAdd(&a.slot_count[slot], 1u);
-          if (!dead) {
-            // streaming store: staging is written once here and read once by k_scatter
-            const uint32_t pos = idx < rem ? old_pos + idx : new_pos + (idx - rem);
-            __stcs(a.stage + pos, make_uint4((uint32_t)rc, (uint32_t)(rc >> 32), keep ? slot : kStageInvalid, pm.w & 0x7fffffffu));
+          pid = pm.w & 0x7fffffffu;
+          slot = pm.y + j;
+          // occlusion culling: an opaque path of a chunk above covers this tile completely
+          if (__ldg(cover + pm.z * (uint32_t)a.tiles_x + pm.x + j) <= pid) {
+            const int4 pc = sh_piece[w][o2];
+            const int Yt = (int)pm.z * kTileFx;
+            keep = (pm.w >> 31) ? column_record<true>(pc.x, pc.y, pc.z, pc.w, Yt, (int)(pm.x + j), rc)
+                                : column_record<false>(pc.x, pc.y, pc.z, pc.w, Yt, (int)(pm.x + j), rc);
           }
         }
+        const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
+        if (kmask == 0) continue;
+        const uint32_t kcount = __popc(kmask);
+        if (!have_blk || blk_used + kcount > kStageBlock) {  // next staging block of this warp
+          if (have_blk && !stage_full && lane == 0) a.stage_used[blk] = blk_used;
+          uint32_t nb2 = 0;
+          if (lane == 0) nb2 = atomicAdd(&a.totals->n_stage_blocks, 1u);
+          blk = __shfl_sync(0xffffffffu, nb2, 0);
+          if (blk >= cap_blocks) {
+            if (lane == 0) atomicOr(&a.totals->overflow_stage, 1u);
+            stage_full = true;
+          }
+          blk_used = 0;
+          have_blk = true;
+        }
+        if (keep) {
+          atomicAdd(&a.slot_count[slot], 1u);
+          if (!stage_full) {
+            // streaming store: staging is written once here and read once by k_scatter
+            const uint32_t pos = blk * kStageBlock + blk_used + __popc(kmask & ((1u << lane) - 1u));
+            __stcs(a.stage + pos, make_uint4((uint32_t)rc, (uint32_t)(rc >> 32), slot, pid));
+          }
+        }
+        blk_used += kcount;
       }
       __syncwarp();
     }
     __syncwarp();
   }
-  if (have_blk && !dead && lane == 0) a.stage_used[blk] = blk_used;
+  if (have_blk && !stage_full && lane == 0) a.stage_used[blk] = blk_used;
 }
 
 // K2, pass 2 of 2: staged records -> their slots.  slot_off holds the END of the slot's record range (relative to the
 // path's base); the counts of pass 1 double as cursors and run back down to zero (order inside a slot is irrelevant:
 // coverage accumulation is integer).
 __global__ void k_scatter(RenderArgs a) {
-  if (a.totals->overflow) return;
+  if (a.totals->overflow | a.totals->overflow_stage) return;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t nblk = min(a.totals->n_stage_blocks, a.caps.stage / kStageBlock);
@@ -994,7 +1117,6 @@ __global__ void k_scatter(RenderArgs a) {
     const uint4 *st = a.stage + (size_t)b * kStageBlock;
     for (uint32_t i = lane; i < used; i += 32) {
       const uint4 e = __ldcs(st + i);
-      if (e.z == kStageInvalid) continue;
       const uint32_t pos = a.path_rec_base[e.w] + a.slot_off[e.z] - atomicSub(&a.slot_count[e.z], 1u);
       a.records[pos] = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
     }
@@ -1008,53 +1130,60 @@ __global__ void k_scatter(RenderArgs a) {
 //     record space is allocated path by path, so there is no global scan over the (much longer) slot array.
 // Grids of up to kBackdropSmall slots: one warp per path, 32 slots per step, coalesced.  Larger grids: one block
 // per path (second kernel), so that a full-screen path is not a serial tail.
-__global__ void k_slot_prefix(RenderArgs a) {
-  if (a.totals->overflow) return;
-  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t pid = warp; pid < a.n_paths; pid += nwarps) {
-    uint32_t wh = a.path_rec[pid].wh;
-    int bw = wh & 0xffff, bh = wh >> 16;
-    const int n = bw * bh;
-    if (n == 0) {
-      if (lane == 0) a.path_rec_base[pid] = 0;
-      continue;
+// First record of a path instance: record space is handed out path by path from one cursor (the placement of the
+// paths in the record buffer varies from run to run; nothing observable depends on it).
+__device__ __forceinline__ uint32_t alloc_records(const RenderArgs &a, uint32_t total) {
+  if (total == 0) return 0u;
+  const uint32_t base = atomicAdd(&a.totals->n_records, total);
+  if (base + total > a.caps.records || base + total < base) atomicOr(&a.totals->overflow, 4u);
+  return base;
+}
+
+// One warp, one path instance of up to kBackdropSmall slots, 32 slots per step (4 steps' loads in flight).
+//   BACKDROP: prefix sum of the backdrop deltas along each tile row, and - for opaque paths - an atomicMax on
+//             tile_cover for every slot without records and with a non-zero winding number (a full-tile cover);
+//   COUNT:    inclusive prefix of the record counts -> slot_off, total -> record allocation.
+template <bool BACKDROP, bool COUNT>
+__device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pid, const uint4 rec, uint32_t lane, uint32_t *cover) {
+  const int bx0 = rec.x & 0xffff, by0 = rec.x >> 16, bw = rec.y & 0xffff, bh = rec.y >> 16;
+  const bool opaque = (rec.z >> 8) & 1u;
+  const int n = bw * bh;
+  const uint32_t s0 = a.path_slot_off[pid];
+  int32_t *bd = a.slot_backdrop + s0;
+  const uint32_t *cnt = a.slot_count + s0;
+  uint32_t *end = a.slot_off + s0;
+  int carry = 0, carry_row = -1;
+  uint32_t ccarry = 0;
+  for (int i0 = 0; i0 < n; i0 += 128) {
+    uint32_t c4[4];
+    int v4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int i = i0 + 32 * u + (int)lane;
+      c4[u] = i < n ? cnt[i] : 0u;
+      v4[u] = (BACKDROP && i < n) ? bd[i] : 0;
     }
-    if (n > kBackdropSmall) continue;
-    const uint32_t s0 = a.path_slot_off[pid];
-    int32_t *bd = a.slot_backdrop + s0;
-    const uint32_t *cnt = a.slot_count + s0;
-    uint32_t *end = a.slot_off + s0;
-    int carry = 0, carry_row = -1;
-    uint32_t ccarry = 0;
-    for (int i0 = 0; i0 < n; i0 += 128) {
-      // four steps' worth of loads in flight before the (serial) scans
-      uint32_t c4[4];
-      int v4[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        int i = i0 + 32 * u + (int)lane;
-        c4[u] = i < n ? cnt[i] : 0u;
-        v4[u] = (i < n && bw > 1) ? bd[i] : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        int i = i0 + 32 * u + (int)lane;
-        if (i0 + 32 * u >= n) break;
-        bool ok = i < n;
-        uint32_t c = c4[u];
+    for (int u = 0; u < 4; u++) {
+      int i = i0 + 32 * u + (int)lane;
+      if (i0 + 32 * u >= n) break;
+      bool ok = i < n;
+      if (COUNT) {
+        uint32_t cc = c4[u];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          uint32_t t = __shfl_up_sync(0xffffffffu, c, o);
-          if ((int)lane >= o) c += t;
+          uint32_t t = __shfl_up_sync(0xffffffffu, cc, o);
+          if ((int)lane >= o) cc += t;
         }
-        c += ccarry;
-        if (ok) end[i] = c;
-        ccarry = __shfl_sync(0xffffffffu, c, 31);
+        cc += ccarry;
+        if (ok) end[i] = cc;
+        ccarry = __shfl_sync(0xffffffffu, cc, 31);
+      }
+      if (BACKDROP) {
+        int row = ok ? i / bw : -2;
+        int col = ok ? i - row * bw : 0;
+        int v = v4[u];
         if (bw > 1) {
-          int row = ok ? i / bw : -2;
-          int col = ok ? i - row * bw : 0;
-          int v = v4[u];
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, v, o);
@@ -1065,25 +1194,26 @@ __global__ void k_slot_prefix(RenderArgs a) {
           carry = __shfl_sync(0xffffffffu, v, 31);
           carry_row = __shfl_sync(0xffffffffu, row, 31);
         }
+        // an opaque path covers this tile completely: it hides the chunks below
+        if (ok && opaque && c4[u] == 0 && v != 0) atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + col, pid + 1u);
       }
     }
-    if (lane == 0) a.path_rec_base[pid] = ccarry;  // total; turned into the base by a scan over the paths
   }
+  if (COUNT && lane == 0) a.path_rec_base[pid] = alloc_records(a, ccarry);
 }
 
-__global__ void __launch_bounds__(256) k_slot_prefix_big(RenderArgs a) {
-  if (a.totals->overflow) return;
-  __shared__ uint32_t sh[32];
+// The same for a path instance with a larger tile grid, by one block: warps over rows for the backdrop, a block-wide
+// prefix for the counts.
+template <bool BACKDROP, bool COUNT>
+__device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid, const uint4 rec, uint32_t *cover, uint32_t *sh) {
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const uint32_t n_big = a.totals->n_big;
-  for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
-    const uint32_t pid = a.big_list[bi];
-    const uint32_t wh = a.path_rec[pid].wh;
-    const int bw = wh & 0xffff, bh = wh >> 16;
-    const uint32_t s0 = a.path_slot_off[pid];
-    // backdrop: warps over rows
+  const int bx0 = rec.x & 0xffff, by0 = rec.x >> 16, bw = rec.y & 0xffff, bh = rec.y >> 16;
+  const bool opaque = (rec.z >> 8) & 1u;
+  const uint32_t s0 = a.path_slot_off[pid];
+  if (BACKDROP) {
     for (int row = (int)w; row < bh; row += (int)nw) {
       int32_t *q = a.slot_backdrop + s0 + row * bw;
+      const uint32_t *cq = a.slot_count + s0 + row * bw;
       int carry = 0;
       for (int x0 = 0; x0 < bw; x0 += 32) {
         int x = x0 + (int)lane;
@@ -1094,29 +1224,95 @@ __global__ void __launch_bounds__(256) k_slot_prefix_big(RenderArgs a) {
           if ((int)lane >= o) v += t;
         }
         v += carry;
-        if (x < bw) q[x] = v;
+        if (x < bw) {
+          q[x] = v;
+          if (opaque && v != 0 && cq[x] == 0) atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + x, pid + 1u);
+        }
         carry = __shfl_sync(0xffffffffu, v, 31);
       }
     }
-    // record counts: block-wide inclusive prefix over the whole grid, 4 slots per thread and step
+  }
+  if (COUNT) {
     const uint32_t n = (uint32_t)(bw * bh);
     uint32_t carry = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x * 4) {
       const uint32_t i = i0 + threadIdx.x * 4;
-      uint32_t c[4];
+      uint32_t cc[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) c[k] = i + k < n ? a.slot_count[s0 + i + k] : 0u;
+      for (int k = 0; k < 4; k++) cc[k] = i + k < n ? a.slot_count[s0 + i + k] : 0u;
       uint32_t tile_total;
-      uint32_t run = carry + block_exclusive(c[0] + c[1] + c[2] + c[3], sh, &tile_total);
+      uint32_t run = carry + block_exclusive(cc[0] + cc[1] + cc[2] + cc[3], sh, &tile_total);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        run += c[k];
+        run += cc[k];
         if (i + k < n) a.slot_off[s0 + i + k] = run;
       }
       carry += tile_total;
     }
-    if (threadIdx.x == 0) a.path_rec_base[pid] = carry;
+    if (threadIdx.x == 0) a.path_rec_base[pid] = alloc_records(a, carry);
     __syncthreads();
+  }
+}
+
+constexpr int kBigBlocksPerFrame = 16;  // blocks (per frame row of the grid) that serve the large-grid paths
+
+// Per depth chunk, after its binning: winding numbers (backdrop prefix) of the chunk's visible paths, and the tiles
+// they cover opaquely.  grid = (small-path blocks + kBigBlocksPerFrame, frames).
+__global__ void __launch_bounds__(256) k_cover(RenderArgs a, uint32_t c) {
+  if (a.totals->overflow) return;
+  __shared__ uint32_t sh[32];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t small_blocks = gridDim.x - kBigBlocksPerFrame;
+  if (blockIdx.x < small_blocks) {
+    const uint32_t frame = blockIdx.y;
+    const uint32_t p0 = __ldg(a.item_path_off + chunk_first(a, c, frame)), p1 = __ldg(a.item_path_off + chunk_first(a, c + 1, frame));
+    const uint32_t nwarps = (small_blocks * blockDim.x) >> 5;
+    uint32_t *cover = a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y);
+    for (uint32_t pid = p0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); pid < p1; pid += nwarps) {
+      if (!a.path_alive[pid]) continue;
+      const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
+      const uint32_t n = (rec.y & 0xffff) * (rec.y >> 16);
+      if (n == 0 || n > (uint32_t)kBackdropSmall) continue;
+      small_path_scan<true, false>(a, pid, rec, lane, cover);
+    }
+  } else {
+    const uint32_t n_big = a.totals->n_big_chunk;  // the visible large paths of this chunk (k_path_alive)
+    const uint32_t nb = kBigBlocksPerFrame * gridDim.y;
+    for (uint32_t bi = (blockIdx.x - small_blocks) * gridDim.y + blockIdx.y; bi < n_big; bi += nb) {
+      const uint32_t pid = a.big_chunk[bi];
+      const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
+      const uint32_t frame = rec.z >> 16;
+      big_path_scan<true, false>(a, pid, rec, a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y), sh);
+    }
+  }
+}
+
+// After the last chunk: inclusive prefix of the record counts of every visible path -> slot_off (END of each slot's
+// record range, relative to the path) and the path's first record (alloc_records).  Record space is allocated path
+// by path, so there is no global scan over the (much longer) slot array.  grid.x = small-path blocks + big blocks.
+constexpr int kPrefixBigBlocks = kNumSM * 2;
+
+__global__ void __launch_bounds__(256) k_slot_prefix(RenderArgs a) {
+  if (a.totals->overflow) return;
+  __shared__ uint32_t sh[32];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t small_blocks = gridDim.x - kPrefixBigBlocks;
+  if (blockIdx.x < small_blocks) {
+    const uint32_t nwarps = (small_blocks * blockDim.x) >> 5;
+    for (uint32_t pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < a.n_paths; pid += nwarps) {
+      if (!a.path_alive[pid]) continue;
+      const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
+      const uint32_t n = (rec.y & 0xffff) * (rec.y >> 16);
+      if (n == 0 || n > (uint32_t)kBackdropSmall) continue;
+      small_path_scan<false, true>(a, pid, rec, lane, nullptr);
+    }
+  } else {
+    const uint32_t n_big = a.totals->n_big;
+    for (uint32_t bi = blockIdx.x - small_blocks; bi < n_big; bi += kPrefixBigBlocks) {
+      const uint32_t pid = a.big_list[bi];  // visible large paths of all chunks
+      const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
+      big_path_scan<false, true>(a, pid, rec, nullptr, sh);
+    }
   }
 }
 
@@ -1294,6 +1490,7 @@ __device__ __forceinline__ Probe probe_slot(const RenderArgs &a, uint32_t pid, b
   int bx0 = rc.x & 0xffff, by0 = rc.x >> 16, bw = rc.y & 0xffff, bh = rc.y >> 16;
   int lx = tx - bx0, ly = ty - by0;
   if (lx < 0 || ly < 0 || lx >= bw || ly >= bh) return pr;
+  if (!__ldg(a.path_alive + pid)) return pr;  // hidden everywhere: never binned, its slots hold nothing
   const uint32_t local = (uint32_t)(ly * bw + lx);
   const uint32_t slot = __ldg(a.path_slot_off + pid) + local;
   const uint32_t rec_base = __ldg(a.path_rec_base + pid);
@@ -1435,6 +1632,7 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
 
     // ---- pass 2: composite in paint order ----
     uint32_t px[8];
+    uint32_t n_hits = 0, n_recs = 0;
     const uint32_t bg = __ldg(a.frame_bg + frame);
 #pragma unroll
     for (int i = 0; i < 8; i++) px[i] = bg;
@@ -1453,6 +1651,8 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
         uint32_t color = __shfl_sync(0xffffffffu, pr.color, src_lane);
         uint32_t cur_pid = __shfl_sync(0xffffffffu, pid, src_lane);
         uint32_t type = info & 0xff;
+        n_hits++;
+        n_recs += o1 - o0;
         uint32_t m[8];
         if (o1 == o0) {
 #pragma unroll
@@ -1474,6 +1674,10 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
       }
     }
 
+    if (lane == 0) {  // statistics: what this tile composited (swfr_stats.fine_*)
+      atomicAdd(&a.totals->fine_hits, n_hits);
+      atomicAdd(&a.totals->fine_records, n_recs);
+    }
     // ---- store: 8 pixels = 32 bytes per lane ----
     if (Y < a.height) {
       uint32_t *dst = a.frames + ((size_t)frame * a.height + Y) * a.width + X0;
@@ -1579,8 +1783,7 @@ static void scan_u32(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, 
 }
 
 const char *stage_name(int i) {
-  static const char *names[kNumStages] = {"flatten_count", "scan_edges",   "path_setup",  "flatten_emit",
-                                          "bin_count",     "slot_prefix", "bin_scatter", "fine"};
+  static const char *names[kNumStages] = {"flatten_count", "scan_edges", "path_setup", "lists", "bin_chunks", "fine"};
   return (i >= 0 && i < kNumStages) ? names[i] : "?";
 }
 
@@ -1615,6 +1818,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   }
   scan_u32(a.path_slot_off, a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
            st, launches);
+  mark(3);
   // candidate lists: row counts (from path setup) -> row lists -> group counts -> group lists
   scan_u32(a.row_count, a.row_off, nullptr, a.n_frames * (uint32_t)a.tiles_y, a.scan_tmp, &a.totals->n_rowent, a.caps.rows,
            &a.totals->overflow, 16u, st, launches);
@@ -1623,36 +1827,33 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
            launches);
   k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);
-  k_zero_slots<<<wide, T, 0, st>>>(a);
+  k_clear_edges<<<wide, T, 0, st>>>(a);
   launches += 2;
-  mark(3);
-  if (a.n_seginst) {
-    k_flatten_emit<<<grid_for(a.n_seginst), kEmitWarps * 32, 0, st>>>(a);
-    launches++;
-  }
   mark(4);
-  if (a.n_seginst) {
-    k_bin<<<wide, kBinWarps * 32, 0, st>>>(a);
-    launches++;
-  }
-  mark(5);
-  // backdrop prefix + record allocation (slot_count -> slot_off, path_rec_base, totals.n_records)
-  if (a.n_paths) {
-    k_slot_prefix<<<grid_for((uint64_t)a.n_paths * 32), T, 0, st>>>(a);
-    k_slot_prefix_big<<<kNumSM * 4, T, 0, st>>>(a);
+  // K1 emit + K2, depth chunk by depth chunk from the top one down: what a chunk covers opaquely hides the
+  // geometry of the chunks below it (grid.y = frame; every kernel walks its frame's part of the chunk)
+  if (a.n_seginst && a.n_paths) {
+    const unsigned per_frame = std::max(1u, wide / std::max(1u, a.n_frames));
+    const dim3 g2(per_frame, a.n_frames);
+    for (uint32_t c = a.n_chunks; c-- > 0;) {
+      if (c + 1 != a.n_chunks) {
+        k_cover_sat<<<a.n_frames, 256, 0, st>>>(a);
+        launches++;
+      }
+      k_path_alive<<<g2, T, 0, st>>>(a, c);
+      k_flatten_emit<<<g2, kEmitWarps * 32, 0, st>>>(a, c);
+      k_bin<<<g2, kBinWarps * 32, 0, st>>>(a, c);
+      k_cover<<<dim3(per_frame + kBigBlocksPerFrame, a.n_frames), T, 0, st>>>(a, c);
+      launches += 4;
+    }
+    k_slot_prefix<<<grid_for((uint64_t)a.n_paths * 32) + kPrefixBigBlocks, T, 0, st>>>(a);
+    k_scatter<<<wide, T, 0, st>>>(a);
     launches += 2;
   }
-  scan_u32(a.path_rec_base, a.path_rec_base, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_records, a.caps.records,
-           &a.totals->overflow, 4u, st, launches);
-  mark(6);
-  if (a.n_seginst) {
-    k_scatter<<<wide, T, 0, st>>>(a);
-    launches++;
-  }
-  mark(7);
+  mark(5);
   k_fine<<<kNumSM * 4, kFineWarps * 32, 0, st>>>(a);
   launches++;
-  mark(8);
+  mark(6);
   return launches;
 }
 

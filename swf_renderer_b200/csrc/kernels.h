@@ -67,11 +67,14 @@ struct Totals {
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work;      // fine-kernel tile queue
   uint32_t n_list;    // candidate-list entries
-  uint32_t n_big;     // path instances whose tile grid is larger than kBackdropSmall
+  uint32_t n_big;     // visible path instances whose tile grid is larger than kBackdropSmall
+  uint32_t n_big_chunk;  // ... of the depth chunk being processed
   uint32_t n_rowent;  // row-list entries
   uint32_t n_stage_blocks;  // staging blocks handed out by the binning pass
   uint32_t overflow_stage;  // the staging buffer was too small (found while binning, after the scans)
-  uint32_t pad[1];
+  uint32_t fine_hits;       // (path, tile) slots composited by k_fine
+  uint32_t fine_records;    // records read by k_fine (the rest of n_records was binned but hidden)
+  uint32_t pad[2];
 };
 
 struct Caps {
@@ -109,6 +112,14 @@ struct RenderArgs {
   unsigned long long *records;  // caps.records
   uint4 *stage;             // caps.stage: (record lo, record hi, slot, path instance) in binning order
   uint32_t *stage_used;     // caps.stage / 256: entries used in each staging block
+  // occlusion culling by depth chunks: the items of every frame are split into n_chunks ranges
+  // in paint order; chunks are binned from the top one down, and what a chunk finds completely covered by an opaque
+  // path hides the geometry of the chunks below it
+  uint32_t n_chunks;            // host-known
+  const uint32_t *chunk_items;  // (n_chunks + 1) * n_frames: first item of chunk c in frame f at [c * n_frames + f]
+  uint32_t *tile_cover;         // n_frames * tiles: 1 + the highest path instance that covers the tile opaquely, 0 = none
+  uint32_t *path_alive;         // n_paths: 0 when every tile of the path's bbox is covered from above
+  uint32_t *cover_sat;          // n_frames * (tiles_x + 1) * (tiles_y + 1): summed-area table of uncovered tiles
   uint32_t *frames;         // n_frames * width * height
   uint32_t *scan_tmp;       // >= 4096 words
   // candidate lists: for every (frame, tile row, group of kGroupTiles tile columns) the path instances whose
@@ -119,14 +130,19 @@ struct RenderArgs {
   uint32_t *row_count;         // n_frames * tiles_y: path instances whose bbox covers the tile row
   uint32_t *row_off;           // n_frames * tiles_y + 1
   uint2 *row_items;            // caps.rows: (path instance, bx0 | bw << 16) per row, in paint order
-  uint32_t *big_list;          // n_paths: path instances with large tile grids
+  uint32_t *big_list;          // n_paths: visible path instances with large tile grids
+  uint32_t *big_chunk;         // n_paths: ... of the depth chunk being processed
+  uint32_t *path_item;         // n_paths: draw item of each path instance
+  uint32_t *item_alive;        // n_items: 1 when any path instance of the draw item is visible
   Totals *totals;
   Caps caps;
 };
 
 // Pipeline stages as seen by the profiler hooks (swfr_get_stage_times).
-constexpr int kNumStages = 8;
+constexpr int kNumStages = 6;
 const char *stage_name(int i);
+
+constexpr int kMaxChunks = 8;
 
 // Enqueues every kernel of one render on `stream`; returns the number of kernels launched.
 // `ev` (optional) points at kNumStages + 1 events recorded at the stage boundaries.

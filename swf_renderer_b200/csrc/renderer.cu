@@ -73,7 +73,8 @@ struct PinnedBuf {
 struct Pass {
   uint32_t f0 = 0, n_frames = 0, n_items = 0, n_seginst = 0, n_paths = 0;
   // offsets into the batch-wide host/device arrays
-  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0;
+  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0, chunk_at = 0;
+  uint32_t n_chunks = 1;  // depth chunks for occlusion culling
 };
 
 struct BitmapRes {
@@ -103,10 +104,11 @@ struct swfr_batch {
   std::vector<Pass> passes;
   PinnedArr<DrawItem> items;
   PinnedArr<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
+  PinnedArr<uint32_t> chunk_items;                   // per pass: (n_chunks + 1) x n_frames first items of the depth chunks
   PinnedArr<uint32_t> frame_bg;                      // per frame: premultiplied RGBA8 the frame starts from
   PinnedArr<SegStatic> dyn_segs;                     // outlines of morph-shape strokes expanded for this batch's draws
   PinnedArr<DefPaint> dyn_paints;
-  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints, d_frame_bg;
+  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints, d_frame_bg, d_chunk_items;
   bool resident = false;
   uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
   cudaEvent_t uploaded = nullptr;  // recorded on the upload stream after the H2D copies
@@ -139,13 +141,14 @@ struct swfr_renderer {
 
   // ---- working memory ----
   DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch, scratch2, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used;
+      slot_off, records, frames, scan_tmp, totals, scratch, scratch2, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive;
   Caps caps{0, 0, 0, 0, 0, 0};
   PinnedBuf pin_totals;
   swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
   int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
   uint32_t host_threads = 0;    // stage flattening threads (0 = min(8, hardware))
   bool clear_to_background = false;
+  uint32_t occlusion_chunks = 0;  // 0 = automatic, 1 = no culling, n = n depth chunks
   bool tiny_arena = false;  // debug: start every working array at a few hundred entries so that growth + re-run is exercised
   cudaStream_t up_stream = nullptr;
 
@@ -412,6 +415,31 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     b.passes.push_back(p);
   }
   if (dyn_seg_at > 0xfffffff0ull) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "too many stroke segments in one batch");
+  // Depth chunks (occlusion culling): the items of every frame are split in paint order into n_chunks ranges whose
+  // sizes double from the top (last painted) chunk downwards - most tiles are covered by the first few opaque
+  // shapes from the top, and everything under a cover is neither flattened nor binned.
+  size_t chunk_at = 0;
+  for (Pass &p : b.passes) {
+    uint64_t max_items = 0;
+    for (uint32_t f = p.f0; f < p.f0 + p.n_frames; f++) max_items = std::max<uint64_t>(max_items, sums[f].items);
+    p.n_chunks = r->occlusion_chunks ? r->occlusion_chunks : (max_items >= 1024 ? 5u : 1u);
+    p.chunk_at = chunk_at;
+    chunk_at += (size_t)(p.n_chunks + 1) * p.n_frames;
+  }
+  CK(b.chunk_items.resize(chunk_at));
+  for (const Pass &p : b.passes) {
+    uint32_t it_run = 0;
+    const uint64_t denom = (1ull << p.n_chunks) - 1;
+    for (uint32_t f = p.f0; f < p.f0 + p.n_frames; f++) {
+      const uint64_t ni = sums[f].items;
+      for (uint32_t c = 0; c <= p.n_chunks; c++) {
+        // chunk c starts after the bottom (2^n - 2^(n-c)) / (2^n - 1) of the items
+        const uint64_t above = ((1ull << (p.n_chunks - c)) - 1) * ni / denom;
+        b.chunk_items[p.chunk_at + (size_t)c * p.n_frames + (f - p.f0)] = it_run + (uint32_t)(ni - above);
+      }
+      it_run += (uint32_t)ni;
+    }
+  }
   b.n_prims = total_prims;
   CK(b.items.resize(items_at));
   CK(b.seg_off.resize(seg_off_at));
@@ -497,6 +525,9 @@ int upload_batch(swfr_renderer *r, swfr_batch &b) {
   if (b.path_off.bytes()) CK(cudaMemcpyAsync(b.d_path_off.p, b.path_off.data(), b.path_off.bytes(), cudaMemcpyHostToDevice, st));
   if (b.frame_off.bytes())
     CK(cudaMemcpyAsync(b.d_frame_off.p, b.frame_off.data(), b.frame_off.bytes(), cudaMemcpyHostToDevice, st));
+  CK(b.d_chunk_items.reserve(std::max<size_t>(b.chunk_items.bytes(), 256)));
+  if (b.chunk_items.bytes())
+    CK(cudaMemcpyAsync(b.d_chunk_items.p, b.chunk_items.data(), b.chunk_items.bytes(), cudaMemcpyHostToDevice, st));
   CK(b.d_frame_bg.reserve(std::max<size_t>(b.frame_bg.bytes(), 256)));
   if (b.frame_bg.bytes()) CK(cudaMemcpyAsync(b.d_frame_bg.p, b.frame_bg.data(), b.frame_bg.bytes(), cudaMemcpyHostToDevice, st));
   CK(b.d_dyn_segs.reserve(std::max<size_t>(b.dyn_segs.bytes(), 256)));
@@ -523,6 +554,21 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   CK(r->path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
   CK(r->path_rec_base.reserve(((size_t)max_paths + 1) * 4 + 256));
   CK(r->big_list.reserve((size_t)max_paths * 4 + 256));
+  CK(r->big_chunk.reserve((size_t)max_paths * 4 + 256));
+  CK(r->path_item.reserve((size_t)max_paths * 4 + 256));
+  {
+    uint32_t max_items = 0;
+    for (const Pass &p : b.passes) max_items = std::max(max_items, p.n_items);
+    CK(r->item_alive.reserve((size_t)max_items * 4 + 256));
+  }
+  CK(r->path_alive.reserve((size_t)max_paths * 4 + 256));
+
+  {
+    uint32_t max_frames = 1;
+    for (const Pass &p : b.passes) max_frames = std::max(max_frames, p.n_frames);
+    CK(r->tile_cover.reserve((size_t)max_frames * r->tiles_x * r->tiles_y * 4 + 256));
+    CK(r->cover_sat.reserve((size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256));
+  }
   CK(r->scan_tmp.reserve(8192 * 4));
   CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
   CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
@@ -586,6 +632,11 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.segs_morph = r->d_morph.as<SegMorph>();
   a.def_paints = r->d_paints.as<DefPaint>();
   a.frame_bg = b.d_frame_bg.as<uint32_t>() + p.f0;
+  a.n_chunks = p.n_chunks;
+  a.chunk_items = b.d_chunk_items.as<uint32_t>() + p.chunk_at;
+  a.tile_cover = r->tile_cover.as<uint32_t>();
+  a.path_alive = r->path_alive.as<uint32_t>();
+  a.cover_sat = r->cover_sat.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
   a.ramps = r->d_ramps.as<float>();
@@ -615,6 +666,9 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.row_items = r->row_items.as<uint2>();
   a.list_items = r->list_items.as<uint32_t>();
   a.big_list = r->big_list.as<uint32_t>();
+  a.big_chunk = r->big_chunk.as<uint32_t>();
+  a.path_item = r->path_item.as<uint32_t>();
+  a.item_alive = r->item_alive.as<uint32_t>();
   a.totals = r->totals.as<Totals>() + pass_index;
   a.caps = r->caps;
   return a;
@@ -744,6 +798,8 @@ int finish(swfr_renderer *r) {
     r->stats.n_edges += t.n_edges;
     r->stats.n_slots += t.n_slots;
     r->stats.n_records += t.n_records;
+    r->stats.fine_slots += t.fine_hits;
+    r->stats.fine_records += t.fine_records;
     err |= t.error;
   }
   // segments read once, draw items read once, binned records written + read once (8 B each),
@@ -886,6 +942,10 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
     case 3: r->profile = value != 0; return SWFR_OK;
     case 4: r->host_threads = (uint32_t)std::min<uint64_t>(value, 256); return SWFR_OK;
     case 5: r->clear_to_background = value != 0; return SWFR_OK;
+    case 7:
+      if (value > (uint64_t)kMaxChunks) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "at most 8 occlusion chunks");
+      r->occlusion_chunks = (uint32_t)value;
+      return SWFR_OK;
     case 6:
       r->tiny_arena = value != 0;
       if (r->tiny_arena) r->caps = Caps{0, 0, 0, 0, 0, 0};
@@ -1268,6 +1328,10 @@ static int debug_pass(swfr_renderer *r, uint32_t frame, const Pass **pass, size_
   const Pass &p = b.passes[r->arena_pass];
   if (frame < p.f0 || frame >= p.f0 + p.n_frames)
     return fail(r, SWFR_ERR_INVALID_ARGUMENT, "debug taps need the frame to be in the last pass (render fewer frames)");
+  if (p.n_chunks > 1)
+    return fail(r, SWFR_ERR_INVALID_ARGUMENT,
+                "debug taps need the complete edge / record lists: set SWFR_OPT_OCCLUSION_CHUNKS to 1 (hidden geometry is "
+                "skipped otherwise)");
   *pass = &p;
   *index = r->arena_pass;
   return SWFR_OK;

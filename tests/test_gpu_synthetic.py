@@ -96,7 +96,8 @@ def test_full_size_properties(built_library):
     r.render(s0)
     a = r.get_image(premultiplied=True).data.copy()
     st = r.stats()
-    assert st["n_primitives"] == N and st["n_edges"] > N and st["n_records"] > st["n_edges"] // 2
+    # occlusion culling is on at this size: most of the geometry is hidden and never binned
+    assert st["n_primitives"] == N and st["n_edges"] > N and st["fine_records"] <= st["n_records"] < st["n_edges"]
     r.render(s0)
     b = r.get_image(premultiplied=True).data.copy()
     np.testing.assert_array_equal(a, b)  # deterministic despite atomics: accumulation is integer
@@ -229,4 +230,51 @@ def test_working_memory_growth_and_rerun(built_library):
     r.sync()
     assert r.stats()["retries"] >= 3
     np.testing.assert_array_equal(buf.numpy().reshape(F, H, W, 4), want)
+    r.close()
+
+
+@pytest.mark.parametrize("chunks", [2, 4, 8])
+def test_occlusion_chunks_do_not_change_pixels(built_library, chunks):
+    """Depth-chunk occlusion culling (SWFR_OPT_OCCLUSION_CHUNKS): geometry under an opaque full-tile cover found by
+    an upper chunk is neither flattened nor binned - the pixels must stay the oracle's, the binned records shrink,
+    and the debug taps (which need complete lists) refuse to run."""
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import SwfrError
+
+    sc = _scene(21, 700, 640, 360, 1.0)  # large shapes: deep overdraw
+    ref = corpus.render_oracle(sc)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    full = r.stats()
+    np.testing.assert_array_equal(r.get_image(premultiplied=True).data, ref)
+    r.set_option(capi.OPT_OCCLUSION_CHUNKS, chunks)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    st = r.stats()
+    bad = (out != ref).any(axis=2)
+    assert not bad.any(), "%d px differ, first %s" % (bad.sum(), np.argwhere(bad)[:5].tolist())
+    assert st["n_records"] < full["n_records"] * 0.8, (st["n_records"], full["n_records"])
+    assert st["fine_records"] == full["fine_records"] and st["fine_slots"] == full["fine_slots"]
+    with pytest.raises(SwfrError):
+        r.debug_edges(0)
+    # a batch: frames cull independently (covers of one frame must not leak into another)
+    sc2 = _scene(22, 500, 640, 360, 1.0)
+    ref2 = corpus.render_oracle(sc2)
+    r2, st2 = corpus.make_product(sc2)
+    r2.close()
+    sid = {id(t): r.register_shape(t) for t in sc2.shapes}
+    stage2 = sw.Stage([sw.StoredShape(sid[id(sc2.shapes[idx])], sw.Matrix2D(m)) for _, idx, m, _ in sc2.frames[0]])
+    empty = sw.Stage([])
+    r.render_batch([stages[0], stage2, empty, stages[0]])
+    np.testing.assert_array_equal(r.get_image(frame=0, premultiplied=True).data, ref)
+    np.testing.assert_array_equal(r.get_image(frame=1, premultiplied=True).data, ref2)
+    assert not r.get_image(frame=2, premultiplied=True).data.any()
+    np.testing.assert_array_equal(r.get_image(frame=3, premultiplied=True).data, ref)
+    # growth / re-run with culling on
+    r.set_option(capi.OPT_DEBUG_TINY_ARENA, 1)
+    r.render_batch([stage2, stages[0]])
+    assert r.stats()["retries"] >= 1
+    np.testing.assert_array_equal(r.get_image(frame=0, premultiplied=True).data, ref2)
+    np.testing.assert_array_equal(r.get_image(frame=1, premultiplied=True).data, ref)
     r.close()
