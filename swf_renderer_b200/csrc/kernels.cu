@@ -304,7 +304,7 @@ __global__ void k_flatten_count(RenderArgs a) {
 // chunk above the one being processed, so for the paths of this chunk "covered" is simply tile_cover != 0.
 // k_cover_sat builds, per frame, the summed-area table of OPEN (uncovered) tiles, (tiles_x + 1) x (tiles_y + 1)
 // entries with a zero first row and column: one block per frame, row prefixes then column prefixes.
-__global__ void __launch_bounds__(256) k_cover_sat(RenderArgs a) {
+__global__ void __launch_bounds__(1024) k_cover_sat(RenderArgs a) {
   if (a.totals->overflow) return;
   const uint32_t frame = blockIdx.x;
   if (frame == 0 && threadIdx.x == 0) a.totals->n_big_chunk = 0;  // the list of the chunk about to be processed
@@ -331,11 +331,17 @@ __global__ void __launch_bounds__(256) k_cover_sat(RenderArgs a) {
     }
   }
   __syncthreads();
-  for (int x = threadIdx.x + 1; x < sw; x += blockDim.x) {  // column prefixes: coalesced across threads
+  for (int x = threadIdx.x + 1; x < sw; x += blockDim.x) {  // column prefixes: coalesced across threads, 8 loads in flight
     uint32_t run = 0;
-    for (int y = 1; y <= ty; y++) {
-      run += sat[(size_t)y * sw + x];
-      sat[(size_t)y * sw + x] = run;
+    for (int y0 = 1; y0 <= ty; y0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = y0 + k <= ty ? sat[(size_t)(y0 + k) * sw + x] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        run += v[k];
+        if (y0 + k <= ty) sat[(size_t)(y0 + k) * sw + x] = run;
+      }
     }
   }
 }
@@ -785,7 +791,7 @@ __global__ void __launch_bounds__(kRowThreads) k_row_lists(RenderArgs a) {
       if (pid < p1) {
         const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));  // xy0, wh
         const int by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
-        hit = bw > 0 && row >= by0 && row < by0 + bh;
+        hit = bw > 0 && row >= by0 && row < by0 + bh && __ldg(a.path_alive + pid) != 0;  // hidden paths are left out
         xr = (r.x & 0xffffu) | ((uint32_t)bw << 16);
       }
       const uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -808,6 +814,7 @@ __global__ void __launch_bounds__(kRowThreads) k_row_lists(RenderArgs a) {
       __syncthreads();
     }
     for (uint32_t g = tid; g < a.groups_x; g += kRowThreads) a.list_off[rl * a.groups_x + g] = sh_grp[g];
+    if (tid == 0) a.row_count[rl] = out - a.row_off[rl];  // entries kept (the offsets were sized for all paths)
     __syncthreads();
   }
 }
@@ -818,7 +825,7 @@ __global__ void k_group_lists(RenderArgs a) {
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t l = warp; l < a.n_lists; l += nwarps) {
     const uint32_t rl = l / a.groups_x, g = l - rl * a.groups_x;
-    const uint32_t r0 = a.row_off[rl], r1 = a.row_off[rl + 1];
+    const uint32_t r0 = a.row_off[rl], r1 = r0 + a.row_count[rl];
     uint32_t out = a.list_off[l];
     const uint32_t gx0 = g * kGroupTiles, gx1 = gx0 + kGroupTiles;
     for (uint32_t base = r0; base < r1; base += 32) {
@@ -1783,7 +1790,7 @@ static void scan_u32(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, 
 }
 
 const char *stage_name(int i) {
-  static const char *names[kNumStages] = {"flatten_count", "scan_edges", "path_setup", "lists", "bin_chunks", "fine"};
+  static const char *names[kNumStages] = {"flatten_count", "scan_edges", "path_setup", "bin_chunks", "lists", "fine"};
   return (i >= 0 && i < kNumStages) ? names[i] : "?";
 }
 
@@ -1819,17 +1826,8 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   scan_u32(a.path_slot_off, a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
            st, launches);
   mark(3);
-  // candidate lists: row counts (from path setup) -> row lists -> group counts -> group lists
-  scan_u32(a.row_count, a.row_off, nullptr, a.n_frames * (uint32_t)a.tiles_y, a.scan_tmp, &a.totals->n_rowent, a.caps.rows,
-           &a.totals->overflow, 16u, st, launches);
-  k_row_lists<<<(unsigned)std::min<uint32_t>(a.n_frames * (uint32_t)a.tiles_y, kNumSM * 8), kRowThreads, 0, st>>>(a);
-  launches++;
-  scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
-           launches);
-  k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);
   k_clear_edges<<<wide, T, 0, st>>>(a);
-  launches += 2;
-  mark(4);
+  launches++;
   // K1 emit + K2, depth chunk by depth chunk from the top one down: what a chunk covers opaquely hides the
   // geometry of the chunks below it (grid.y = frame; every kernel walks its frame's part of the chunk)
   if (a.n_seginst && a.n_paths) {
@@ -1837,7 +1835,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
     const dim3 g2(per_frame, a.n_frames);
     for (uint32_t c = a.n_chunks; c-- > 0;) {
       if (c + 1 != a.n_chunks) {
-        k_cover_sat<<<a.n_frames, 256, 0, st>>>(a);
+        k_cover_sat<<<a.n_frames, 1024, 0, st>>>(a);
         launches++;
       }
       k_path_alive<<<g2, T, 0, st>>>(a, c);
@@ -1850,6 +1848,16 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
     k_scatter<<<wide, T, 0, st>>>(a);
     launches += 2;
   }
+  mark(4);
+  // candidate lists of the visible paths (for k_fine): row counts (from path setup) -> row lists -> group counts -> group lists
+  scan_u32(a.row_count, a.row_off, nullptr, a.n_frames * (uint32_t)a.tiles_y, a.scan_tmp, &a.totals->n_rowent, a.caps.rows,
+           &a.totals->overflow, 16u, st, launches);
+  k_row_lists<<<(unsigned)std::min<uint32_t>(a.n_frames * (uint32_t)a.tiles_y, kNumSM * 8), kRowThreads, 0, st>>>(a);
+  launches++;
+  scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
+           launches);
+  k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);
+  launches++;
   mark(5);
   k_fine<<<kNumSM * 4, kFineWarps * 32, 0, st>>>(a);
   launches++;
