@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames-per-pass", type=int, default=0, help="0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--occlusion-chunks", type=int, default=0, help="0 = library default (automatic)")
     ap.add_argument("--uhd-frames", type=int, default=16,
                     help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
     return ap.parse_args()
@@ -244,6 +245,8 @@ def run_ours(a):
     r.set_option(capi.OPT_RETAIN_COMPILED, 0)
     if a.frames_per_pass:
         r.set_option(capi.OPT_FRAMES_PER_PASS, a.frames_per_pass)
+    if a.occlusion_chunks:
+        r.set_option(capi.OPT_OCCLUSION_CHUNKS, a.occlusion_chunks)
     # stage-flattening threads: the box's cores are shared by the ranks of the node
     cores = max(1, len(os.sched_getaffinity(0)))
     r.set_option(capi.OPT_HOST_THREADS, max(1, min(8, cores // max(world, 1))))

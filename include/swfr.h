@@ -229,7 +229,7 @@ typedef enum swfr_option {
   SWFR_OPT_HOST_THREADS = 4,
   SWFR_OPT_OCCLUSION_CHUNKS = 7,   /* depth chunks for occlusion culling: the items of a frame are binned in this many
                                       ranges from the top (last painted) down, and geometry under an opaque full-tile
-                                      cover found by an upper chunk is skipped.  0 (default): automatic (5 for frames
+                                      cover found by an upper chunk is skipped.  0 (default): automatic (4 for frames
                                       of >= 1024 items, else 1); 1: no culling - every edge and record is produced, which
                                       the swfr_debug_edges / swfr_debug_tile_counts taps need; up to 8.  Pixels are
                                       identical for every setting */

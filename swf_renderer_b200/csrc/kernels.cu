@@ -361,7 +361,8 @@ __global__ void k_path_alive(RenderArgs a, uint32_t c) {
   for (uint32_t pid = p0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); pid < p1; pid += nwarps) {
     const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));
     const int bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
-    bool alive = bw > 0;
+    // without culling (one chunk) every path is emitted, also those outside the viewport: the edge tap lists them all
+    bool alive = bw > 0 || a.n_chunks == 1;
     if (alive && c + 1 != a.n_chunks) {  // nothing has been binned above the top chunk
       const uint32_t open = __ldg(sat + (size_t)(by0 + bh) * sw + bx0 + bw) - __ldg(sat + (size_t)by0 * sw + bx0 + bw) -
                             __ldg(sat + (size_t)(by0 + bh) * sw + bx0) + __ldg(sat + (size_t)by0 * sw + bx0);

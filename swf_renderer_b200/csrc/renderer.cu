@@ -422,7 +422,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   for (Pass &p : b.passes) {
     uint64_t max_items = 0;
     for (uint32_t f = p.f0; f < p.f0 + p.n_frames; f++) max_items = std::max<uint64_t>(max_items, sums[f].items);
-    p.n_chunks = r->occlusion_chunks ? r->occlusion_chunks : (max_items >= 1024 ? 5u : 1u);
+    p.n_chunks = r->occlusion_chunks ? r->occlusion_chunks : (max_items >= 1024 ? 4u : 1u);
     p.chunk_at = chunk_at;
     chunk_at += (size_t)(p.n_chunks + 1) * p.n_frames;
   }

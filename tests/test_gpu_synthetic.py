@@ -278,3 +278,52 @@ def test_occlusion_chunks_do_not_change_pixels(built_library, chunks):
     np.testing.assert_array_equal(r.get_image(frame=0, premultiplied=True).data, ref2)
     np.testing.assert_array_equal(r.get_image(frame=1, premultiplied=True).data, ref)
     r.close()
+
+
+def _random_placement_scene(seed, n_shapes, w, h):
+    """Shapes of the synthetic stream under hostile placement: scales from 1/200 to 400, any rotation, shear,
+    mirroring, centres up to several frames away from the viewport - most geometry is clipped, some edges are
+    clamped at +-32768 px, many shapes are sub-pixel."""
+    rng = np.random.RandomState(seed)
+    fr = synth.SynthFrame(1000 + seed, n_shapes, w, h, 0.5)
+    sc = corpus.Scene(w, h)
+    for i, t in enumerate(synth.textures()):
+        sc.bitmaps[i] = t
+    for i in range(fr.n):
+        s = float(np.exp(rng.uniform(np.log(0.005), np.log(400.0))))
+        if rng.rand() < 0.5:
+            s = float(rng.uniform(0.3, 3.0))
+        ang = rng.uniform(0, 2 * np.pi)
+        sx, sy = s * rng.uniform(0.2, 1.0), s * rng.choice([-1.0, 1.0])
+        shear = rng.uniform(-0.5, 0.5)
+        a, b = sx * np.cos(ang), sx * np.sin(ang)
+        c, d = -sy * np.sin(ang) + shear * a, sy * np.cos(ang) + shear * b
+        tx = rng.uniform(-2.0, 3.0) * w * 20.0 if rng.rand() < 0.3 else rng.uniform(0, w) * 20.0
+        ty = rng.uniform(-2.0, 3.0) * h * 20.0 if rng.rand() < 0.3 else rng.uniform(0, h) * 20.0
+        # Matrix2D order: scale_x, scale_y, rotate_skew0, rotate_skew1, tx, ty  (x' = m0 x + m3 y + m4, y' = m2 x + m1 y + m5)
+        m = [float(np.float32(v)) for v in (a, d, b, c, tx, ty)]
+        sc.draw_shape(sc.add_shape(fr.ast(i)), m)
+    return sc
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_hostile_placements_bit_exact(built_library, seed):
+    """Extreme scales, shear, mirroring, far off-screen and clamped geometry: edges, bin counts and pixels still equal
+    the oracle's, with and without occlusion chunks."""
+    from swf_renderer_b200 import capi
+
+    sc = _random_placement_scene(seed, 160, 400, 300)
+    ref, info = corpus.render_oracle(sc, want_debug=True)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    edges, epath = r.debug_edges(0)
+    np.testing.assert_array_equal(edges, info["edges"])
+    np.testing.assert_array_equal(epath, info["edge_path"])
+    np.testing.assert_array_equal(r.debug_tile_counts(0), info["tile_counts"])
+    bad = (out != ref).any(axis=2)
+    assert not bad.any(), "%d px differ, first %s" % (bad.sum(), np.argwhere(bad)[:5].tolist())
+    r.set_option(capi.OPT_OCCLUSION_CHUNKS, 3)
+    r.render(stages[0])
+    np.testing.assert_array_equal(r.get_image(premultiplied=True).data, ref)
+    r.close()
