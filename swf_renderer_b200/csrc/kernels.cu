@@ -10,6 +10,7 @@
 //   ts/src/lib/css-color.ts:11-13                    colour channel quantisation of morph-lerped colours
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -1860,7 +1861,12 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
   k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);
   launches++;
   mark(5);
-  k_fine<<<kNumSM * 4, kFineWarps * 32, 0, st>>>(a);
+  static const int fine_blocks = [] {
+    const char *e = getenv("SWFR_FINE_BLOCKS_PER_SM");
+    int v = e ? atoi(e) : 4;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
+  k_fine<<<kNumSM * fine_blocks, kFineWarps * 32, 0, st>>>(a);
   launches++;
   mark(6);
   return launches;

@@ -140,8 +140,15 @@ struct swfr_renderer {
   std::vector<BitmapDev> h_bitmaps;
 
   // ---- working memory ----
-  DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop,
-      slot_off, records, frames, scan_tmp, totals, scratch, scratch2, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive;
+  // Two arenas: consecutive passes of a batch alternate between them and between two streams, so that the many
+  // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
+  struct Arena {
+    DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive;
+  };
+  Arena arena[2];
+  cudaStream_t stream2 = nullptr;          // passes with an odd index
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  DevBuf frames, totals, scratch, scratch2;
   Caps caps{0, 0, 0, 0, 0, 0};
   PinnedBuf pin_totals;
   swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
@@ -546,30 +553,34 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     max_seg = std::max(max_seg, p.n_seginst);
     max_paths = std::max(max_paths, p.n_paths);
   }
-  CK(r->seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
-  CK(r->seg_item.reserve((size_t)max_seg * 4 + 256));
-  CK(r->path_bbox.reserve((size_t)max_paths * 16 + 256));
-  CK(r->path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
-  CK(r->paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
-  CK(r->path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
-  CK(r->path_rec_base.reserve(((size_t)max_paths + 1) * 4 + 256));
-  CK(r->big_list.reserve((size_t)max_paths * 4 + 256));
-  CK(r->big_chunk.reserve((size_t)max_paths * 4 + 256));
-  CK(r->path_item.reserve((size_t)max_paths * 4 + 256));
+  const int n_arenas = b.passes.size() > 1 ? 2 : 1;  // a single pass never needs the second working set
+  for (int k = 0; k < n_arenas; k++) {
+  swfr_renderer::Arena &A = r->arena[k];
+  CK(A.seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
+  CK(A.seg_item.reserve((size_t)max_seg * 4 + 256));
+  CK(A.path_bbox.reserve((size_t)max_paths * 16 + 256));
+  CK(A.path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
+  CK(A.paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
+  CK(A.path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
+  CK(A.path_rec_base.reserve(((size_t)max_paths + 1) * 4 + 256));
+  CK(A.big_list.reserve((size_t)max_paths * 4 + 256));
+  CK(A.big_chunk.reserve((size_t)max_paths * 4 + 256));
+  CK(A.path_item.reserve((size_t)max_paths * 4 + 256));
   {
     uint32_t max_items = 0;
     for (const Pass &p : b.passes) max_items = std::max(max_items, p.n_items);
-    CK(r->item_alive.reserve((size_t)max_items * 4 + 256));
+    CK(A.item_alive.reserve((size_t)max_items * 4 + 256));
   }
-  CK(r->path_alive.reserve((size_t)max_paths * 4 + 256));
+  CK(A.path_alive.reserve((size_t)max_paths * 4 + 256));
 
   {
     uint32_t max_frames = 1;
     for (const Pass &p : b.passes) max_frames = std::max(max_frames, p.n_frames);
-    CK(r->tile_cover.reserve((size_t)max_frames * r->tiles_x * r->tiles_y * 4 + 256));
-    CK(r->cover_sat.reserve((size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256));
+    CK(A.tile_cover.reserve((size_t)max_frames * r->tiles_x * r->tiles_y * 4 + 256));
+    CK(A.cover_sat.reserve((size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256));
   }
-  CK(r->scan_tmp.reserve(8192 * 4));
+  CK(A.scan_tmp.reserve(8192 * 4));
+  }
   CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
   CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
   Caps want = r->caps;
@@ -596,26 +607,30 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   size_t max_lists = (size_t)std::max<uint32_t>(1, r->frames_per_pass) * r->tiles_y * groups_x;
   for (const Pass &p : b.passes) max_lists = std::max(max_lists, (size_t)p.n_frames * r->tiles_y * groups_x);
-  CK(r->list_off.reserve((max_lists + 1) * 4 + 256));
-  CK(r->list_items.reserve((size_t)want.list * 4));
   size_t max_rows = max_lists / groups_x;
-  CK(r->row_count.reserve((max_rows + 1) * 4 + 256));
-  CK(r->row_off.reserve((max_rows + 1) * 4 + 256));
-  CK(r->row_items.reserve((size_t)want.rows * 8));
-  CK(r->edges.reserve((size_t)want.edges * 16));
-  CK(r->edge_pid.reserve((size_t)want.edges * 4));
-  CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
-  CK(r->slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
-  CK(r->slot_off.reserve(((size_t)want.slots + 1) * 4));
-  CK(r->records.reserve((size_t)want.records * 8));
-  CK(r->stage.reserve((size_t)want.stage * 16));
-  CK(r->stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
+  for (int k = 0; k < n_arenas; k++) {
+  swfr_renderer::Arena &A = r->arena[k];
+  CK(A.list_off.reserve((max_lists + 1) * 4 + 256));
+  CK(A.list_items.reserve((size_t)want.list * 4));
+  CK(A.row_count.reserve((max_rows + 1) * 4 + 256));
+  CK(A.row_off.reserve((max_rows + 1) * 4 + 256));
+  CK(A.row_items.reserve((size_t)want.rows * 8));
+  CK(A.edges.reserve((size_t)want.edges * 16));
+  CK(A.edge_pid.reserve((size_t)want.edges * 4));
+  CK(A.slot_count.reserve(((size_t)want.slots + 1) * 4));
+  CK(A.slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
+  CK(A.slot_off.reserve(((size_t)want.slots + 1) * 4));
+  CK(A.records.reserve((size_t)want.records * 8));
+  CK(A.stage.reserve((size_t)want.stage * 16));
+  CK(A.stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
+  }
   r->caps = want;
   return SWFR_OK;
 }
 
 RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_t pass_index) {
   RenderArgs a{};
+  const swfr_renderer::Arena &A = r->arena[pass_index & 1];
   a.width = (int)r->width;
   a.height = (int)r->height;
   a.tiles_x = (int)r->tiles_x;
@@ -634,41 +649,41 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.frame_bg = b.d_frame_bg.as<uint32_t>() + p.f0;
   a.n_chunks = p.n_chunks;
   a.chunk_items = b.d_chunk_items.as<uint32_t>() + p.chunk_at;
-  a.tile_cover = r->tile_cover.as<uint32_t>();
-  a.path_alive = r->path_alive.as<uint32_t>();
-  a.cover_sat = r->cover_sat.as<uint32_t>();
+  a.tile_cover = A.tile_cover.as<uint32_t>();
+  a.path_alive = A.path_alive.as<uint32_t>();
+  a.cover_sat = A.cover_sat.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
   a.ramps = r->d_ramps.as<float>();
   a.bitmaps = r->d_bitmaps.as<BitmapDev>();
-  a.seg_edge_off = r->seg_edge_off.as<uint32_t>();
-  a.seg_item = r->seg_item.as<uint32_t>();
-  a.path_bbox = r->path_bbox.as<int32_t>();
-  a.path_rec = r->path_rec.as<PathRec>();
-  a.paint_inst = r->paint_inst.as<PaintInst>();
-  a.path_slot_off = r->path_slot_off.as<uint32_t>();
-  a.path_rec_base = r->path_rec_base.as<uint32_t>();
-  a.edges = r->edges.as<int4>();
-  a.edge_pid = r->edge_pid.as<uint32_t>();
-  a.slot_count = r->slot_count.as<uint32_t>();
-  a.slot_backdrop = r->slot_backdrop.as<int32_t>();
-  a.slot_off = r->slot_off.as<uint32_t>();
-  a.records = r->records.as<unsigned long long>();
-  a.stage = r->stage.as<uint4>();
-  a.stage_used = r->stage_used.as<uint32_t>();
+  a.seg_edge_off = A.seg_edge_off.as<uint32_t>();
+  a.seg_item = A.seg_item.as<uint32_t>();
+  a.path_bbox = A.path_bbox.as<int32_t>();
+  a.path_rec = A.path_rec.as<PathRec>();
+  a.paint_inst = A.paint_inst.as<PaintInst>();
+  a.path_slot_off = A.path_slot_off.as<uint32_t>();
+  a.path_rec_base = A.path_rec_base.as<uint32_t>();
+  a.edges = A.edges.as<int4>();
+  a.edge_pid = A.edge_pid.as<uint32_t>();
+  a.slot_count = A.slot_count.as<uint32_t>();
+  a.slot_backdrop = A.slot_backdrop.as<int32_t>();
+  a.slot_off = A.slot_off.as<uint32_t>();
+  a.records = A.records.as<unsigned long long>();
+  a.stage = A.stage.as<uint4>();
+  a.stage_used = A.stage_used.as<uint32_t>();
   a.frames = r->frames.as<uint32_t>() + (size_t)p.f0 * r->width * r->height;
-  a.scan_tmp = r->scan_tmp.as<uint32_t>();
+  a.scan_tmp = A.scan_tmp.as<uint32_t>();
   a.groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   a.n_lists = p.n_frames * r->tiles_y * a.groups_x;
-  a.list_off = r->list_off.as<uint32_t>();
-  a.row_count = r->row_count.as<uint32_t>();
-  a.row_off = r->row_off.as<uint32_t>();
-  a.row_items = r->row_items.as<uint2>();
-  a.list_items = r->list_items.as<uint32_t>();
-  a.big_list = r->big_list.as<uint32_t>();
-  a.big_chunk = r->big_chunk.as<uint32_t>();
-  a.path_item = r->path_item.as<uint32_t>();
-  a.item_alive = r->item_alive.as<uint32_t>();
+  a.list_off = A.list_off.as<uint32_t>();
+  a.row_count = A.row_count.as<uint32_t>();
+  a.row_off = A.row_off.as<uint32_t>();
+  a.row_items = A.row_items.as<uint2>();
+  a.list_items = A.list_items.as<uint32_t>();
+  a.big_list = A.big_list.as<uint32_t>();
+  a.big_chunk = A.big_chunk.as<uint32_t>();
+  a.path_item = A.path_item.as<uint32_t>();
+  a.item_alive = A.item_alive.as<uint32_t>();
   a.totals = r->totals.as<Totals>() + pass_index;
   a.caps = r->caps;
   return a;
@@ -701,14 +716,31 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
   }
   r->copy_reqs.clear();
   if (b.uploaded) CK(cudaStreamWaitEvent(r->stream, b.uploaded, 0));
+  // Consecutive passes alternate between two arenas and two streams (fork after the upload, join at the end), so
+  // that they overlap on the GPU; with SWFR_OPT_PROFILE the passes stay on one stream and the stage times are clean.
+  const bool overlap = b.passes.size() > 1 && !r->profile;
+  if (overlap) {
+    if (!r->stream2) {
+      CK(cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&r->fork_ev, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&r->join_ev, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(r->fork_ev, r->stream));
+    CK(cudaStreamWaitEvent(r->stream2, r->fork_ev, 0));
+  }
   for (size_t i = 0; i < b.passes.size(); i++) {
+    cudaStream_t st = (overlap && (i & 1)) ? r->stream2 : r->stream;
     // a device->host copy of the previous render may still be reading the frames this pass overwrites
     for (const swfr_renderer::CopyFence &cf : r->copy_fences)
       if (cf.first < b.passes[i].f0 + b.passes[i].n_frames && b.passes[i].f0 < cf.first + cf.count)
-        CK(cudaStreamWaitEvent(r->stream, cf.done, 0));
-    launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream,
+        CK(cudaStreamWaitEvent(st, cf.done, 0));
+    launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), st,
                                         r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr);
-    CK(cudaEventRecord(r->pass_done[i], r->stream));
+    CK(cudaEventRecord(r->pass_done[i], st));
+  }
+  if (overlap) {
+    CK(cudaEventRecord(r->join_ev, r->stream2));
+    CK(cudaStreamWaitEvent(r->stream, r->join_ev, 0));
   }
   for (const swfr_renderer::CopyFence &cf : r->copy_fences) r->fence_pool.push_back(cf.done);
   r->copy_fences.clear();
@@ -743,8 +775,6 @@ int finish(swfr_renderer *r) {
       if (t.overflow & 4u) want.records = std::max(want.records, grow(t.n_records));
       if (t.overflow & 8u) want.list = std::max(want.list, grow(t.n_list));
       if (t.overflow & 16u) want.rows = std::max(want.rows, grow(t.n_rowent));
-      CK(r->list_items.reserve((size_t)want.list * 4));
-      CK(r->row_items.reserve((size_t)want.rows * 8));
       if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
       if (t.overflow_stage) {
         uint64_t need = ((uint64_t)t.n_stage_blocks + t.n_stage_blocks / 8 + 64) * 256;
@@ -752,14 +782,19 @@ int finish(swfr_renderer *r) {
       }
       if (!r->tiny_arena)
         want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
-      CK(r->stage.reserve((size_t)want.stage * 16));
-      CK(r->stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
-      CK(r->edges.reserve((size_t)want.edges * 16));
-      CK(r->edge_pid.reserve((size_t)want.edges * 4));
-      CK(r->slot_count.reserve(((size_t)want.slots + 1) * 4));
-      CK(r->slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
-      CK(r->slot_off.reserve(((size_t)want.slots + 1) * 4));
-      CK(r->records.reserve((size_t)want.records * 8));
+      for (int k = 0; k < (np > 1 ? 2 : 1); k++) {
+        swfr_renderer::Arena &A = r->arena[k];
+        CK(A.list_items.reserve((size_t)want.list * 4));
+        CK(A.row_items.reserve((size_t)want.rows * 8));
+        CK(A.stage.reserve((size_t)want.stage * 16));
+        CK(A.stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
+        CK(A.edges.reserve((size_t)want.edges * 16));
+        CK(A.edge_pid.reserve((size_t)want.edges * 4));
+        CK(A.slot_count.reserve(((size_t)want.slots + 1) * 4));
+        CK(A.slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
+        CK(A.slot_off.reserve(((size_t)want.slots + 1) * 4));
+        CK(A.records.reserve((size_t)want.records * 8));
+      }
       r->caps = want;
       r->stats.retries++;
       r->arena_pass = i;
@@ -921,6 +956,12 @@ void swfr_destroy(swfr_renderer *r) {
   if (r->copy_stream) {
     cudaStreamSynchronize(r->copy_stream);
     cudaStreamDestroy(r->copy_stream);
+  }
+  if (r->stream2) {
+    cudaStreamSynchronize(r->stream2);
+    cudaStreamDestroy(r->stream2);
+    cudaEventDestroy(r->fork_ev);
+    cudaEventDestroy(r->join_ev);
   }
   if (r->up_stream) {
     cudaStreamSynchronize(r->up_stream);
@@ -1343,6 +1384,7 @@ int swfr_debug_edges(swfr_renderer *r, uint32_t frame, int32_t *edges, int32_t *
   const Pass *p;
   size_t pi;
   int rc = debug_pass(r, frame, &p, &pi);
+  const swfr_renderer::Arena &A = r->arena[pi & 1];
   if (rc != SWFR_OK) return rc;
   const swfr_batch &b = *r->last;
   // frame -> path range -> item range -> segment-instance range -> edge range
@@ -1358,14 +1400,14 @@ int swfr_debug_edges(swfr_renderer *r, uint32_t frame, int32_t *edges, int32_t *
   (void)path_hi;
   uint32_t s_lo = so[i_lo], s_hi = so[i_hi];
   uint32_t e_lo = 0, e_hi = 0;
-  CK(cudaMemcpy(&e_lo, r->seg_edge_off.as<uint32_t>() + s_lo, 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(&e_hi, r->seg_edge_off.as<uint32_t>() + s_hi, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&e_lo, A.seg_edge_off.as<uint32_t>() + s_lo, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&e_hi, A.seg_edge_off.as<uint32_t>() + s_hi, 4, cudaMemcpyDeviceToHost));
   uint64_t cnt = e_hi - e_lo;
   if (n) *n = cnt;
   uint64_t take = std::min<uint64_t>(cnt, cap);
-  if (edges && take) CK(cudaMemcpy(edges, r->edges.as<int4>() + e_lo, take * 16, cudaMemcpyDeviceToHost));
+  if (edges && take) CK(cudaMemcpy(edges, A.edges.as<int4>() + e_lo, take * 16, cudaMemcpyDeviceToHost));
   if (edge_path && take) {
-    CK(cudaMemcpy(edge_path, r->edge_pid.as<uint32_t>() + e_lo, take * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(edge_path, A.edge_pid.as<uint32_t>() + e_lo, take * 4, cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < take; i++) edge_path[i] -= (int32_t)path_lo;  // index within the frame
   }
   return SWFR_OK;
