@@ -145,9 +145,11 @@ struct swfr_renderer {
   struct Arena {
     DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive;
   };
-  Arena arena[2];
-  cudaStream_t stream2 = nullptr;          // passes with an odd index
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  static constexpr int kArenas = 4;
+  Arena arena[kArenas];
+  int n_arenas = 2;                         // arenas (and streams) in use: pass i runs in arena / on stream i % n_arenas
+  cudaStream_t extra_stream[kArenas - 1] = {nullptr, nullptr, nullptr};  // streams 1 .. n_arenas - 1 (stream 0 is `stream`)
+  cudaEvent_t fork_ev = nullptr, join_ev[kArenas - 1] = {nullptr, nullptr, nullptr};
   DevBuf frames, totals, scratch, scratch2;
   Caps caps{0, 0, 0, 0, 0, 0};
   PinnedBuf pin_totals;
@@ -553,7 +555,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     max_seg = std::max(max_seg, p.n_seginst);
     max_paths = std::max(max_paths, p.n_paths);
   }
-  const int n_arenas = b.passes.size() > 1 ? 2 : 1;  // a single pass never needs the second working set
+  const int n_arenas = (int)std::min<size_t>(b.passes.size(), (size_t)r->n_arenas);  // a single pass needs one working set
   for (int k = 0; k < n_arenas; k++) {
   swfr_renderer::Arena &A = r->arena[k];
   CK(A.seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
@@ -630,7 +632,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
 
 RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_t pass_index) {
   RenderArgs a{};
-  const swfr_renderer::Arena &A = r->arena[pass_index & 1];
+  const swfr_renderer::Arena &A = r->arena[pass_index % (size_t)r->n_arenas];
   a.width = (int)r->width;
   a.height = (int)r->height;
   a.tiles_x = (int)r->tiles_x;
@@ -718,18 +720,22 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
   if (b.uploaded) CK(cudaStreamWaitEvent(r->stream, b.uploaded, 0));
   // Consecutive passes alternate between two arenas and two streams (fork after the upload, join at the end), so
   // that they overlap on the GPU; with SWFR_OPT_PROFILE the passes stay on one stream and the stage times are clean.
-  const bool overlap = b.passes.size() > 1 && !r->profile;
+  const bool overlap = b.passes.size() > 1 && !r->profile && r->n_arenas > 1;
+  const int n_streams = overlap ? (int)std::min<size_t>(b.passes.size(), (size_t)r->n_arenas) : 1;
   if (overlap) {
-    if (!r->stream2) {
-      CK(cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&r->fork_ev, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&r->join_ev, cudaEventDisableTiming));
-    }
+    if (!r->fork_ev) CK(cudaEventCreateWithFlags(&r->fork_ev, cudaEventDisableTiming));
     CK(cudaEventRecord(r->fork_ev, r->stream));
-    CK(cudaStreamWaitEvent(r->stream2, r->fork_ev, 0));
+    for (int k = 1; k < n_streams; k++) {
+      if (!r->extra_stream[k - 1]) {
+        CK(cudaStreamCreateWithFlags(&r->extra_stream[k - 1], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&r->join_ev[k - 1], cudaEventDisableTiming));
+      }
+      CK(cudaStreamWaitEvent(r->extra_stream[k - 1], r->fork_ev, 0));
+    }
   }
   for (size_t i = 0; i < b.passes.size(); i++) {
-    cudaStream_t st = (overlap && (i & 1)) ? r->stream2 : r->stream;
+    const int sk = overlap ? (int)(i % (size_t)r->n_arenas) : 0;
+    cudaStream_t st = sk ? r->extra_stream[sk - 1] : r->stream;
     // a device->host copy of the previous render may still be reading the frames this pass overwrites
     for (const swfr_renderer::CopyFence &cf : r->copy_fences)
       if (cf.first < b.passes[i].f0 + b.passes[i].n_frames && b.passes[i].f0 < cf.first + cf.count)
@@ -738,9 +744,9 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
                                         r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr);
     CK(cudaEventRecord(r->pass_done[i], st));
   }
-  if (overlap) {
-    CK(cudaEventRecord(r->join_ev, r->stream2));
-    CK(cudaStreamWaitEvent(r->stream, r->join_ev, 0));
+  for (int k = 1; k < n_streams; k++) {
+    CK(cudaEventRecord(r->join_ev[k - 1], r->extra_stream[k - 1]));
+    CK(cudaStreamWaitEvent(r->stream, r->join_ev[k - 1], 0));
   }
   for (const swfr_renderer::CopyFence &cf : r->copy_fences) r->fence_pool.push_back(cf.done);
   r->copy_fences.clear();
@@ -782,7 +788,7 @@ int finish(swfr_renderer *r) {
       }
       if (!r->tiny_arena)
         want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
-      for (int k = 0; k < (np > 1 ? 2 : 1); k++) {
+      for (int k = 0; k < (int)std::min<size_t>(np, (size_t)r->n_arenas); k++) {
         swfr_renderer::Arena &A = r->arena[k];
         CK(A.list_items.reserve((size_t)want.list * 4));
         CK(A.row_items.reserve((size_t)want.rows * 8));
@@ -937,6 +943,7 @@ int swfr_create_on_stream(int device, uint32_t width, uint32_t height, void *cud
     r->own_stream = true;
   }
   if (const char *e = getenv("SWFR_FRAMES_PER_PASS")) r->frames_per_pass = (uint32_t)std::max(1, atoi(e));
+  if (const char *e = getenv("SWFR_ARENAS")) r->n_arenas = std::min(std::max(1, atoi(e)), (int)swfr_renderer::kArenas);
   *out = r;
   return SWFR_OK;
 }
@@ -957,12 +964,13 @@ void swfr_destroy(swfr_renderer *r) {
     cudaStreamSynchronize(r->copy_stream);
     cudaStreamDestroy(r->copy_stream);
   }
-  if (r->stream2) {
-    cudaStreamSynchronize(r->stream2);
-    cudaStreamDestroy(r->stream2);
-    cudaEventDestroy(r->fork_ev);
-    cudaEventDestroy(r->join_ev);
-  }
+  for (int k = 0; k < swfr_renderer::kArenas - 1; k++)
+    if (r->extra_stream[k]) {
+      cudaStreamSynchronize(r->extra_stream[k]);
+      cudaStreamDestroy(r->extra_stream[k]);
+      cudaEventDestroy(r->join_ev[k]);
+    }
+  if (r->fork_ev) cudaEventDestroy(r->fork_ev);
   if (r->up_stream) {
     cudaStreamSynchronize(r->up_stream);
     cudaStreamDestroy(r->up_stream);
@@ -1384,7 +1392,7 @@ int swfr_debug_edges(swfr_renderer *r, uint32_t frame, int32_t *edges, int32_t *
   const Pass *p;
   size_t pi;
   int rc = debug_pass(r, frame, &p, &pi);
-  const swfr_renderer::Arena &A = r->arena[pi & 1];
+  const swfr_renderer::Arena &A = r->arena[pi % (size_t)r->n_arenas];
   if (rc != SWFR_OK) return rc;
   const swfr_batch &b = *r->last;
   // frame -> path range -> item range -> segment-instance range -> edge range
