@@ -278,13 +278,16 @@ def run_ours(a):
         return float(t.item())
 
     # ---- value: stages resident in HBM ----
-    batch = r.create_batch((stage_arr, keep))
     # E_tile of SURVEY 8(d) - the records the path's algorithm bins, the sum of the bit-exact tile bin counts - comes
-    # from one render without occlusion culling; the timed renders skip most of them (hidden under opaque covers).
+    # from one render without occlusion culling (the chunk layout is fixed when a batch is built); the timed renders
+    # skip most of those records (hidden under opaque covers).
     r.set_option(capi.OPT_OCCLUSION_CHUNKS, 1)
-    batch.render()
+    full = r.create_batch((stage_arr, keep))
+    full.render()
     n_records_full = r.stats()["n_records"]
+    full.close()
     r.set_option(capi.OPT_OCCLUSION_CHUNKS, a.occlusion_chunks)
+    batch = r.create_batch((stage_arr, keep))
     for _ in range(max(a.warmup, 3)):
         batch.render()
     r.sync()

@@ -1409,6 +1409,45 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
     const int ii0 = rep ? floormod(i0, p.bw) : i0;
     int jj = rep ? floormod(j0, p.bh) : j0;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const int ncol = (int)ceilf(hix) - i0;  // texel columns i0 .. i0 + ncol - 1 are those with (float)i < hix
+    if (ncol <= 3) {
+      // the usual footprints (bilinear, 2x minification): column weights, wrapped column indices and validity are
+      // computed once per pixel instead of once per tap; the taps are visited in the same order (rows outer, columns
+      // inner) with the same operands, so the sums are the oracle's
+      float wxc[3];
+      int ic[3];
+      bool vc[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const int i = i0 + c;
+        int t = ii0 + c;
+        if (rep)
+          while (t >= p.bw) t -= p.bw;
+        ic[c] = t;
+        vc[c] = c < ncol && (rep || (i >= 0 && i < p.bw));
+        const float vl = fmaxf(lox, (float)i), vh = fminf(hix, (float)(i + 1));
+        wxc[c] = fmaxf(vh - vl, 0.0f) * irx;
+      }
+      for (int j = j0; (float)j < hiy; j++) {
+        const int jcur = jj;
+        jj++;
+        if (rep && jj == p.bh) jj = 0;
+        if (!rep && (j < 0 || j >= p.bh)) continue;
+        float wl = fmaxf(loy, (float)j), wh = fminf(hiy, (float)(j + 1));
+        float wy = fmaxf(wh - wl, 0.0f) * iry;
+        const float yc = (float)jcur + 0.5f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (!vc[c]) continue;
+          uchar4 t = tex2D<uchar4>(tex, (float)ic[c] + 0.5f, yc);
+          float wgt = wxc[c] * wy;
+          acc0 = acc0 + wgt * (float)t.x;
+          acc1 = acc1 + wgt * (float)t.y;
+          acc2 = acc2 + wgt * (float)t.z;
+          acc3 = acc3 + wgt * (float)t.w;
+        }
+      }
+    } else {
     for (int j = j0; (float)j < hiy; j++) {
       const int jcur = jj;
       jj++;
@@ -1431,6 +1470,7 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
         acc2 = acc2 + wgt * (float)t.z;
         acc3 = acc3 + wgt * (float)t.w;
       }
+    }
     }
     uint32_t o = (uint32_t)__float2int_rn(fminf(fmaxf(acc0, 0.0f), 255.0f));
     o |= (uint32_t)__float2int_rn(fminf(fmaxf(acc1, 0.0f), 255.0f)) << 8;
@@ -1670,7 +1710,17 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
           slot_coverage(a, o0, o1, bd, acc, cross, lane, m);
         }
         // ---- paint + blend ----
-        if (type == PAINT_SOLID) {
+        if (type == PAINT_SOLID && o1 == o0) {
+          // the whole tile inside a solid path: over_masked(px, color, 255) without its per-pixel case analysis
+          const uint32_t ca = color >> 24;
+          if (ca == 255u) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) px[i] = color;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) px[i] = color + mul_un8x4(px[i], 255u - ca);
+          }
+        } else if (type == PAINT_SOLID) {
 #pragma unroll
           for (int i = 0; i < 8; i++)
             if (m[i]) px[i] = over_masked(px[i], color, m[i]);
