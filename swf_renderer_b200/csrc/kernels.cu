@@ -244,7 +244,7 @@ __global__ void k_init(RenderArgs a) {
     a.totals->n_edges = a.totals->n_slots = a.totals->n_records = 0;
     a.totals->overflow = 0;
     a.totals->error = 0;
-    a.totals->work = 0;
+    for (int k = 0; k < kMaxFineSlices; k++) a.totals->work[k] = 0;
     a.totals->n_list = 0;
     a.totals->n_big = 0;
     a.totals->n_big_chunk = 0;
@@ -1636,7 +1636,7 @@ __device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
+__global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
   if (a.totals->overflow | a.totals->overflow_stage) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
@@ -1648,13 +1648,13 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a) {
   __syncwarp();
   const int row = lane & 15, half = lane >> 4;
   const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
-  const uint32_t total = tiles * a.n_frames;
+  const uint32_t total = tiles * (frame_end - frame_begin);  // this launch composites frames [frame_begin, frame_end)
   while (true) {
     uint32_t w = 0;
-    if (lane == 0) w = atomicAdd(&a.totals->work, 1u);
+    if (lane == 0) w = atomicAdd(&a.totals->work[slice], 1u);
     w = __shfl_sync(0xffffffffu, w, 0);
     if (w >= total) break;
-    uint32_t frame = w / tiles, tile = w - frame * tiles;
+    uint32_t frame = frame_begin + w / tiles, tile = w % tiles;
     int ty = (int)(tile / (uint32_t)a.tiles_x), tx = (int)(tile - (uint32_t)ty * a.tiles_x);
     const int X0 = tx * kTile + half * 8, Y = ty * kTile + row;
     // candidates: the paint-ordered list of this tile's (row, column group)
@@ -1847,7 +1847,7 @@ const char *stage_name(int i) {
 }
 
 // ev (optional): kNumStages + 1 events recorded at the stage boundaries (profiling runs only).
-int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
+int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEvent_t *slice_done) {
   int launches = 0;
   const int T = 256;
   auto grid_for = [&](uint64_t n) {
@@ -1916,8 +1916,14 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev) {
     int v = e ? atoi(e) : 4;
     return v < 1 ? 1 : (v > 4 ? 4 : v);
   }();
-  k_fine<<<kNumSM * fine_blocks, kFineWarps * 32, 0, st>>>(a);
-  launches++;
+  {
+    const uint32_t fs = fine_slice_frames(a.n_frames), ns = fine_slices(a.n_frames);
+    for (uint32_t k = 0; k < ns; k++) {
+      k_fine<<<kNumSM * fine_blocks, kFineWarps * 32, 0, st>>>(a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
+      launches++;
+      if (slice_done) cudaEventRecord(slice_done[k], st);
+    }
+  }
   mark(6);
   return launches;
 }

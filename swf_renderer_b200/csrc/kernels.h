@@ -61,11 +61,14 @@ struct BitmapDev {
 };
 
 // Counters written by the device, read by the host after a sync.
+constexpr int kFineSliceFrames = 16;  // k_fine is launched per slice of this many frames, so that finished frames can
+constexpr int kMaxFineSlices = 16;    // leave for the host while the rest of the pass is still being composited
+
 struct Totals {
   uint32_t n_edges, n_slots, n_records;
   uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists, bit4 row lists
   uint32_t error;     // bit0: unknown bitmap id
-  uint32_t work;      // fine-kernel tile queue
+  uint32_t work[kMaxFineSlices];  // fine-kernel tile queues, one per slice of frames
   uint32_t n_list;    // candidate-list entries
   uint32_t n_big;     // visible path instances whose tile grid is larger than kBackdropSmall
   uint32_t n_big_chunk;  // ... of the depth chunk being processed
@@ -146,7 +149,19 @@ constexpr int kMaxChunks = 8;
 
 // Enqueues every kernel of one render on `stream`; returns the number of kernels launched.
 // `ev` (optional) points at kNumStages + 1 events recorded at the stage boundaries.
-int launch_render(const RenderArgs &a, cudaStream_t stream, cudaEvent_t *ev = nullptr);
+// `slice_done` (optional): one event per slice of frames (fine_slices(a.n_frames) of them), recorded when that slice's
+// frames are final.
+int launch_render(const RenderArgs &a, cudaStream_t stream, cudaEvent_t *ev = nullptr, cudaEvent_t *slice_done = nullptr);
+// Frames per slice / number of slices of a pass of n_frames frames.
+inline uint32_t fine_slice_frames(uint32_t n_frames) {
+  uint32_t f = kFineSliceFrames;
+  while ((n_frames + f - 1) / f > (uint32_t)kMaxFineSlices) f *= 2;
+  return f;
+}
+inline uint32_t fine_slices(uint32_t n_frames) {
+  uint32_t f = fine_slice_frames(n_frames);
+  return n_frames ? (n_frames + f - 1) / f : 1;
+}
 
 void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
 void launch_premultiply(const uint8_t *src, size_t stride, uint32_t w, uint32_t h, uint32_t *dst, uint32_t *translucent,

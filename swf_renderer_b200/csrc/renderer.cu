@@ -175,7 +175,7 @@ struct swfr_renderer {
   uint32_t stage_launches = 0;
   // readback overlapped with rendering: one event per pass, copies on their own stream
   cudaStream_t copy_stream = nullptr;
-  std::vector<cudaEvent_t> pass_done;
+  std::vector<cudaEvent_t> pass_done;  // kMaxFineSlices events per pass: slice k of pass i at [i * kMaxFineSlices + k]
   bool copy_pending = false;
   struct CopyReq {
     uint32_t first, count;
@@ -711,7 +711,7 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
     }
     r->prof_passes = b.passes.size();
   }
-  while (r->pass_done.size() < b.passes.size()) {
+  while (r->pass_done.size() < b.passes.size() * kMaxFineSlices) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     r->pass_done.push_back(e);
@@ -741,8 +741,8 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
       if (cf.first < b.passes[i].f0 + b.passes[i].n_frames && b.passes[i].f0 < cf.first + cf.count)
         CK(cudaStreamWaitEvent(st, cf.done, 0));
     launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), st,
-                                        r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr);
-    CK(cudaEventRecord(r->pass_done[i], st));
+                                        r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr,
+                                        r->pass_done.data() + i * kMaxFineSlices);
   }
   for (int k = 1; k < n_streams; k++) {
     CK(cudaEventRecord(r->join_ev[k - 1], r->extra_stream[k - 1]));
@@ -1258,20 +1258,24 @@ int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uin
   const swfr_batch &b = *r->last;
   for (size_t i = 0; i < b.passes.size(); i++) {
     const Pass &p = b.passes[i];
-    uint32_t lo = std::max(first, p.f0), hi = std::min(first + count, p.f0 + p.n_frames);
-    if (lo >= hi) continue;
-    CK(cudaStreamWaitEvent(r->copy_stream, r->pass_done[i], 0));
-    CK(cudaMemcpyAsync(dst + (size_t)(lo - first) * fb, (const char *)r->frames.p + (size_t)lo * fb, (size_t)(hi - lo) * fb,
-                       cudaMemcpyDeviceToHost, r->copy_stream));
-    cudaEvent_t done;
-    if (!r->fence_pool.empty()) {
-      done = r->fence_pool.back();
-      r->fence_pool.pop_back();
-    } else {
-      CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    const uint32_t fs = fine_slice_frames(p.n_frames), ns = fine_slices(p.n_frames);
+    for (uint32_t k = 0; k < ns; k++) {  // every slice of the pass' frames leaves as soon as it is final
+      const uint32_t s0 = p.f0 + k * fs, s1 = std::min(p.f0 + p.n_frames, s0 + fs);
+      uint32_t lo = std::max(first, s0), hi = std::min(first + count, s1);
+      if (lo >= hi) continue;
+      CK(cudaStreamWaitEvent(r->copy_stream, r->pass_done[i * kMaxFineSlices + k], 0));
+      CK(cudaMemcpyAsync(dst + (size_t)(lo - first) * fb, (const char *)r->frames.p + (size_t)lo * fb, (size_t)(hi - lo) * fb,
+                         cudaMemcpyDeviceToHost, r->copy_stream));
+      cudaEvent_t done;
+      if (!r->fence_pool.empty()) {
+        done = r->fence_pool.back();
+        r->fence_pool.pop_back();
+      } else {
+        CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(done, r->copy_stream));
+      r->copy_fences.push_back(swfr_renderer::CopyFence{lo, hi - lo, done});
     }
-    CK(cudaEventRecord(done, r->copy_stream));
-    r->copy_fences.push_back(swfr_renderer::CopyFence{lo, hi - lo, done});
   }
   r->copy_pending = true;
   r->copy_reqs.push_back(swfr_renderer::CopyReq{first, count, dst});
