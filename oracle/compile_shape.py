@@ -330,3 +330,132 @@ def _js_dump(v, indent):
 def to_golden_json(shape):
     """``JSON.stringify(shape, null, 2) + "\\n"`` (decode-shape.spec.ts:18)."""
     return _js_dump(shape, 0) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------
+# The Rust crate's decoder (rs/src/decoder/shape_decoder.rs), restated to pin the shape.rs.log goldens
+# (rs/src/lib.rs:38-69: `format!("{:#?}\n", decode_shape(&ast.shape))`).  Same layering and single-pass chain
+# extraction as the TypeScript compiler, but every segment becomes a straight LineTo (control points are dropped,
+# shape_decoder.rs:42-58) and styles are kept as swf-tree values.
+# ---------------------------------------------------------------------------------------------
+
+
+def rust_decode_shape(tag):
+    """decode_shape (shape_decoder.rs:18-33): [{"points": [(x, y)], "verbs": [...], "fill": style|None, "line": style|None}]."""
+    shape = tag["shape"]
+
+    def new_layer(styles):  # StyleLayerBuilder::new (shape_decoder.rs:181-207)
+        return {"fills": [(s, []) for s in styles["fill"]], "lines": [(s, []) for s in styles["line"]], "l": 0, "r": 0, "n": 0}
+
+    layers = []
+    top = new_layer(shape["initial_styles"])
+    pos = (0, 0)
+    for rec in shape["records"]:
+        if rec["type"] == "edge":  # apply_edge (shape_decoder.rs:104-109), add_segment (:209-219)
+            end = (pos[0] + rec["delta"]["x"], pos[1] + rec["delta"]["y"])
+            if top["l"]:
+                top["fills"][top["l"] - 1][1].append((pos, end))
+            if top["r"]:
+                top["fills"][top["r"] - 1][1].append((end, pos))
+            if top["n"]:
+                top["lines"][top["n"] - 1][1].append((pos, end))
+            pos = end
+        else:  # apply_style_change (shape_decoder.rs:111-127): new styles, left, right, line, move_to
+            if rec.get("new_styles") is not None:
+                layers.append(top)
+                top = new_layer(rec["new_styles"])
+            if rec.get("left_fill") is not None:
+                top["l"] = rec["left_fill"]
+            if rec.get("right_fill") is not None:
+                top["r"] = rec["right_fill"]
+            if rec.get("line_style") is not None:
+                top["n"] = rec["line_style"]
+            if rec.get("move_to") is not None:
+                pos = (rec["move_to"]["x"], rec["move_to"]["y"])
+    layers.append(top)
+
+    def to_path(segments):  # segments_to_path + extract_continuous (shape_decoder.rs:42-80)
+        points, verbs = [], []
+        open_set = list(segments)
+        while open_set:
+            first = open_set.pop(0)
+            start, end = first
+            chain, remaining = [first], []
+            for seg in open_set:
+                if seg[0] == end:
+                    end = seg[1]
+                    chain.append(seg)
+                elif seg[1] == start:
+                    start = seg[0]
+                    chain.insert(0, seg)
+                else:
+                    remaining.append(seg)
+            open_set = remaining
+            for k, seg in enumerate(chain):
+                if k == 0:
+                    points.append(seg[0])
+                    verbs.append("MoveTo")
+                points.append(seg[1])
+                verbs.append("LineTo")
+        return points, verbs
+
+    paths = []
+    for layer in layers:  # get_shape (shape_decoder.rs:129-165): fills, then lines, empty sets skipped
+        for style, segs in layer["fills"]:
+            if segs:
+                p, v = to_path(segs)
+                paths.append({"points": p, "verbs": v, "fill": style, "line": None})
+        for style, segs in layer["lines"]:
+            if segs:
+                p, v = to_path(segs)
+                paths.append({"points": p, "verbs": v, "fill": None, "line": style})
+    return paths
+
+
+def _rust_fill(style, ind):
+    if style["type"] != "solid":
+        raise NotImplementedError("Debug formatting of %s fills (no golden uses them)" % style["type"])
+    c = style["color"]
+    pad = " " * ind
+    return (
+        "Solid(\n%s    Solid {\n%s        color: StraightSRgba8 {\n%s            r: %d,\n%s            g: %d,\n"
+        "%s            b: %d,\n%s            a: %d,\n%s        },\n%s    },\n%s)"
+        % (pad, pad, pad, c["r"], pad, c["g"], pad, c["b"], pad, c["a"], pad, pad, pad)
+    )
+
+
+def rust_debug(paths):
+    """`{:#?}` of the Rust `Shape` (derive(Debug) on Shape / StyledPath, lyon's Path, swf-tree's styles)."""
+    cap = {"round": "Round", "none": "None", "square": "Square"}
+    out = ["Shape {", "    paths: ["]
+    for p in paths:
+        out += ["        StyledPath {", "            path: Path {", "                points: ["]
+        out += ["                    (%s,%s)," % (_rust_f32(x), _rust_f32(y)) for x, y in p["points"]]
+        out += ["                ],", "                verbs: ["]
+        out += ["                    %s," % v for v in p["verbs"]]
+        out += ["                ],", "            },"]
+        if p["fill"] is None:
+            out.append("            fill: None,")
+        else:
+            out += ["            fill: Some(", "                " + _rust_fill(p["fill"], 16) + ",", "            ),"]
+        if p["line"] is None:
+            out.append("            line: None,")
+        else:
+            ls = p["line"]
+            if ls["join"]["type"] != "round":
+                raise NotImplementedError("Debug formatting of %s joins (no golden uses them)" % ls["join"]["type"])
+            out += ["            line: Some(", "                LineStyle {"]
+            out += ["                    width: %d," % ls["width"], "                    start_cap: %s," % cap[ls["start_cap"]],
+                    "                    end_cap: %s," % cap[ls["end_cap"]], "                    join: Round,"]
+            for k in ("no_h_scale", "no_v_scale", "no_close", "pixel_hinting"):
+                out.append("                    %s: %s," % (k, "true" if ls[k] else "false"))
+            out += ["                    fill: " + _rust_fill(ls["fill"], 20) + ",", "                },", "            ),"]
+        out.append("        },")
+    out += ["    ],", "}"]
+    return "\n".join(out) + "\n"
+
+
+def _rust_f32(v):
+    """Debug of an f32 holding an integer-valued twips coordinate: one decimal place."""
+    f = float(v)
+    return "%.1f" % f if f == int(f) else repr(f)
