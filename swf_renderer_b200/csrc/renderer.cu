@@ -942,7 +942,7 @@ int swfr_create_on_stream(int device, uint32_t width, uint32_t height, void *cud
     }
     r->own_stream = true;
   }
-  if (const char *e = getenv("SWFR_FRAMES_PER_PASS")) r->frames_per_pass = (uint32_t)std::max(1, atoi(e));
+  if (const char *e = getenv("SWFR_FRAMES_PER_PASS")) r->frames_per_pass = (uint32_t)std::min(std::max(1, atoi(e)), 4096);
   if (const char *e = getenv("SWFR_ARENAS")) r->n_arenas = std::min(std::max(1, atoi(e)), (int)swfr_renderer::kArenas);
   *out = r;
   return SWFR_OK;
@@ -987,7 +987,7 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   switch (key) {
     case 1: r->retain_compiled = value != 0; return SWFR_OK;
-    case 2: r->frames_per_pass = (uint32_t)std::max<uint64_t>(1, value); return SWFR_OK;
+    case 2: r->frames_per_pass = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, value), 4096); return SWFR_OK;  // grid.y = frames
     case 3: r->profile = value != 0; return SWFR_OK;
     case 4: r->host_threads = (uint32_t)std::min<uint64_t>(value, 256); return SWFR_OK;
     case 5: r->clear_to_background = value != 0; return SWFR_OK;
