@@ -288,14 +288,16 @@ def run_ours(a):
     full.close()
     r.set_option(capi.OPT_OCCLUSION_CHUNKS, a.occlusion_chunks)
     batch = r.create_batch((stage_arr, keep))
+    # clocks are sampled from the warm-up on (the same load as the timed steps), every 100 ms, until the timed
+    # region ends
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(a.warmup, 3)):
         batch.render()
     r.sync()
     stats = r.stats()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(a.steps):
