@@ -267,6 +267,10 @@ __global__ void k_init(RenderArgs a) {
 }
 
 // One warp per draw item, lanes over its segments (contiguous in the segment store).
+// COUNT: also the number of line pieces of every segment (-> seg_edge_off, scanned into ordered edge offsets).  With
+// occlusion culling only visible segments are ever flattened, in no particular order, so the count is left to
+// k_flatten_emit and this kernel only finds the path bounds.
+template <bool COUNT>
 __global__ void k_flatten_count(RenderArgs a) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -279,7 +283,7 @@ __global__ void k_flatten_count(RenderArgs a) {
       bool curve;
       uint32_t pid;
       load_segment(a, item, j - s0, p, curve, pid);
-      a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
+      if (COUNT) a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
       a.seg_item[j] = it;
       int minx = min(p[0], min(p[2], p[4])), maxx = max(p[0], max(p[2], p[4]));
       int miny = min(p[1], min(p[3], p[5])), maxy = max(p[1], max(p[3], p[5]));
@@ -354,6 +358,8 @@ __global__ void k_path_alive(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
   const uint32_t frame = blockIdx.y;
   const uint32_t i0 = chunk_first(a, c, frame), i1 = chunk_first(a, c + 1, frame);
+  // unordered edges: those of this chunk start at the current cursor (k_flatten_emit<false> of the chunk runs next)
+  if (blockIdx.x == 0 && frame == 0 && threadIdx.x == 0) a.chunk_edge[c] = a.totals->n_edges;
   const uint32_t p0 = __ldg(a.item_path_off + i0), p1 = __ldg(a.item_path_off + i1);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -396,6 +402,10 @@ __global__ void k_path_alive(RenderArgs a, uint32_t c) {
 // control point, or the last point of the previous round.  Stores are coalesced 16-byte writes.
 constexpr int kEmitWarps = 8;
 
+// ORDERED (one depth chunk, every path emitted): piece counts and edge offsets come from k_flatten_count<true> + scan,
+// so the edge list is in segment order (what the edge tap returns).  Otherwise the pieces are counted here, for
+// visible segments only, and each warp takes the room for its 32 segments' edges from one cursor.
+template <bool ORDERED>
 __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
   __shared__ int sh_p[kEmitWarps][32][6];
@@ -428,8 +438,12 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
         bool curve;
         uint32_t pid;
         load_segment(a, item, local, p, curve, pid);
-        off = a.seg_edge_off[j];
-        n = (int)(a.seg_edge_off[j + 1] - off);
+        if (ORDERED) {
+          off = a.seg_edge_off[j];
+          n = (int)(a.seg_edge_off[j + 1] - off);
+        } else {
+          n = piece_count(curve, p);
+        }
 #pragma unroll
         for (int k = 0; k < 6; k++) sh_p[w][lane][k] = p[k];
         sh_inv[w][lane] = piece_inv2den(curve, n);
@@ -444,6 +458,17 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int excl = incl - n;
+    bool room = true;
+    if (!ORDERED) {
+      uint32_t base_e = 0;
+      if (lane == 0 && total) base_e = atomicAdd(&a.totals->n_edges, (uint32_t)total);
+      base_e = __shfl_sync(0xffffffffu, base_e, 0);
+      off = base_e + (uint32_t)excl;
+      if (total && (base_e + (uint32_t)total > a.caps.edges || base_e + (uint32_t)total < base_e)) {
+        if (lane == 0) atomicOr(&a.totals->overflow, 1u);
+        room = false;
+      }
+    }
     __syncwarp();
     int carry_x = 0, carry_y = 0;
     for (int k0 = 0; k0 < total; k0 += 32) {
@@ -474,7 +499,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
       }
       carry_x = __shfl_sync(0xffffffffu, qx, 31);
       carry_y = __shfl_sync(0xffffffffu, qy, 31);
-      if (k0 + (int)lane < total) {
+      if (room && k0 + (int)lane < total) {
         a.edges[off_o + (uint32_t)(i - 1)] = make_int4(px, py, qx, qy);
         a.edge_pid[off_o + (uint32_t)(i - 1)] = pc & 0x7fffffffu;
       }
@@ -847,14 +872,6 @@ __global__ void k_group_lists(RenderArgs a) {
   }
 }
 
-// Marks every edge as "not emitted" (edge_pid = ~0): with occlusion culling only the geometry of paths that are still
-// visible somewhere is emitted and binned.  (The slots of those paths are cleared by k_path_alive.)
-__global__ void k_clear_edges(RenderArgs a) {
-  if (a.totals->overflow) return;
-  uint32_t stride = gridDim.x * blockDim.x;
-  uint32_t ne = a.totals->n_edges;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += stride) a.edge_pid[i] = 0xffffffffu;
-}
 
 // ======================================================================================================
 // K2: tile binning (count, then scatter of tile-clipped 8-byte records)
@@ -971,8 +988,10 @@ __device__ __forceinline__ bool column_record(int xs, int ys, int xe, int ye, in
 // geometry again.
 constexpr int kBinWarps = 8;
 
+template <bool ORDERED>
 __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
+  __shared__ uint32_t sh_cover[kBinWarps][32];  // per edge: first tile of its frame in the cover map
   __shared__ int4 sh_edge[kBinWarps][32];
   __shared__ uint4 sh_path[kBinWarps][32];   // xy0, bw | first band << 16, slot base, path instance
   __shared__ int4 sh_piece[kBinWarps][32];   // band piece xs, ys, xe, ye
@@ -980,11 +999,17 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * kBinWarps * 32;
   const uint32_t cap_blocks = a.caps.stage / kStageBlock;
-  // edges of depth chunk c in frame blockIdx.y (segments, hence edges, are stored in item order)
-  const uint32_t frame = blockIdx.y;
-  const uint32_t e_begin = a.seg_edge_off[__ldg(a.item_seg_off + chunk_first(a, c, frame))];
-  const uint32_t e_end = a.seg_edge_off[__ldg(a.item_seg_off + chunk_first(a, c + 1, frame))];
-  const uint32_t *cover = a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y);
+  // ORDERED: the edges of depth chunk c in frame blockIdx.y (segments, hence edges, are stored in item order);
+  // otherwise the edges the chunk's k_flatten_emit appended, of all frames (grid.y = 1)
+  uint32_t e_begin, e_end;
+  if (ORDERED) {
+    e_begin = a.seg_edge_off[__ldg(a.item_seg_off + chunk_first(a, c, blockIdx.y))];
+    e_end = a.seg_edge_off[__ldg(a.item_seg_off + chunk_first(a, c + 1, blockIdx.y))];
+  } else {
+    e_begin = a.chunk_edge[c];
+    e_end = min(a.totals->n_edges, a.caps.edges);
+  }
+  const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
   uint32_t blk = 0, blk_used = kStageBlock;  // current staging block of this warp (none yet)
   bool have_blk = false, stage_full = false;
   for (uint32_t base = e_begin + (blockIdx.x * kBinWarps + w) * 32; base < e_end; base += stride) {
@@ -992,7 +1017,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
     int nb = 0;
     if (e < e_end) {
       const uint32_t pid = a.edge_pid[e];
-      if (pid != 0xffffffffu) {  // ~0: the edge was not emitted (its path is hidden)
+      {
         const int4 ed = a.edges[e];
         const PathRec rec = a.path_rec[pid];
         const int bw = rec.wh & 0xffff, bh = rec.wh >> 16, by0 = rec.xy0 >> 16;
@@ -1006,6 +1031,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
             nb = b_last - b_first + 1;
             sh_edge[w][lane] = ed;
             sh_path[w][lane] = make_uint4(rec.xy0, (uint32_t)bw | ((uint32_t)b_first << 16), a.path_slot_off[pid], pid);
+            sh_cover[w][lane] = (rec.info >> 16) * tiles;
           }
         }
       }
@@ -1041,8 +1067,9 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
         if (piece.c1 >= piece.c0) {
           nc = (uint32_t)(piece.c1 - piece.c0 + 1);
           sh_piece[w][lane] = make_int4(piece.xs, piece.ys, piece.xe, piece.ye);
-          sh_pmeta[w][lane] = make_uint4((uint32_t)piece.c0, piece.row_base + (uint32_t)(piece.c0 - bx0), (uint32_t)b,
-                                         pp.w | (small ? 0x80000000u : 0u));
+          // .z = index of the band's first tile in the cover map (the band top follows from the piece: see level 2)
+          sh_pmeta[w][lane] = make_uint4((uint32_t)piece.c0, piece.row_base + (uint32_t)(piece.c0 - bx0),
+                                         sh_cover[w][o] + (uint32_t)b * (uint32_t)a.tiles_x, pp.w | (small ? 0x80000000u : 0u));
         }
       }
       uint32_t cincl = nc;
@@ -1074,9 +1101,10 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
           pid = pm.w & 0x7fffffffu;
           slot = pm.y + j;
           // occlusion culling: an opaque path of a chunk above covers this tile completely
-          if (__ldg(cover + pm.z * (uint32_t)a.tiles_x + pm.x + j) <= pid) {
+          if (__ldg(a.tile_cover + pm.z + pm.x + j) <= pid) {
             const int4 pc = sh_piece[w][o2];
-            const int Yt = (int)pm.z * kTileFx;
+            // a band piece lies in [Yt, Yt + 4096) with at most its lower end on the bottom line
+            const int Yt = min(pc.y, pc.w) & ~(kTileFx - 1);
             keep = (pm.w >> 31) ? column_record<true>(pc.x, pc.y, pc.z, pc.w, Yt, (int)(pm.x + j), rc)
                                 : column_record<false>(pc.x, pc.y, pc.z, pc.w, Yt, (int)(pm.x + j), rc);
           }
@@ -1862,14 +1890,21 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   mark(0);
   k_init<<<grid_for(a.n_paths), T, 0, st>>>(a);
   launches++;
+  // One depth chunk: every path is flattened, edges in segment order (the taps' mode).  More: only what is visible is
+  // flattened, unordered, chunk by chunk.
+  const bool ordered = a.n_chunks == 1;
   if (a.n_seginst) {
-    k_flatten_count<<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
+    if (ordered)
+      k_flatten_count<true><<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
+    else
+      k_flatten_count<false><<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
     launches++;
   }
   mark(1);
   // edges: seg_edge_off (piece counts) -> exclusive offsets, total -> totals.n_edges
-  scan_u32(a.seg_edge_off, a.seg_edge_off, nullptr, a.n_seginst, a.scan_tmp, &a.totals->n_edges, a.caps.edges, &a.totals->overflow, 1u,
-           st, launches);
+  if (ordered)
+    scan_u32(a.seg_edge_off, a.seg_edge_off, nullptr, a.n_seginst, a.scan_tmp, &a.totals->n_edges, a.caps.edges, &a.totals->overflow,
+             1u, st, launches);
   mark(2);
   if (a.n_paths) {
     k_path_setup<<<grid_for(a.n_paths), T, 0, st>>>(a);
@@ -1878,8 +1913,6 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   scan_u32(a.path_slot_off, a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
            st, launches);
   mark(3);
-  k_clear_edges<<<wide, T, 0, st>>>(a);
-  launches++;
   // K1 emit + K2, depth chunk by depth chunk from the top one down: what a chunk covers opaquely hides the
   // geometry of the chunks below it (grid.y = frame; every kernel walks its frame's part of the chunk)
   if (a.n_seginst && a.n_paths) {
@@ -1891,8 +1924,13 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
         launches++;
       }
       k_path_alive<<<g2, T, 0, st>>>(a, c);
-      k_flatten_emit<<<g2, kEmitWarps * 32, 0, st>>>(a, c);
-      k_bin<<<g2, kBinWarps * 32, 0, st>>>(a, c);
+      if (ordered) {
+        k_flatten_emit<true><<<g2, kEmitWarps * 32, 0, st>>>(a, c);
+        k_bin<true><<<g2, kBinWarps * 32, 0, st>>>(a, c);
+      } else {
+        k_flatten_emit<false><<<g2, kEmitWarps * 32, 0, st>>>(a, c);
+        k_bin<false><<<wide, kBinWarps * 32, 0, st>>>(a, c);
+      }
       k_cover<<<dim3(per_frame + kBigBlocksPerFrame, a.n_frames), T, 0, st>>>(a, c);
       launches += 4;
     }

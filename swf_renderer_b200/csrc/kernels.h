@@ -123,6 +123,7 @@ struct RenderArgs {
   uint32_t *tile_cover;         // n_frames * tiles: 1 + the highest path instance that covers the tile opaquely, 0 = none
   uint32_t *path_alive;         // n_paths: 0 when every tile of the path's bbox is covered from above
   uint32_t *cover_sat;          // n_frames * (tiles_x + 1) * (tiles_y + 1): summed-area table of uncovered tiles
+  uint32_t *chunk_edge;         // kMaxChunks + 1: edge cursor at the start of each depth chunk (unordered edges)
   uint32_t *frames;         // n_frames * width * height
   uint32_t *scan_tmp;       // >= 4096 words
   // candidate lists: for every (frame, tile row, group of kGroupTiles tile columns) the path instances whose

@@ -143,7 +143,7 @@ struct swfr_renderer {
   // Two arenas: consecutive passes of a batch alternate between them and between two streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
-    DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive;
+    DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive, chunk_edge;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
@@ -582,6 +582,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     CK(A.cover_sat.reserve((size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256));
   }
   CK(A.scan_tmp.reserve(8192 * 4));
+  CK(A.chunk_edge.reserve(64 * 4));
   }
   CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
   CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
@@ -654,6 +655,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.tile_cover = A.tile_cover.as<uint32_t>();
   a.path_alive = A.path_alive.as<uint32_t>();
   a.cover_sat = A.cover_sat.as<uint32_t>();
+  a.chunk_edge = A.chunk_edge.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
   a.ramps = r->d_ramps.as<float>();
