@@ -359,6 +359,12 @@ int compile_definition(const swfr_define_shape *tag, bool morph, CompiledDef &ou
       }
     }
   }
+  // bounds of every device path (start and end state: SegMorph holds s[6] then e[6] = 6 points)
+  if (!out.segs.empty())
+    set_paint_bounds(out.paints.data(), out.paints.size(), out.segs[0].s, out.segs.size(), sizeof(SegMorph) / sizeof(float), 6,
+                     &out.segs[0].path_flags, sizeof(SegMorph));
+  else
+    set_paint_bounds(out.paints.data(), out.paints.size(), nullptr, 0, 0, 0, nullptr, 0);
   return SWFR_OK;
 }
 

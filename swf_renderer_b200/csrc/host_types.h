@@ -39,7 +39,37 @@ struct DefPaint {
   double focal;
   int32_t lut;       // index of the 257-entry ramp in the ramp store, -1 if none
   uint32_t bitmap_id;
+  float bounds[4];   // x_min, y_min, x_max, y_max of the path's control points in twips, both morph states
+                     // (x_min > x_max: no segments); the device derives the instance's tile bbox from its corners
 };
+
+// Bounds of the control points of every path of a definition's segments -> DefPaint::bounds.
+inline void set_paint_bounds(DefPaint *paints, size_t n_paints, const float *seg_points, size_t n_segs, size_t seg_stride_floats,
+                             size_t points_per_seg, const uint32_t *path_flags, size_t flags_stride_bytes) {
+  for (size_t k = 0; k < n_paints; k++) {
+    paints[k].bounds[0] = paints[k].bounds[1] = 1.0f;
+    paints[k].bounds[2] = paints[k].bounds[3] = 0.0f;  // empty
+  }
+  for (size_t i = 0; i < n_segs; i++) {
+    const uint32_t pf = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(path_flags) + i * flags_stride_bytes);
+    const size_t path = pf & 0x7fffffffu;
+    if (path >= n_paints) continue;
+    DefPaint &p = paints[path];
+    const float *q = seg_points + i * seg_stride_floats;
+    for (size_t k = 0; k < points_per_seg; k++) {
+      const float x = q[2 * k], y = q[2 * k + 1];
+      if (p.bounds[0] > p.bounds[2]) {
+        p.bounds[0] = p.bounds[2] = x;
+        p.bounds[1] = p.bounds[3] = y;
+      } else {
+        p.bounds[0] = x < p.bounds[0] ? x : p.bounds[0];
+        p.bounds[2] = x > p.bounds[2] ? x : p.bounds[2];
+        p.bounds[1] = y < p.bounds[1] ? y : p.bounds[1];
+        p.bounds[3] = y > p.bounds[3] ? y : p.bounds[3];
+      }
+    }
+  }
+}
 
 // Definition table entry.
 struct DefEntry {

@@ -258,18 +258,13 @@ __global__ void k_init(RenderArgs a) {
   for (uint32_t l = i; l < a.caps.stage / kStageBlock; l += stride) a.stage_used[l] = 0;
   for (uint32_t l = i; l < a.n_frames * (uint32_t)(a.tiles_x * a.tiles_y); l += stride) a.tile_cover[l] = 0;
   for (uint32_t l = i; l < a.n_items; l += stride) a.item_alive[l] = 0;
-  for (uint32_t p = i; p < a.n_paths; p += stride) {
-    a.path_bbox[4 * p + 0] = INT_MAX;
-    a.path_bbox[4 * p + 1] = INT_MAX;
-    a.path_bbox[4 * p + 2] = INT_MIN;
-    a.path_bbox[4 * p + 3] = INT_MIN;
-  }
 }
 
 // One warp per draw item, lanes over its segments (contiguous in the segment store).
-// COUNT: also the number of line pieces of every segment (-> seg_edge_off, scanned into ordered edge offsets).  With
-// occlusion culling only visible segments are ever flattened, in no particular order, so the count is left to
-// k_flatten_emit and this kernel only finds the path bounds.
+// One warp per draw item, lanes over its (contiguous) segments: the draw item of every segment instance, and (COUNT,
+// the ordered mode) the number of line pieces of every segment -> seg_edge_off, scanned into edge offsets.  With
+// occlusion culling only visible segments are ever flattened, in no particular order, and the pieces are counted by
+// k_flatten_emit.
 template <bool COUNT>
 __global__ void k_flatten_count(RenderArgs a) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -277,29 +272,18 @@ __global__ void k_flatten_count(RenderArgs a) {
   for (uint32_t it = warp; it < a.n_items; it += nwarps) {
     const uint32_t s0 = __ldg(a.item_seg_off + it), s1 = __ldg(a.item_seg_off + it + 1);
     if (s0 == s1) continue;
+    if (!COUNT) {
+      for (uint32_t j = s0 + lane; j < s1; j += 32) a.seg_item[j] = it;
+      continue;
+    }
     const ItemRegs item = load_item(a, it);
     for (uint32_t j = s0 + lane; j < s1; j += 32) {
       int p[6];
       bool curve;
       uint32_t pid;
       load_segment(a, item, j - s0, p, curve, pid);
-      if (COUNT) a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
+      a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
       a.seg_item[j] = it;
-      int minx = min(p[0], min(p[2], p[4])), maxx = max(p[0], max(p[2], p[4]));
-      int miny = min(p[1], min(p[3], p[5])), maxy = max(p[1], max(p[3], p[5]));
-      // lanes working on the same path combine their bounds before touching memory
-      const unsigned active = __activemask();
-      const unsigned grp = __match_any_sync(active, pid);
-      minx = __reduce_min_sync(grp, minx);
-      miny = __reduce_min_sync(grp, miny);
-      maxx = __reduce_max_sync(grp, maxx);
-      maxy = __reduce_max_sync(grp, maxy);
-      if (lane == (uint32_t)(__ffs(grp) - 1)) {
-        atomicMin(&a.path_bbox[4 * pid + 0], minx);
-        atomicMin(&a.path_bbox[4 * pid + 1], miny);
-        atomicMax(&a.path_bbox[4 * pid + 2], maxx);
-        atomicMax(&a.path_bbox[4 * pid + 3], maxy);
-      }
     }
   }
 }
@@ -682,9 +666,25 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
     const DrawItem &item = a.items[it];
     const DefPaint &dp = ((item.kind & ITEM_KIND_MASK) == ITEM_DYNAMIC ? a.paints_dynamic
                                                                        : a.def_paints)[item.paint_first + (pid - a.item_path_off[it])];
-    // ---- tile bbox ----
-    int minx = a.path_bbox[4 * pid + 0], miny = a.path_bbox[4 * pid + 1];
-    int maxx = a.path_bbox[4 * pid + 2], maxy = a.path_bbox[4 * pid + 3];
+    // ---- tile bbox: the device-space hull of the corners of the path's control-point bounds (both morph states).
+    // The transform is affine, so every control point of the instance lies inside it up to rounding; one 1/256 px
+    // unit of padding covers that.  (Exact for translations and scales, looser under rotation.)
+    int minx = 1, miny = 1, maxx = 0, maxy = 0;
+    if (dp.bounds[0] <= dp.bounds[2]) {
+      double ctm[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) ctm[k] = (double)item.m[k] * 0.05;
+      minx = miny = INT_MAX;
+      maxx = maxy = INT_MIN;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int fx, fy;
+        to_device_fx(ctm, (double)dp.bounds[(k & 1) ? 2 : 0], (double)dp.bounds[(k & 2) ? 3 : 1], fx, fy);
+        minx = min(minx, fx), maxx = max(maxx, fx);
+        miny = min(miny, fy), maxy = max(maxy, fy);
+      }
+      minx -= 1, miny -= 1, maxx += 1, maxy += 1;
+    }
     int bx0 = 0, by0 = 0, bw = 0, bh = 0;
     if (minx <= maxx) {
       bx0 = max(minx >> 12, 0);

@@ -102,7 +102,6 @@ struct RenderArgs {
   const BitmapDev *bitmaps;
   uint32_t *seg_edge_off;   // n_seginst + 1 (piece counts, then exclusive scan)
   uint32_t *seg_item;       // n_seginst: draw item of each segment instance
-  int32_t *path_bbox;       // n_paths * 4 (min x, min y, max x, max y in 24.8)
   PathRec *path_rec;        // n_paths
   PaintInst *paint_inst;    // n_paths
   uint32_t *path_slot_off;  // n_paths + 1

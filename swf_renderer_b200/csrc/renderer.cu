@@ -143,7 +143,7 @@ struct swfr_renderer {
   // Two arenas: consecutive passes of a batch alternate between them and between two streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
-    DevBuf seg_edge_off, seg_item, path_bbox, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive, chunk_edge;
+    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive, chunk_edge;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
@@ -249,6 +249,7 @@ static void expand_morph_strokes(const std::vector<MorphLine> &lines, double r, 
   double width_state = 1.0;
   std::vector<Command> cmds;
   std::vector<StrokeSeg> ss;
+  const size_t paint0 = paints.size(), seg0 = segs.size();  // path indices are local to this draw
   for (const MorphLine &ml : lines) {
     double w = lerp_host(ml.w0, ml.w1, r);
     if (w > 0) width_state = w;
@@ -263,7 +264,7 @@ static void expand_morph_strokes(const std::vector<MorphLine> &lines, double r, 
     }
     ss.clear();
     stroke_commands(cmds, width_state, true, ss);
-    uint32_t path = (uint32_t)paints.size();
+    uint32_t path = (uint32_t)(paints.size() - paint0);
     DefPaint p{};
     p.type = PAINT_SOLID;
     p.lut = -1;
@@ -278,6 +279,9 @@ static void expand_morph_strokes(const std::vector<MorphLine> &lines, double r, 
       segs.push_back(g);
     }
   }
+  if (paints.size() > paint0)
+    set_paint_bounds(paints.data() + paint0, paints.size() - paint0, segs.size() > seg0 ? segs[seg0].p : nullptr, segs.size() - seg0,
+                     sizeof(SegStatic) / sizeof(float), 3, segs.size() > seg0 ? &segs[seg0].path_flags : nullptr, sizeof(SegStatic));
 }
 
 // Flattens stages into draw items (reference: CanvasRenderer.renderStage / drawDisplayObject,
@@ -560,7 +564,6 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   swfr_renderer::Arena &A = r->arena[k];
   CK(A.seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
   CK(A.seg_item.reserve((size_t)max_seg * 4 + 256));
-  CK(A.path_bbox.reserve((size_t)max_paths * 16 + 256));
   CK(A.path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
   CK(A.paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
   CK(A.path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
@@ -662,7 +665,6 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.bitmaps = r->d_bitmaps.as<BitmapDev>();
   a.seg_edge_off = A.seg_edge_off.as<uint32_t>();
   a.seg_item = A.seg_item.as<uint32_t>();
-  a.path_bbox = A.path_bbox.as<int32_t>();
   a.path_rec = A.path_rec.as<PathRec>();
   a.paint_inst = A.paint_inst.as<PaintInst>();
   a.path_slot_off = A.path_slot_off.as<uint32_t>();

@@ -181,6 +181,11 @@ def test_morph_strokes_in_a_batched_sweep_and_float_ratio(built_library):
         sc.draw_morph(plain, [0.5, 0.5, 0.0, 0.0, m[4] * 0.5, m[5] * 0.5], 65535 - rt, frame=f)
     sc.draw_morph(idx, m, 0, frame=len(ratios), ratio_f=0.5)
     sc.draw_morph(idx, m, 0, frame=len(ratios) + 1, ratio_f=0.25)
+    # several stroked morph shapes in one frame (each draw gets its own transient stroke definition)
+    f2 = len(ratios) + 2
+    sc.draw_morph(idx, m, 20000, frame=f2)
+    sc.draw_morph(idx, [0.6, 0.6, 0.0, 0.0, m[4] * 0.6 + 300.0, m[5] * 0.6 + 200.0], 50000, frame=f2)
+    sc.draw_morph(idx, [0.5, 0.5, 0.2, -0.2, m[4] * 0.5 + 900.0, m[5] * 0.5], 65535, frame=f2)
     r, stages = corpus.make_product(sc)
     r.set_option(capi.OPT_FRAMES_PER_PASS, 4)
     r.render_batch(stages)
