@@ -248,6 +248,7 @@ __global__ void k_init(RenderArgs a) {
     a.totals->n_list = 0;
     a.totals->n_big = 0;
     a.totals->n_big_chunk = 0;
+    a.totals->n_alive_items = 0;
     a.totals->n_rowent = 0;
     a.totals->n_stage_blocks = 0;
     a.totals->overflow_stage = 0;
@@ -261,21 +262,16 @@ __global__ void k_init(RenderArgs a) {
 }
 
 // One warp per draw item, lanes over its segments (contiguous in the segment store).
-// One warp per draw item, lanes over its (contiguous) segments: the draw item of every segment instance, and (COUNT,
-// the ordered mode) the number of line pieces of every segment -> seg_edge_off, scanned into edge offsets.  With
-// occlusion culling only visible segments are ever flattened, in no particular order, and the pieces are counted by
-// k_flatten_emit.
-template <bool COUNT>
+// The ordered mode (one depth chunk): one warp per draw item, lanes over its (contiguous) segments - the draw item of
+// every segment instance and the number of line pieces of every segment -> seg_edge_off, scanned into edge offsets.
+// (With occlusion culling only visible segments are flattened, in no particular order, and k_flatten_emit<false>
+// counts their pieces itself.)
 __global__ void k_flatten_count(RenderArgs a) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t it = warp; it < a.n_items; it += nwarps) {
     const uint32_t s0 = __ldg(a.item_seg_off + it), s1 = __ldg(a.item_seg_off + it + 1);
     if (s0 == s1) continue;
-    if (!COUNT) {
-      for (uint32_t j = s0 + lane; j < s1; j += 32) a.seg_item[j] = it;
-      continue;
-    }
     const ItemRegs item = load_item(a, it);
     for (uint32_t j = s0 + lane; j < s1; j += 32) {
       int p[6];
@@ -296,7 +292,10 @@ __global__ void k_flatten_count(RenderArgs a) {
 __global__ void __launch_bounds__(1024) k_cover_sat(RenderArgs a) {
   if (a.totals->overflow) return;
   const uint32_t frame = blockIdx.x;
-  if (frame == 0 && threadIdx.x == 0) a.totals->n_big_chunk = 0;  // the list of the chunk about to be processed
+  if (frame == 0 && threadIdx.x == 0) {  // the lists of the chunk about to be processed
+    a.totals->n_big_chunk = 0;
+    a.totals->n_alive_items = 0;
+  }
   const int tx = a.tiles_x, ty = a.tiles_y, sw = tx + 1;
   const uint32_t *cover = a.tile_cover + frame * (uint32_t)(tx * ty);
   uint32_t *sat = a.cover_sat + (size_t)frame * (size_t)sw * (size_t)(ty + 1);
@@ -363,11 +362,11 @@ __global__ void k_path_alive(RenderArgs a, uint32_t c) {
       a.path_alive[pid] = alive ? 1u : 0u;
       a.path_rec_base[pid] = 0;
       if (alive) {
-        a.item_alive[a.path_item[pid]] = 1u;
-        if (bw * bh > kBackdropSmall) {  // large tile grids are scanned by whole blocks: this chunk's list, and all of them
-          a.big_chunk[atomicAdd(&a.totals->n_big_chunk, 1u)] = pid;
-          a.big_list[atomicAdd(&a.totals->n_big, 1u)] = pid;
-        }
+        // the draw items with something visible: k_flatten_emit<false> walks this list (one entry per item)
+        const uint32_t it = a.path_item[pid];
+        if (atomicExch(&a.item_alive[it], 1u) == 0u) a.alive_items[atomicAdd(&a.totals->n_alive_items, 1u)] = it;
+        // large tile grids are scanned by whole blocks
+        if (bw * bh > kBackdropSmall) a.big_chunk[atomicAdd(&a.totals->n_big_chunk, 1u)] = pid;
       }
     }
     if (alive) {
@@ -389,26 +388,18 @@ constexpr int kEmitWarps = 8;
 // ORDERED (one depth chunk, every path emitted): piece counts and edge offsets come from k_flatten_count<true> + scan,
 // so the edge list is in segment order (what the edge tap returns).  Otherwise the pieces are counted here, for
 // visible segments only, and each warp takes the room for its 32 segments' edges from one cursor.
+// 32 segment instances (lane `lane` holds segment j when `valid`; in the unordered mode all of them belong to draw
+// item it_known): pieces of the visible ones, spread evenly over the lanes.
 template <bool ORDERED>
-__global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, uint32_t c) {
-  if (a.totals->overflow) return;
-  __shared__ int sh_p[kEmitWarps][32][6];
-  __shared__ double sh_inv[kEmitWarps][32];
-  __shared__ uint32_t sh_pid[kEmitWarps][32];  // path instance | curve << 31
-  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t stride = gridDim.x * kEmitWarps * 32;
-  // segment instances of depth chunk c in frame blockIdx.y
-  const uint32_t s_begin = __ldg(a.item_seg_off + chunk_first(a, c, blockIdx.y));
-  const uint32_t s_end = __ldg(a.item_seg_off + chunk_first(a, c + 1, blockIdx.y));
-  for (uint32_t base = s_begin + (blockIdx.x * kEmitWarps + w) * 32; base < s_end; base += stride) {
-    const uint32_t j = base + lane;
+__device__ __forceinline__ void emit_segments(const RenderArgs &a, int (*sh_p)[6], double *sh_inv, uint32_t *sh_pid, uint32_t lane,
+                                              uint32_t j, bool valid, uint32_t it_known) {
     int n = 0;
     uint32_t off = 0;
-    if (j < s_end) {
-      const uint32_t it = a.seg_item[j];
-      bool visible = __ldg(a.item_alive + it) != 0;  // no path of the draw item is visible: skip it at once
+    if (valid) {
+      const uint32_t it = ORDERED ? a.seg_item[j] : it_known;
+      bool visible = true;
       uint32_t local = 0;
-      if (visible) {
+      {
         local = j - __ldg(a.item_seg_off + it);
         ItemRegs head;  // the three fields segment_pid needs; the matrix is loaded for visible paths only
         head.seg_first = __ldg(&a.items[it].seg_first);
@@ -429,9 +420,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
           n = piece_count(curve, p);
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) sh_p[w][lane][k] = p[k];
-        sh_inv[w][lane] = piece_inv2den(curve, n);
-        sh_pid[w][lane] = pid | (curve ? 0x80000000u : 0u);
+        for (int k = 0; k < 6; k++) sh_p[lane][k] = p[k];
+        sh_inv[lane] = piece_inv2den(curve, n);
+        sh_pid[lane] = pid | (curve ? 0x80000000u : 0u);
       }
     }
     int incl = n;
@@ -469,10 +460,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
       const int i = k - first + 1;  // 1..n_o
       int p[6];
 #pragma unroll
-      for (int q = 0; q < 6; q++) p[q] = sh_p[w][o][q];
-      const uint32_t pc = sh_pid[w][o];
+      for (int q = 0; q < 6; q++) p[q] = sh_p[o][q];
+      const uint32_t pc = sh_pid[o];
       int qx, qy;
-      piece_point((pc >> 31) != 0, p, n_o, i, sh_inv[w][o], qx, qy);
+      piece_point((pc >> 31) != 0, p, n_o, i, sh_inv[o], qx, qy);
       int px = __shfl_up_sync(0xffffffffu, qx, 1), py = __shfl_up_sync(0xffffffffu, qy, 1);
       if (i == 1) {
         px = p[0];
@@ -489,6 +480,31 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
       }
     }
     __syncwarp();
+}
+
+template <bool ORDERED>
+__global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, uint32_t c) {
+  if (a.totals->overflow) return;
+  __shared__ int sh_p[kEmitWarps][32][6];
+  __shared__ double sh_inv[kEmitWarps][32];
+  __shared__ uint32_t sh_pid[kEmitWarps][32];  // path instance | curve << 31
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (ORDERED) {
+    // segment instances of depth chunk c in frame blockIdx.y, in order
+    const uint32_t stride = gridDim.x * kEmitWarps * 32;
+    const uint32_t s_begin = __ldg(a.item_seg_off + chunk_first(a, c, blockIdx.y));
+    const uint32_t s_end = __ldg(a.item_seg_off + chunk_first(a, c + 1, blockIdx.y));
+    for (uint32_t base = s_begin + (blockIdx.x * kEmitWarps + w) * 32; base < s_end; base += stride)
+      emit_segments<true>(a, sh_p[w], sh_inv[w], sh_pid[w], lane, base + lane, base + lane < s_end, 0u);
+  } else {
+    // the draw items of the chunk with a visible path (listed by k_path_alive), one warp per item
+    const uint32_t n_alive = a.totals->n_alive_items;
+    const uint32_t nwarps = gridDim.x * gridDim.y * kEmitWarps;
+    for (uint32_t ai = (blockIdx.y * gridDim.x + blockIdx.x) * kEmitWarps + w; ai < n_alive; ai += nwarps) {
+      const uint32_t it = a.alive_items[ai];
+      const uint32_t s0 = __ldg(a.item_seg_off + it), s1 = __ldg(a.item_seg_off + it + 1);
+      for (uint32_t base = s0; base < s1; base += 32) emit_segments<false>(a, sh_p[w], sh_inv[w], sh_pid[w], lane, base + lane, base + lane < s1, it);
+    }
   }
 }
 
@@ -795,6 +811,37 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
 //   k_row_lists   - one block per (frame, tile row) sweeps the frame's path instances in order and keeps those whose
 //                   bbox covers the row, as (path instance, tile x-range); it also counts entries per column group;
 //   k_group_lists - one warp per (frame, row, group) sweeps that row list in order and keeps the overlapping ones.
+// The visible path instances of every frame, in paint order (ordered compaction, one block per frame): what the row
+// lists are built from.
+__global__ void __launch_bounds__(1024) k_alive_paths(RenderArgs a) {
+  if (a.totals->overflow) return;
+  __shared__ uint32_t sh_warp[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (uint32_t frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+    const uint32_t p0 = a.frame_path_off[frame], p1 = a.frame_path_off[frame + 1];
+    uint32_t out = p0;
+    for (uint32_t base = p0; base < p1; base += 1024) {
+      const uint32_t pid = base + tid;
+      const bool hit = pid < p1 && __ldg(a.path_alive + pid) != 0 && (__ldg(&a.path_rec[pid].wh) & 0xffffu) != 0;
+      const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) sh_warp[w] = __popc(mask);
+      __syncthreads();
+      uint32_t wbase = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        const uint32_t c = sh_warp[k];
+        if (k < (int)w) wbase += c;
+        tot += c;
+      }
+      if (hit) a.alive_paths[out + wbase + __popc(mask & ((1u << lane) - 1u))] = pid;
+      out += tot;
+      __syncthreads();
+    }
+    if (tid == 0) a.alive_count[frame] = out - p0;
+    __syncthreads();
+  }
+}
+
 constexpr int kRowThreads = 256;
 constexpr int kMaxGroups = 512;  // tile columns <= 4096: frames up to 65536 px wide
 
@@ -807,18 +854,19 @@ __global__ void __launch_bounds__(kRowThreads) k_row_lists(RenderArgs a) {
   for (uint32_t rl = blockIdx.x; rl < n_rows; rl += gridDim.x) {
     const uint32_t frame = rl / (uint32_t)a.tiles_y;
     const int row = (int)(rl - frame * (uint32_t)a.tiles_y);
-    const uint32_t p0 = a.frame_path_off[frame], p1 = a.frame_path_off[frame + 1];
+    // the frame's visible paths, in paint order (k_alive_paths): hidden ones are left out of the lists
+    const uint32_t p0 = a.frame_path_off[frame], p1 = p0 + a.alive_count[frame];
     for (uint32_t g = tid; g < a.groups_x; g += kRowThreads) sh_grp[g] = 0;
     __syncthreads();
     uint32_t out = a.row_off[rl];
     for (uint32_t base = p0; base < p1; base += kRowThreads) {
-      const uint32_t pid = base + tid;
       bool hit = false;
-      uint32_t xr = 0;
-      if (pid < p1) {
+      uint32_t xr = 0, pid = 0;
+      if (base + tid < p1) {
+        pid = __ldg(a.alive_paths + base + tid);
         const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));  // xy0, wh
         const int by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
-        hit = bw > 0 && row >= by0 && row < by0 + bh && __ldg(a.path_alive + pid) != 0;  // hidden paths are left out
+        hit = row >= by0 && row < by0 + bh;
         xr = (r.x & 0xffffu) | ((uint32_t)bw << 16);
       }
       const uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -1293,8 +1341,11 @@ __device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid,
 
 constexpr int kBigBlocksPerFrame = 16;  // blocks (per frame row of the grid) that serve the large-grid paths
 
-// Per depth chunk, after its binning: winding numbers (backdrop prefix) of the chunk's visible paths, and the tiles
-// they cover opaquely.  grid = (small-path blocks + kBigBlocksPerFrame, frames).
+// Per depth chunk, after its binning (a path is binned in its own chunk only, so its counts are final): winding
+// numbers (backdrop prefix) of the chunk's visible paths, the tiles they cover opaquely, and the inclusive prefix of
+// their record counts -> slot_off (END of each slot's record range, relative to the path) + the path's first record
+// (alloc_records): record space is allocated path by path, so there is no global scan over the (much longer) slot
+// array.  grid = (small-path blocks + kBigBlocksPerFrame, frames).
 __global__ void __launch_bounds__(256) k_cover(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
   __shared__ uint32_t sh[32];
@@ -1310,7 +1361,7 @@ __global__ void __launch_bounds__(256) k_cover(RenderArgs a, uint32_t c) {
       const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
       const uint32_t n = (rec.y & 0xffff) * (rec.y >> 16);
       if (n == 0 || n > (uint32_t)kBackdropSmall) continue;
-      small_path_scan<true, false>(a, pid, rec, lane, cover);
+      small_path_scan<true, true>(a, pid, rec, lane, cover);
     }
   } else {
     const uint32_t n_big = a.totals->n_big_chunk;  // the visible large paths of this chunk (k_path_alive)
@@ -1319,36 +1370,7 @@ __global__ void __launch_bounds__(256) k_cover(RenderArgs a, uint32_t c) {
       const uint32_t pid = a.big_chunk[bi];
       const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
       const uint32_t frame = rec.z >> 16;
-      big_path_scan<true, false>(a, pid, rec, a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y), sh);
-    }
-  }
-}
-
-// After the last chunk: inclusive prefix of the record counts of every visible path -> slot_off (END of each slot's
-// record range, relative to the path) and the path's first record (alloc_records).  Record space is allocated path
-// by path, so there is no global scan over the (much longer) slot array.  grid.x = small-path blocks + big blocks.
-constexpr int kPrefixBigBlocks = kNumSM * 2;
-
-__global__ void __launch_bounds__(256) k_slot_prefix(RenderArgs a) {
-  if (a.totals->overflow) return;
-  __shared__ uint32_t sh[32];
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t small_blocks = gridDim.x - kPrefixBigBlocks;
-  if (blockIdx.x < small_blocks) {
-    const uint32_t nwarps = (small_blocks * blockDim.x) >> 5;
-    for (uint32_t pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < a.n_paths; pid += nwarps) {
-      if (!a.path_alive[pid]) continue;
-      const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
-      const uint32_t n = (rec.y & 0xffff) * (rec.y >> 16);
-      if (n == 0 || n > (uint32_t)kBackdropSmall) continue;
-      small_path_scan<false, true>(a, pid, rec, lane, nullptr);
-    }
-  } else {
-    const uint32_t n_big = a.totals->n_big;
-    for (uint32_t bi = blockIdx.x - small_blocks; bi < n_big; bi += kPrefixBigBlocks) {
-      const uint32_t pid = a.big_list[bi];  // visible large paths of all chunks
-      const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
-      big_path_scan<false, true>(a, pid, rec, nullptr, sh);
+      big_path_scan<true, true>(a, pid, rec, a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y), sh);
     }
   }
 }
@@ -1894,11 +1916,10 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   // flattened, unordered, chunk by chunk.
   const bool ordered = a.n_chunks == 1;
   if (a.n_seginst) {
-    if (ordered)
-      k_flatten_count<true><<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
-    else
-      k_flatten_count<false><<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
-    launches++;
+    if (ordered) {
+      k_flatten_count<<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
+      launches++;
+    }
   }
   mark(1);
   // edges: seg_edge_off (piece counts) -> exclusive offsets, total -> totals.n_edges
@@ -1934,16 +1955,16 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
       k_cover<<<dim3(per_frame + kBigBlocksPerFrame, a.n_frames), T, 0, st>>>(a, c);
       launches += 4;
     }
-    k_slot_prefix<<<grid_for((uint64_t)a.n_paths * 32) + kPrefixBigBlocks, T, 0, st>>>(a);
     k_scatter<<<wide, T, 0, st>>>(a);
-    launches += 2;
+    launches++;
   }
   mark(4);
   // candidate lists of the visible paths (for k_fine): row counts (from path setup) -> row lists -> group counts -> group lists
   scan_u32(a.row_count, a.row_off, nullptr, a.n_frames * (uint32_t)a.tiles_y, a.scan_tmp, &a.totals->n_rowent, a.caps.rows,
            &a.totals->overflow, 16u, st, launches);
+  k_alive_paths<<<(unsigned)std::min<uint32_t>(a.n_frames, kNumSM * 8), 1024, 0, st>>>(a);
   k_row_lists<<<(unsigned)std::min<uint32_t>(a.n_frames * (uint32_t)a.tiles_y, kNumSM * 8), kRowThreads, 0, st>>>(a);
-  launches++;
+  launches += 2;
   scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
            launches);
   k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);

@@ -143,7 +143,7 @@ struct swfr_renderer {
   // Two arenas: consecutive passes of a batch alternate between them and between two streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
-    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive, chunk_edge;
+    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
@@ -575,12 +575,15 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     uint32_t max_items = 0;
     for (const Pass &p : b.passes) max_items = std::max(max_items, p.n_items);
     CK(A.item_alive.reserve((size_t)max_items * 4 + 256));
+    CK(A.alive_items.reserve((size_t)max_items * 4 + 256));
   }
   CK(A.path_alive.reserve((size_t)max_paths * 4 + 256));
+  CK(A.alive_paths.reserve((size_t)max_paths * 4 + 256));
 
   {
     uint32_t max_frames = 1;
     for (const Pass &p : b.passes) max_frames = std::max(max_frames, p.n_frames);
+    CK(A.alive_count.reserve((size_t)max_frames * 4 + 256));
     CK(A.tile_cover.reserve((size_t)max_frames * r->tiles_x * r->tiles_y * 4 + 256));
     CK(A.cover_sat.reserve((size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256));
   }
@@ -690,6 +693,9 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.big_chunk = A.big_chunk.as<uint32_t>();
   a.path_item = A.path_item.as<uint32_t>();
   a.item_alive = A.item_alive.as<uint32_t>();
+  a.alive_items = A.alive_items.as<uint32_t>();
+  a.alive_paths = A.alive_paths.as<uint32_t>();
+  a.alive_count = A.alive_count.as<uint32_t>();
   a.totals = r->totals.as<Totals>() + pass_index;
   a.caps = r->caps;
   return a;
