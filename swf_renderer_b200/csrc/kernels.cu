@@ -248,6 +248,7 @@ __global__ void k_init(RenderArgs a) {
     a.totals->n_list = 0;
     a.totals->n_big = 0;
     a.totals->n_big_chunk = 0;
+    a.totals->n_small_chunk = 0;
     a.totals->n_alive_items = 0;
     a.totals->n_rowent = 0;
     a.totals->n_stage_blocks = 0;
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(1024) k_cover_sat(RenderArgs a) {
   const uint32_t frame = blockIdx.x;
   if (frame == 0 && threadIdx.x == 0) {  // the lists of the chunk about to be processed
     a.totals->n_big_chunk = 0;
+    a.totals->n_small_chunk = 0;
     a.totals->n_alive_items = 0;
   }
   const int tx = a.tiles_x, ty = a.tiles_y, sw = tx + 1;
@@ -365,8 +367,11 @@ __global__ void k_path_alive(RenderArgs a, uint32_t c) {
         // the draw items with something visible: k_flatten_emit<false> walks this list (one entry per item)
         const uint32_t it = a.path_item[pid];
         if (atomicExch(&a.item_alive[it], 1u) == 0u) a.alive_items[atomicAdd(&a.totals->n_alive_items, 1u)] = it;
-        // large tile grids are scanned by whole blocks
-        if (bw * bh > kBackdropSmall) a.big_chunk[atomicAdd(&a.totals->n_big_chunk, 1u)] = pid;
+        // the chunk's visible paths for k_cover: small tile grids are scanned by one warp each, large ones by a block
+        if (bw * bh > kBackdropSmall)
+          a.big_chunk[atomicAdd(&a.totals->n_big_chunk, 1u)] = pid;
+        else if (bw * bh > 0)
+          a.small_chunk[atomicAdd(&a.totals->n_small_chunk, 1u)] = pid;
       }
     }
     if (alive) {
@@ -1339,38 +1344,33 @@ __device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid,
   }
 }
 
-constexpr int kBigBlocksPerFrame = 16;  // blocks (per frame row of the grid) that serve the large-grid paths
+constexpr int kCoverBigBlocks = kNumSM * 8;  // blocks that serve the large-grid paths
 
 // Per depth chunk, after its binning (a path is binned in its own chunk only, so its counts are final): winding
 // numbers (backdrop prefix) of the chunk's visible paths, the tiles they cover opaquely, and the inclusive prefix of
 // their record counts -> slot_off (END of each slot's record range, relative to the path) + the path's first record
 // (alloc_records): record space is allocated path by path, so there is no global scan over the (much longer) slot
-// array.  grid = (small-path blocks + kBigBlocksPerFrame, frames).
+// array.  grid = small-path blocks + kCoverBigBlocks.
 __global__ void __launch_bounds__(256) k_cover(RenderArgs a, uint32_t c) {
   if (a.totals->overflow) return;
   __shared__ uint32_t sh[32];
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t small_blocks = gridDim.x - kBigBlocksPerFrame;
+  const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
+  const uint32_t small_blocks = gridDim.x - kCoverBigBlocks;
   if (blockIdx.x < small_blocks) {
-    const uint32_t frame = blockIdx.y;
-    const uint32_t p0 = __ldg(a.item_path_off + chunk_first(a, c, frame)), p1 = __ldg(a.item_path_off + chunk_first(a, c + 1, frame));
+    const uint32_t n_small = a.totals->n_small_chunk;  // the chunk's visible paths with small grids (k_path_alive)
     const uint32_t nwarps = (small_blocks * blockDim.x) >> 5;
-    uint32_t *cover = a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y);
-    for (uint32_t pid = p0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); pid < p1; pid += nwarps) {
-      if (!a.path_alive[pid]) continue;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_small; i += nwarps) {
+      const uint32_t pid = a.small_chunk[i];
       const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
-      const uint32_t n = (rec.y & 0xffff) * (rec.y >> 16);
-      if (n == 0 || n > (uint32_t)kBackdropSmall) continue;
-      small_path_scan<true, true>(a, pid, rec, lane, cover);
+      small_path_scan<true, true>(a, pid, rec, lane, a.tile_cover + (rec.z >> 16) * tiles);
     }
   } else {
-    const uint32_t n_big = a.totals->n_big_chunk;  // the visible large paths of this chunk (k_path_alive)
-    const uint32_t nb = kBigBlocksPerFrame * gridDim.y;
-    for (uint32_t bi = (blockIdx.x - small_blocks) * gridDim.y + blockIdx.y; bi < n_big; bi += nb) {
+    const uint32_t n_big = a.totals->n_big_chunk;  // ... with large grids
+    for (uint32_t bi = blockIdx.x - small_blocks; bi < n_big; bi += kCoverBigBlocks) {
       const uint32_t pid = a.big_chunk[bi];
       const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
-      const uint32_t frame = rec.z >> 16;
-      big_path_scan<true, true>(a, pid, rec, a.tile_cover + frame * (uint32_t)(a.tiles_x * a.tiles_y), sh);
+      big_path_scan<true, true>(a, pid, rec, a.tile_cover + (rec.z >> 16) * tiles, sh);
     }
   }
 }
@@ -1952,7 +1952,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
         k_flatten_emit<false><<<g2, kEmitWarps * 32, 0, st>>>(a, c);
         k_bin<false><<<wide, kBinWarps * 32, 0, st>>>(a, c);
       }
-      k_cover<<<dim3(per_frame + kBigBlocksPerFrame, a.n_frames), T, 0, st>>>(a, c);
+      k_cover<<<wide + kCoverBigBlocks, T, 0, st>>>(a, c);
       launches += 4;
     }
     k_scatter<<<wide, T, 0, st>>>(a);

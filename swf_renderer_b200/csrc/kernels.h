@@ -72,13 +72,13 @@ struct Totals {
   uint32_t n_list;    // candidate-list entries
   uint32_t n_big;     // visible path instances whose tile grid is larger than kBackdropSmall
   uint32_t n_big_chunk;  // visible path instances with large tile grids in the depth chunk being processed
+  uint32_t n_small_chunk;  // ... with small tile grids
   uint32_t n_alive_items;  // draw items with a visible path in the depth chunk being processed
   uint32_t n_rowent;  // row-list entries
   uint32_t n_stage_blocks;  // staging blocks handed out by the binning pass
   uint32_t overflow_stage;  // the staging buffer was too small (found while binning, after the scans)
   uint32_t fine_hits;       // (path, tile) slots composited by k_fine
   uint32_t fine_records;    // records read by k_fine (the rest of n_records was binned but hidden)
-  uint32_t pad[1];
 };
 
 struct Caps {
@@ -136,6 +136,7 @@ struct RenderArgs {
   uint2 *row_items;            // caps.rows: (path instance, bx0 | bw << 16) per row, in paint order
   uint32_t *big_list;          // n_paths: visible path instances with large tile grids
   uint32_t *big_chunk;         // n_paths: ... of the depth chunk being processed
+  uint32_t *small_chunk;       // n_paths: visible path instances with small tile grids of the depth chunk being processed
   uint32_t *path_item;         // n_paths: draw item of each path instance
   uint32_t *item_alive;        // n_items: 1 when any path instance of the draw item is visible
   uint32_t *alive_items;       // n_items: those draw items, listed per depth chunk
