@@ -222,6 +222,33 @@ def run_reference(a):
 # ----------------------------------------------------------------------------------------------------------
 
 
+def pin_to_gpu_numa_node(local):
+    """One process per GPU: keep the rank's threads and its pinned host buffers (first-touch) on the NUMA node the
+    GPU's PCIe lanes hang off, so that the ranks' device->host traffic does not all cross one socket.  Best effort:
+    returns a short description, or None when sysfs gives no answer."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        mine = cpus & set(os.sched_getaffinity(0))
+        if not mine or mine == set(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, mine)
+        return "gpu %s -> cpus %s" % (bdf, txt)
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -238,6 +265,7 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
@@ -249,7 +277,8 @@ def run_ours(a):
         r.set_option(capi.OPT_OCCLUSION_CHUNKS, a.occlusion_chunks)
     # stage-flattening threads: the box's cores are shared by the ranks of the node
     cores = max(1, len(os.sched_getaffinity(0)))
-    r.set_option(capi.OPT_HOST_THREADS, max(1, min(8, cores // max(world, 1))))
+    ranks_sharing = max(world, 1) if numa is None else max(1, (world + 1) // 2)  # ranks on this rank's cores
+    r.set_option(capi.OPT_HOST_THREADS, max(1, min(8, cores // ranks_sharing)))
 
     # ---- inputs: textures, definitions, stages (host arrays) ----
     for i, t in enumerate(synth.textures()):
@@ -465,6 +494,7 @@ def run_ours(a):
                 "mode": "streaming: render_batch(host stages) + read_frames_async(pinned) per step, 2 output buffers, "
                         "sync at the end",
                 "ms_per_step_sync_every_step": e2e_serial_ms,
+                "numa": numa,
                 "checksum": checksum,
             },
             "gpu_launches": launches,
