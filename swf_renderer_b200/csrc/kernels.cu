@@ -246,7 +246,6 @@ __global__ void k_init(RenderArgs a) {
     a.totals->error = 0;
     for (int k = 0; k < kMaxFineSlices; k++) a.totals->work[k] = 0;
     a.totals->n_list = 0;
-    a.totals->n_big = 0;
     a.totals->n_big_chunk = 0;
     a.totals->n_small_chunk = 0;
     a.totals->n_alive_items = 0;

@@ -70,7 +70,6 @@ struct Totals {
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work[kMaxFineSlices];  // fine-kernel tile queues, one per slice of frames
   uint32_t n_list;    // candidate-list entries
-  uint32_t n_big;     // visible path instances whose tile grid is larger than kBackdropSmall
   uint32_t n_big_chunk;  // visible path instances with large tile grids in the depth chunk being processed
   uint32_t n_small_chunk;  // ... with small tile grids
   uint32_t n_alive_items;  // draw items with a visible path in the depth chunk being processed
@@ -134,7 +133,6 @@ struct RenderArgs {
   uint32_t *row_count;         // n_frames * tiles_y: path instances whose bbox covers the tile row
   uint32_t *row_off;           // n_frames * tiles_y + 1
   uint2 *row_items;            // caps.rows: (path instance, bx0 | bw << 16) per row, in paint order
-  uint32_t *big_list;          // n_paths: visible path instances with large tile grids
   uint32_t *big_chunk;         // n_paths: ... of the depth chunk being processed
   uint32_t *small_chunk;       // n_paths: visible path instances with small tile grids of the depth chunk being processed
   uint32_t *path_item;         // n_paths: draw item of each path instance

@@ -143,7 +143,7 @@ struct swfr_renderer {
   // Two arenas: consecutive passes of a batch alternate between them and between two streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
-    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, big_list, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
+    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
@@ -568,7 +568,6 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   CK(A.paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
   CK(A.path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
   CK(A.path_rec_base.reserve(((size_t)max_paths + 1) * 4 + 256));
-  CK(A.big_list.reserve((size_t)max_paths * 4 + 256));
   CK(A.big_chunk.reserve((size_t)max_paths * 4 + 256));
   CK(A.small_chunk.reserve((size_t)max_paths * 4 + 256));
   CK(A.path_item.reserve((size_t)max_paths * 4 + 256));
@@ -690,7 +689,6 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.row_off = A.row_off.as<uint32_t>();
   a.row_items = A.row_items.as<uint2>();
   a.list_items = A.list_items.as<uint32_t>();
-  a.big_list = A.big_list.as<uint32_t>();
   a.big_chunk = A.big_chunk.as<uint32_t>();
   a.small_chunk = A.small_chunk.as<uint32_t>();
   a.path_item = A.path_item.as<uint32_t>();
