@@ -327,3 +327,23 @@ def test_hostile_placements_bit_exact(built_library, seed):
     r.render(stages[0])
     np.testing.assert_array_equal(r.get_image(premultiplied=True).data, ref)
     r.close()
+
+
+@pytest.mark.parametrize("frame_index,n_shapes,w,h,rs", [(31, 3000, 1920, 1080, 1.0), (32, 1500, 3840, 2160, 2.0)])
+def test_automatic_culling_at_full_resolution_matches_oracle(built_library, frame_index, n_shapes, w, h, rs):
+    """Frames of 1024 or more items switch occlusion culling on by themselves (4 depth chunks, unordered edges, only
+    visible geometry flattened): the pixels at 1080p and at 4K must still be the oracle's."""
+    from swf_renderer_b200.renderer import SwfrError
+
+    sc = _scene(frame_index, n_shapes, w, h, rs)
+    ref = corpus.render_oracle(sc)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    st = r.stats()
+    with pytest.raises(SwfrError):  # culling was on: the taps refuse
+        r.debug_tile_counts(0)
+    r.close()
+    bad = (out != ref).any(axis=2)
+    assert not bad.any(), "%d px differ, first %s" % (bad.sum(), np.argwhere(bad)[:5].tolist())
+    assert st["fine_records"] <= st["n_records"] and st["n_edges"] > 0
