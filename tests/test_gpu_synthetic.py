@@ -347,3 +347,26 @@ def test_automatic_culling_at_full_resolution_matches_oracle(built_library, fram
     bad = (out != ref).any(axis=2)
     assert not bad.any(), "%d px differ, first %s" % (bad.sum(), np.argwhere(bad)[:5].tolist())
     assert st["fine_records"] <= st["n_records"] and st["n_edges"] > 0
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (17, 3), (333, 77), (15, 16), (16, 15), (130, 1)])
+def test_odd_viewport_sizes(built_library, w, h):
+    """Viewports that are not multiples of the 16 px tile or of the 4-pixel store width (partial tiles, scalar
+    stores), down to a single pixel."""
+    from swf_renderer_b200 import capi
+
+    sc = _scene(40 + w, 60, w, h, 0.3)
+    ref, info = corpus.render_oracle(sc, want_debug=True)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    np.testing.assert_array_equal(r.debug_tile_counts(0), info["tile_counts"])
+    assert out.shape == ref.shape == (h, w, 4)
+    np.testing.assert_array_equal(out, ref)
+    r.set_option(capi.OPT_OCCLUSION_CHUNKS, 2)
+    r.render_batch([stages[0], stages[0], stages[0]])
+    for f in range(3):
+        np.testing.assert_array_equal(r.get_image(frame=f, premultiplied=True).data, ref)
+    straight = r.get_image(frame=1).data  # un-premultiplied read-back with a row stride of 4 * w
+    assert straight.shape == (h, w, 4) and (straight[..., 3] == ref[..., 3]).all()
+    r.close()
