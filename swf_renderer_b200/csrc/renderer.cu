@@ -340,13 +340,18 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     return (pr.flags & SWFR_PRIM_RATIO_F32) ? (double)pr.ratio_f : (double)pr.ratio / 65535.0;
   };
   auto run = [&](auto &&fn) {
-    if (nt == 1) {
-      fn(0u);
-      return;
-    }
+    // frames t, t + nt, ... go to worker t; if the process cannot start a thread, the caller does that share itself
+    // (no exception may cross the C ABI)
     std::vector<std::thread> th;
-    for (uint32_t t = 1; t < nt; t++) th.emplace_back(fn, t);
-    fn(0u);
+    std::vector<uint32_t> mine{0u};
+    for (uint32_t t = 1; t < nt; t++) {
+      try {
+        th.emplace_back(fn, t);
+      } catch (...) {
+        mine.push_back(t);
+      }
+    }
+    for (uint32_t t : mine) fn(t);
     for (std::thread &x : th) x.join();
   };
   run([&](uint32_t t) {
