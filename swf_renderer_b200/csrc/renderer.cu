@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <new>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -197,6 +199,20 @@ namespace {
 int fail(swfr_renderer *r, int code, const std::string &msg) {
   if (r) r->last_error = msg;
   return code;
+}
+
+// No C++ exception may cross the C ABI: host allocations and the shape compiler run inside this guard.
+template <class F>
+int guarded(swfr_renderer *r, F &&f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    return fail(r, SWFR_ERR_OOM, "host allocation failed");
+  } catch (const std::exception &e) {
+    return fail(r, SWFR_ERR_INVALID_ARGUMENT, e.what());
+  } catch (...) {
+    return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unexpected exception");
+  }
 }
 
 #define CK(call)                                                                                        \
@@ -1019,10 +1035,10 @@ int swfr_set_option(swfr_renderer *r, uint32_t key, uint64_t value) {
 }
 
 int swfr_register_shape(swfr_renderer *r, const swfr_define_shape *tag, uint32_t *out_id) {
-  return register_def(r, tag, false, out_id);
+  return guarded(r, [&] { return register_def(r, tag, false, out_id); });
 }
 int swfr_register_morph_shape(swfr_renderer *r, const swfr_define_shape *tag, uint32_t *out_id) {
-  return register_def(r, tag, true, out_id);
+  return guarded(r, [&] { return register_def(r, tag, true, out_id); });
 }
 
 namespace {
@@ -1134,15 +1150,17 @@ int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n) {
   // scratch batch the previous render does not use, and only then settle the previous render.
   r->scratch_ix ^= 1;
   swfr_batch &b = r->scratch_batch[r->scratch_ix];
-  if (r->last == &b) {  // only when finish() kept an older scratch alive: settle first
-    int rc0 = finish(r);
-    if (rc0 != SWFR_OK) return rc0;
-  }
-  int rc = build_batch(r, stages, n, b);
-  if (rc != SWFR_OK) return rc;
-  rc = upload_batch(r, b);
-  if (rc != SWFR_OK) return rc;
-  return launch_batch(r, b);
+  return guarded(r, [&]() -> int {
+    if (r->last == &b) {  // only when finish() kept an older scratch alive: settle first
+      int rc0 = finish(r);
+      if (rc0 != SWFR_OK) return rc0;
+    }
+    int rc = build_batch(r, stages, n, b);
+    if (rc != SWFR_OK) return rc;
+    rc = upload_batch(r, b);
+    if (rc != SWFR_OK) return rc;
+    return launch_batch(r, b);
+  });
 }
 
 int swfr_render(swfr_renderer *r, const swfr_stage *stage) { return swfr_render_batch(r, stage, 1); }
