@@ -666,6 +666,12 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
         dbg->n_edges += (int64_t)ne;
       }
       if (ne == 0) continue;
+      /* ---- paint ---- */
+      paint_inst paint;
+      make_paint(sc, &sc->paints[def->first_path + lp], m0, ratio, &paint);
+      /* A path whose paint cannot be evaluated, or whose solid colour is premultiplied 0 (alpha 0: over() returns the
+       * destination unchanged), composites nothing: it is flattened (the edge tap above lists it) but not binned. */
+      if (!paint.valid || (paint.type == SWFO_PAINT_SOLID && paint.solid == 0)) continue;
       /* ---- tile grid over the bbox ---- */
       grid_t g;
       int32_t bx0 = minx >> 12, bx1 = maxx >> 12, by0 = miny >> 12, by1 = maxy >> 12;
@@ -694,10 +700,7 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
       }
       for (int32_t ly = 0; ly < g.bh; ly++) /* prefix sum of backdrop deltas along each tile row */
         for (int32_t lx = 1; lx < g.bw; lx++) g.backdrop[ly * g.bw + lx] += g.backdrop[ly * g.bw + lx - 1];
-      /* ---- paint ---- */
-      paint_inst paint;
-      make_paint(sc, &sc->paints[def->first_path + lp], m0, ratio, &paint);
-      if (paint.valid) {
+      {
         for (int32_t ly = 0; ly < g.bh; ly++) {
           for (int32_t lx = 0; lx < g.bw; lx++) {
             int32_t slot = ly * g.bw + lx;
