@@ -1685,7 +1685,9 @@ __device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
+// Four resident blocks per SM (64 registers per thread): measured best - 3 blocks at 80 registers 0.75 ms per launch,
+// 4 at 64 0.54, 5 at 48 and 6 at 40 0.56 (1080p / 10 k shapes, 16 frames per launch).
+__global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
   if (a.totals->overflow | a.totals->overflow_stage) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
@@ -1698,7 +1700,10 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a, uint32_t
   const int row = lane & 15, half = lane >> 4;
   const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
   const uint32_t total = tiles * (frame_end - frame_begin);  // this launch composites frames [frame_begin, frame_end)
-  while (true) {
+  // (a warp leaves through the break below; the bound only states that no warp can take more than `total` tiles.  With
+  // a counted loop ptxas fits the kernel in 64 registers without a single spill; with `while (true)` it spills 92 bytes
+  // into the tile loop and a launch takes 0.61 instead of 0.54 ms)
+  for (uint32_t taken = 0; taken < total; taken++) {
     uint32_t w = 0;
     if (lane == 0) w = atomicAdd(&a.totals->work[slice], 1u);
     w = __shfl_sync(0xffffffffu, w, 0);
@@ -1774,10 +1779,23 @@ __global__ void __launch_bounds__(kFineWarps * 32) k_fine(RenderArgs a, uint32_t
           for (int i = 0; i < 8; i++)
             if (m[i]) px[i] = over_masked(px[i], color, m[i]);
         } else {
+          // One copy of the paint code, eight trips.  px[] and the masks are only ever indexed statically (the pixels
+          // rotate through px[0], the masks are packed into two words), so both stay in registers: a dynamic index
+          // would put them in local memory for the whole kernel.
           const PaintInst &pi = a.paint_inst[cur_pid];
+          uint32_t mlo = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+          uint32_t mhi = m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
 #pragma unroll 1
-          for (int i = 0; i < 8; i++)
-            if (m[i]) px[i] = over_masked(px[i], eval_paint(type, pi, X0 + i, Y), m[i]);
+          for (int i = 0; i < 8; i++) {
+            const uint32_t mm = mlo & 255u;
+            uint32_t v = px[0];
+            if (mm) v = over_masked(v, eval_paint(type, pi, X0 + i, Y), mm);
+#pragma unroll
+            for (int k = 0; k < 7; k++) px[k] = px[k + 1];
+            px[7] = v;
+            mlo = __funnelshift_r(mlo, mhi, 8);
+            mhi >>= 8;
+          }
         }
       }
     }
