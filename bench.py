@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--frames-per-pass", type=int, default=0, help="0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--occlusion-chunks", type=int, default=0, help="0 = library default (automatic)")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1 only: also time the optional gather of the ranks' finished frames onto rank 0, GPU to GPU "
+                         "(NCCL over NVLink; SURVEY 8e - off the hot path, reported as its own object)")
     ap.add_argument("--uhd-frames", type=int, default=16,
                     help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
     return ap.parse_args()
@@ -423,6 +426,35 @@ def run_ours(a):
         r.sync()
     e2e_serial_ms = (time.perf_counter() - t0) / n_serial * 1e3
 
+    # ---- optional: gather the finished frames of all ranks onto rank 0, device to device (not part of `value` / `e2e`) ----
+    gather = None
+    if a.gather and world > 1:
+        try:
+            from swf_renderer_b200 import sharding
+
+            r.sync()
+            local_frames = r.device_frames()
+            n_global = world * int(local_frames.shape[0])
+            for _ in range(2):
+                sharding.gather_frames(local_frames, n_global, dst=0)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_g = 5
+            g0.record()
+            for _ in range(n_g):
+                out = sharding.gather_frames(local_frames, n_global, dst=0)
+            g1.record()
+            barrier()
+            gms = max_over_ranks(g0.elapsed_time(g1)) / n_g
+            moved = (world - 1) * local_frames.numel()
+            gather = {"ms": gms, "bytes_into_rank0": moved, "GB/s": moved / (gms / 1e3) / 1e9, "frames": n_global,
+                      "how": "torch.distributed.gather (NCCL) of the renderers' frame stores + interleave into frame order on rank 0"}
+            if rank == 0:
+                gather["first_frame_matches_rank0"] = bool(torch.equal(out[0], local_frames[0]))
+            del out
+        except Exception as e:  # the optional line must never cost the bench line
+            gather = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- secondary: the same stream at 3840x2160 (BASELINE metric "at 1080p/4K"), device-resident stages ----
     uhd = None
     if a.uhd_frames > 0:
@@ -504,6 +536,8 @@ def run_ours(a):
         }
         if uhd is not None:
             line["uhd"] = uhd
+        if gather is not None:
+            line["gather"] = gather
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(a)
         print(json.dumps(line), flush=True)

@@ -108,6 +108,7 @@ class HeadlessRenderer:
         self._lib = capi.load()
         self._h = C.c_void_p()
         self.width, self.height = int(width), int(height)
+        self.device = int(device)
         if cuda_stream is None:
             rc = self._lib.swfr_create(device, self.width, self.height, C.byref(self._h))
         else:
@@ -186,6 +187,23 @@ class HeadlessRenderer:
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         self._check(self._lib.swfr_read_image(self._h, frame, out.ctypes.data, self.width * 4, 1 if premultiplied else 0))
         return Image(ImageMetadata(self.width, self.height, self.width * 4), out)
+
+    def device_frames(self):
+        """The finished frames of the last render where they lie in HBM, as a torch uint8 tensor
+        [frames, height, width, 4] (premultiplied RGBA8, no copy; valid until the next render).  For callers that keep
+        the pixels on the GPU or move them between GPUs (`sharding.gather_frames`); call sync() first."""
+        import torch
+
+        ptr, n = C.c_void_p(), C.c_uint32()
+        self._check(self._lib.swfr_device_frames(self._h, C.byref(ptr), C.byref(n)))
+        shape = (int(n.value), self.height, self.width, 4)
+
+        class _Frames:  # minimal CUDA array interface holder
+            __cuda_array_interface__ = {"shape": shape, "typestr": "|u1", "data": (int(ptr.value or 0), False), "version": 2}
+
+        if n.value == 0 or not ptr.value:
+            return torch.empty((0, self.height, self.width, 4), dtype=torch.uint8, device="cuda:%d" % self.device)
+        return torch.as_tensor(_Frames(), device="cuda:%d" % self.device)
 
     def stats(self) -> dict:
         st = capi.Stats()

@@ -28,6 +28,40 @@ def gather_order(n_frames: int, world: int) -> List[Tuple[int, int]]:
     return [owner_of_frame(f, world) for f in range(n_frames)]
 
 
+def gather_frames(local_frames, n_frames: int, dst: int = 0, group=None):
+    """Optional gather of finished frames onto rank ``dst`` (off the hot path, its own line in the bench).
+
+    ``local_frames``: this rank's frames as a tensor [n_local, H, W, 4] in local-slot order - on the GPU the
+    renderer's own frame store (`HeadlessRenderer.device_frames()`, no copy), so with the NCCL backend the pixels travel
+    GPU to GPU over NVLink / NVSwitch; on CPU (gloo) a host tensor.  ``n_frames`` is the global frame count.  Returns
+    [n_frames, H, W, 4] in global frame order on ``dst`` and None elsewhere.  Frame f sits on rank f mod world in slot
+    f div world, so the ranks' tensors interleave; ranks with one frame fewer are padded for the collective."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        if local_frames.shape[0] != n_frames:
+            raise ValueError("rank holds %d frames, expected %d" % (local_frames.shape[0], n_frames))
+        return local_frames
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = len(range(rank, n_frames, world))
+    if local_frames.shape[0] != mine:
+        raise ValueError("rank %d holds %d frames, expected %d" % (rank, local_frames.shape[0], mine))
+    slots = (n_frames + world - 1) // world
+    send = local_frames
+    if mine < slots:  # pad to the common slot count
+        pad = torch.zeros((slots - mine,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=local_frames.device)
+        send = torch.cat([local_frames, pad], dim=0)
+    send = send.contiguous()
+    parts = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    # parts[r][s] is global frame s * world + r: stack along a new rank axis and flatten (slot, rank) -> frame
+    out = torch.stack(parts, dim=1).reshape((slots * world,) + tuple(send.shape[1:]))
+    return out[:n_frames]
+
+
 def reduce_max_time(ms: float, group=None) -> float:
     """MAX over ranks of a device time, as the benchmark contract requires (never a wall clock)."""
     import torch

@@ -72,3 +72,50 @@ def test_two_rank_gloo_sharded_sweep(tmp_path):
     assert sorted(got) == list(range(6))
     for f in range(6):
         assert got[f] == int(corpus.render_oracle(sc, frame=f).astype(np.int64).sum())
+
+
+def _gather_worker(rank, world, port, out_dir, n_frames):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from swf_renderer_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.frames_of_rank(n_frames, rank, world)
+    # frame f is filled with the value f (3 x 5 "pixels")
+    local = torch.stack([torch.full((3, 5, 4), f, dtype=torch.uint8) for f in mine]) if mine else torch.zeros((0, 3, 5, 4), dtype=torch.uint8)
+    out = sharding.gather_frames(local, n_frames, dst=0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), out.numpy())
+    else:
+        assert out is None
+    if rank == 1:  # a rank that holds the wrong number of frames is an error, not a silent misplacement
+        wrong = torch.zeros((len(mine) + 1, 3, 5, 4), dtype=torch.uint8)
+        with pytest.raises(ValueError):
+            sharding.gather_frames(wrong, n_frames, dst=0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [6, 7, 1])
+def test_two_rank_gloo_frame_gather_restores_frame_order(tmp_path, n_frames):
+    world, port = 2, _free_port()
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path), n_frames), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "gathered.npy"))
+    assert got.shape == (n_frames, 3, 5, 4)
+    for f in range(n_frames):
+        assert (got[f] == f).all()
+
+
+def test_frame_gather_single_process_is_the_identity():
+    import torch
+
+    from swf_renderer_b200 import sharding
+
+    x = torch.arange(2 * 3 * 5 * 4, dtype=torch.uint8).reshape(2, 3, 5, 4)
+    assert sharding.gather_frames(x, 2) is x
+    with pytest.raises(ValueError):
+        sharding.gather_frames(x, 3)
