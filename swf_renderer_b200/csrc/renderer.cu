@@ -1138,7 +1138,7 @@ int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t
   if (rc != SWFR_OK) return rc;
   if (w) *w = ww;
   if (h) *h = hh;
-  if (rgba && cap >= out.size()) memcpy(rgba, out.data(), out.size());
+  if (rgba && !out.empty() && cap >= out.size()) memcpy(rgba, out.data(), out.size());
   return SWFR_OK;
 }
 
