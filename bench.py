@@ -156,9 +156,9 @@ def cpu_baseline_single(a):
 
     _, sc = _oracle_scene(0, a)
     t = time.perf_counter()
-    raster.render_scene(sc)
+    pixels = raster.render_scene(sc)
     dt = time.perf_counter() - t
-    return {
+    return pixels, {
         "value": a.width * a.height / dt / 1e6,
         "unit": UNIT,
         "cores": 1,
@@ -339,6 +339,8 @@ def run_ours(a):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = r.stats()["kernel_launches"] * a.steps
+    # frame 0 of the batch the timed loop just rendered (compared with the oracle's frame 0 below: `parity`)
+    timed_frame0 = r.get_image(frame=0, premultiplied=True).data.copy() if rank == 0 else None
     value = world * px_per_step * a.steps / (ms / 1e3) / 1e6
 
     # ---- roofline of the dominant kernel, CUDA events on the launching stream (separate pass) ----
@@ -417,6 +419,7 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end to end)
     e2e_value = world * px_per_step * a.steps / e2e_s / 1e6
     checksum = int(host_out[(a.steps - 1) & 1][:: 4096].to(torch.int64).sum().item())
+    e2e_frame0 = host_out[(a.steps - 1) & 1][: a.width * a.height * 4].numpy().reshape(a.height, a.width, 4).copy()
     # the same call sequence without overlap between steps (sync after every step), for reference
     t0 = time.perf_counter()
     n_serial = min(a.steps, 5)
@@ -538,9 +541,20 @@ def run_ours(a):
             line["uhd"] = uhd
         if gather is not None:
             line["gather"] = gather
+        parity_ok = True
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_single(a)
+            # the oracle renders frame 0 of the same stream for the CPU baseline; its pixels check frame 0 of the timed
+            # device-resident batch and frame 0 of the end-to-end host buffer, bit for bit
+            want, line["cpu_baseline"] = cpu_baseline_single(a)
+            d_timed = int((timed_frame0 != want).any(axis=2).sum())
+            d_e2e = int((e2e_frame0 != want).any(axis=2).sum())
+            parity_ok = d_timed == 0 and d_e2e == 0
+            line["parity"] = {"frame0_equal": parity_ok, "px_diff": d_timed, "px_diff_e2e": d_e2e,
+                              "against": "oracle/raster.c, frame 0 of the timed batch and of the e2e host buffer, "
+                                         "premultiplied RGBA8, bit-exact"}
         print(json.dumps(line), flush=True)
+        if not parity_ok:
+            raise SystemExit("bench.py: the timed configuration differs from the oracle (see `parity` in the line)")
     if batch is not None:
         batch.close()
     r.close()

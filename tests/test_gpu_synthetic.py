@@ -370,3 +370,72 @@ def test_odd_viewport_sizes(built_library, w, h):
     straight = r.get_image(frame=1).data  # un-premultiplied read-back with a row stride of 4 * w
     assert straight.shape == (h, w, 4) and (straight[..., 3] == ref[..., 3]).all()
     r.close()
+
+
+def _oracle_frame(frame_index, n_shapes, w, h, rs=1.0):
+    """The oracle's picture of one frame of the synthetic stream (the construction bench.py's cpu_baseline uses)."""
+    from oracle import compile_shape as cs
+    from oracle import raster
+
+    fr = synth.SynthFrame(frame_index, n_shapes, w, h, rs)
+    b = raster._Builder({i: t for i, t in enumerate(synth.textures())})
+    for i in range(fr.n):
+        b.add_item(raster.add_shape_def(b, cs.compile_shape(fr.ast(i))), fr.matrix(i))
+    return raster.render_scene(b.scene(w, h))
+
+
+@pytest.mark.parametrize(
+    "w,h,rs,n_frames,fpp,check",
+    [
+        # bench.py's headline configuration: 10 000 shapes per frame at 1080p, ONE batch, library defaults (4 depth
+        # chunks, 16 frames per pass, passes alternating over two arenas / streams); one frame of passes 0, 1 and 2
+        (1920, 1080, 1.0, 33, 0, (0, 17, 32)),
+        # bench.py's 4K line: radii x2, 8 frames per pass; one frame of passes 0 and 1
+        (3840, 2160, 2.0, 9, 8, (3, 8)),
+    ],
+)
+def test_benchmarked_configuration_matches_oracle(built_library, w, h, rs, n_frames, fpp, check):
+    """The configuration bench.py times (BASELINE configs[4]), pixel for pixel against the oracle: multi-pass batch of
+    10 000-shape frames through create_batch / render (device-resident stages, `value`) AND through
+    render_stage_array + read_frames_async into pinned host memory (`e2e`)."""
+    import torch
+
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import stage_array_from_numpy, stages_from_prims
+
+    N = 10000
+    r = sw.HeadlessRenderer(w, h)
+    r.set_option(capi.OPT_RETAIN_COMPILED, 0)
+    if fpp:
+        r.set_option(capi.OPT_FRAMES_PER_PASS, fpp)
+    for j, t in enumerate(synth.textures()):
+        r.register_bitmap(j, t)
+    prims = []
+    for f in range(n_frames):
+        fr = synth.SynthFrame(f, N, w, h, rs)
+        prims.append(stage_array_from_numpy(fr.register(r), fr.matrices()))
+    arr, keep = stages_from_prims(prims)
+    batch = r.create_batch((arr, keep))
+    batch.render()
+    batch.render()  # the second render reuses the arenas the first one sized
+    st = r.stats()
+    assert st["retries"] == 0 and st["n_primitives"] == N * n_frames
+    want = {f: _oracle_frame(f, N, w, h, rs) for f in check}
+    for f in check:
+        out = r.get_image(frame=f, premultiplied=True).data
+        bad = (out != want[f]).any(axis=2)
+        assert not bad.any(), "resident batch, frame %d: %d px differ, first %s" % (f, bad.sum(), np.argwhere(bad)[:5].tolist())
+    batch.close()
+    # the end-to-end path: host stage arrays in, frames out to pinned host memory, two renders in flight
+    fb = w * h * 4
+    host = [torch.zeros(n_frames * fb, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    for i in range(2):
+        r.render_stage_array(arr, n_frames)
+        r.read_frames_async(0, n_frames, host[i].data_ptr())
+    r.sync()
+    for i in range(2):
+        frames = host[i].numpy().reshape(n_frames, h, w, 4)
+        for f in check:
+            assert np.array_equal(frames[f], want[f]), "streamed render %d, frame %d differs from the oracle" % (i, f)
+    r.close()
