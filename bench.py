@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--gather", action="store_true",
                     help="N > 1 only: also time the optional gather of the ranks' finished frames onto rank 0, GPU to GPU "
                          "(NCCL over NVLink; SURVEY 8e - off the hot path, reported as its own object)")
+    ap.add_argument("--quick", action="store_true", help="experiments: skip the sync-every-step leg of e2e")
     ap.add_argument("--uhd-frames", type=int, default=16,
                     help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
     return ap.parse_args()
@@ -338,7 +339,8 @@ def run_ours(a):
     r.sync()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = r.stats()["kernel_launches"] * a.steps
+    launches_per_render = r.stats()["kernel_launches"]
+    launches = launches_per_render * a.steps
     # frame 0 of the batch the timed loop just rendered (compared with the oracle's frame 0 below: `parity`)
     timed_frame0 = r.get_image(frame=0, premultiplied=True).data.copy() if rank == 0 else None
     value = world * px_per_step * a.steps / (ms / 1e3) / 1e6
@@ -422,12 +424,12 @@ def run_ours(a):
     e2e_frame0 = host_out[(a.steps - 1) & 1][: a.width * a.height * 4].numpy().reshape(a.height, a.width, 4).copy()
     # the same call sequence without overlap between steps (sync after every step), for reference
     t0 = time.perf_counter()
-    n_serial = min(a.steps, 5)
+    n_serial = 0 if a.quick else min(a.steps, 5)
     for i in range(n_serial):
         r.render_stage_array(stage_arr, a.frames)
         r.read_frames_async(0, a.frames, host_out[i & 1].data_ptr())
         r.sync()
-    e2e_serial_ms = (time.perf_counter() - t0) / n_serial * 1e3
+    e2e_serial_ms = (time.perf_counter() - t0) / max(n_serial, 1) * 1e3 if n_serial else None
 
     # ---- optional: gather the finished frames of all ranks onto rank 0, device to device (not part of `value` / `e2e`) ----
     gather = None
@@ -533,6 +535,7 @@ def run_ours(a):
                 "checksum": checksum,
             },
             "gpu_launches": launches,
+            "launches_per_render": launches_per_render,
             "roofline": roofline,
             "per_step": {k: stats[k] for k in ("n_primitives", "n_segments", "n_edges", "n_slots", "n_records", "fine_slots",
                                                 "fine_records", "retries")},

@@ -111,7 +111,12 @@ extern "C" {
 int swfr_flatten_display_stage(const swfr_display_stage *stage, swfr_display_primitive *out, uint32_t cap, uint32_t *n) {
   if (!stage || !n) return SWFR_ERR_INVALID_ARGUMENT;
   uint32_t count = 0;
-  int rc = walk(stage->children, stage->n_children, Affine{}, 0, out, cap, count);
+  int rc;
+  try {
+    rc = walk(stage->children, stage->n_children, Affine{}, 0, out, cap, count);
+  } catch (...) {
+    rc = SWFR_ERR_OOM;
+  }
   *n = count;
   return rc;
 }
@@ -132,6 +137,7 @@ int swfr_write_pam(const uint8_t *rgba, uint32_t width, uint32_t height, size_t 
 int swfr_write_png(const uint8_t *rgba, uint32_t width, uint32_t height, size_t stride, uint8_t *out, uint64_t cap,
                    uint64_t *n) {
   if (!rgba || !n || width == 0 || height == 0 || stride < (size_t)width * 4) return SWFR_ERR_INVALID_ARGUMENT;
+  try {  // no exception may cross the C ABI
   // 8-bit RGBA, non-interlaced, filter type 0 on every row, one IDAT
   std::vector<uint8_t> raw((size_t)height * ((size_t)width * 4 + 1));
   for (uint32_t y = 0; y < height; y++) {
@@ -157,6 +163,9 @@ int swfr_write_png(const uint8_t *rgba, uint32_t width, uint32_t height, size_t 
   if (!out || cap < png.size()) return out ? SWFR_ERR_INVALID_ARGUMENT : SWFR_OK;
   memcpy(out, png.data(), png.size());
   return SWFR_OK;
+  } catch (...) {
+    return SWFR_ERR_OOM;
+  }
 }
 
 }  // extern "C"

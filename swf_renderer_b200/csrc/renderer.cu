@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <new>
 #include <exception>
@@ -142,32 +143,57 @@ struct swfr_renderer {
   std::vector<BitmapDev> h_bitmaps;
 
   // ---- working memory ----
-  // Two arenas: consecutive passes of a batch alternate between them and between two streams, so that the many
+  // Arenas: consecutive passes of a batch alternate between them and between the pass streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
     DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
-  int n_arenas = 2;                         // arenas (and streams) in use: pass i runs in arena / on stream i % n_arenas
-  cudaStream_t extra_stream[kArenas - 1] = {nullptr, nullptr, nullptr};  // streams 1 .. n_arenas - 1 (stream 0 is `stream`)
-  cudaEvent_t fork_ev = nullptr, join_ev[kArenas - 1] = {nullptr, nullptr, nullptr};
-  DevBuf frames, totals, scratch, scratch2;
+  int n_arenas = 2;                         // arenas (and pass streams) in use: pass i runs in arena / on pass stream i % n_arenas
+  // Passes never run on `stream` itself: pass i of every render goes to pass_stream[i % n_arenas] (so the passes of
+  // consecutive renders that share an arena are ordered by their stream, and nothing else orders them: render k + 1
+  // starts while the last passes of render k are still running), and `stream` only waits for the render's last
+  // kernels (join), so that whatever the caller enqueues on it afterwards sees finished frames.
+  cudaStream_t pass_stream[kArenas] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t join_ev[kArenas] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t render_done = nullptr;  // recorded on `stream` after the join of the newest render
+  // pass layout of the newest render: a render with a different layout writes frame ranges on other streams than its
+  // predecessor did, and then waits for the predecessor as a whole
+  uint32_t layout_frames = 0, layout_fpp = 0;
+  DevBuf frames, scratch, scratch2;
   Caps caps{0, 0, 0, 0, 0, 0};
-  PinnedBuf pin_totals;
-  swfr_batch scratch_batch[2];  // swfr_render / swfr_render_batch alternate, so that the stages of render k + 1 are
-  int scratch_ix = 0;           // flattened and uploaded while render k is still on the GPU
+  // Renders in flight.  A render is *settled* (its device counters read back: overflow of the working memory ->
+  // grow and re-run, errors, statistics) lazily: when a later render needs the host to catch up, at swfr_sync, or
+  // before anything reads its results synchronously - never between two renders that are enqueued back to back.
+  static constexpr int kSlots = 3;  // counter blocks / scratch batches: at most two renders are in flight
+  struct CopyReq {
+    uint32_t first, count;
+    uint8_t *dst;
+  };
+  struct InFlight {
+    swfr_batch *b = nullptr;
+    int slot = 0;           // totals[slot] / pin_totals[slot]
+    uint32_t launches = 0;
+    std::vector<CopyReq> copy_reqs;  // swfr_read_frames_async requests (re-issued if the render has to be re-run)
+  };
+  std::deque<InFlight> inflight;  // oldest first
+  DevBuf totals[kSlots];
+  PinnedBuf pin_totals[kSlots];
+  cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};  // recorded on `stream` after the counters' D2H copy
+  int next_slot = 0;
+  swfr_batch scratch_batch[kSlots];  // swfr_render / swfr_render_batch rotate, so that the stages of render k + 1 are
+  int scratch_ix = 0;                // flattened and uploaded while renders k - 1 and k are still on the GPU
   uint32_t host_threads = 0;    // stage flattening threads (0 = min(8, hardware))
   bool clear_to_background = false;
   uint32_t occlusion_chunks = 0;  // 0 = automatic, 1 = no culling, n = n depth chunks
   bool tiny_arena = false;  // debug: start every working array at a few hundred entries so that growth + re-run is exercised
   cudaStream_t up_stream = nullptr;
 
-  // ---- last render ----
+  // ---- newest render ----
   swfr_batch *last = nullptr;
-  bool pending = false;
   uint32_t frames_rendered = 0;
-  swfr_stats stats{};
+  swfr_stats stats{};  // of the newest settled render
   std::vector<Totals> last_totals;
   size_t arena_pass = 0;  // index of the pass whose working set is in the arena
   bool profile = false;   // record CUDA events at the stage boundaries of every pass
@@ -175,15 +201,10 @@ struct swfr_renderer {
   size_t prof_passes = 0;
   float stage_ms[kNumStages] = {0};
   uint32_t stage_launches = 0;
-  // readback overlapped with rendering: one event per pass, copies on their own stream
+  // readback overlapped with rendering: one event per slice of a pass, copies on their own stream
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> pass_done;  // kMaxFineSlices events per pass: slice k of pass i at [i * kMaxFineSlices + k]
   bool copy_pending = false;
-  struct CopyReq {
-    uint32_t first, count;
-    uint8_t *dst;
-  };
-  std::vector<CopyReq> copy_reqs;  // since the last launch (re-issued if a pass had to be re-run)
   // frame ranges whose device->host copy may still be in flight when the next render starts: that render's pass
   // which overwrites the range waits for the event (recorded on the copy stream)
   struct CopyFence {
@@ -371,7 +392,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     for (std::thread &x : th) x.join();
   };
   run([&](uint32_t t) {
-    for (uint32_t f = t; f < n; f += nt) {
+    for (uint32_t f = t; f < n; f += nt) try {  // an exception in a worker thread must not reach std::terminate
       FrameSum &s = sums[f];
       const swfr_stage &st = stages[f];
       for (uint32_t i = 0; i < st.n_primitives; i++) {
@@ -402,9 +423,12 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
           }
         }
       }
+    } catch (...) {
+      sums[f].err = SWFR_ERR_OOM;
     }
   });
   for (uint32_t f = 0; f < n; f++) {
+    if (sums[f].err == SWFR_ERR_OOM) return fail(r, SWFR_ERR_OOM, "host allocation failed while flattening the stages");
     if (sums[f].err == SWFR_ERR_INVALID_ID) return fail(r, SWFR_ERR_INVALID_ID, "unknown shape id " + std::to_string(sums[f].bad_id));
     if (sums[f].err != SWFR_OK) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "unknown display primitive kind");
   }
@@ -574,47 +598,21 @@ int upload_batch(swfr_renderer *r, swfr_batch &b) {
   return SWFR_OK;
 }
 
+int finish(swfr_renderer *r);
+
+// Sizes the working memory for batch b.  Runs twice: a dry run that only finds out whether any array has to grow -
+// if so, the renders in flight are settled first (they use the arrays that would be freed) - then the real one.
 int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
-  uint32_t max_seg = 0, max_paths = 0;
+  uint32_t max_seg = 0, max_paths = 0, max_items = 0, max_frames = 1;
   for (const Pass &p : b.passes) {
     max_seg = std::max(max_seg, p.n_seginst);
     max_paths = std::max(max_paths, p.n_paths);
+    max_items = std::max(max_items, p.n_items);
+    max_frames = std::max(max_frames, p.n_frames);
   }
   const int n_arenas = (int)std::min<size_t>(b.passes.size(), (size_t)r->n_arenas);  // a single pass needs one working set
-  for (int k = 0; k < n_arenas; k++) {
-  swfr_renderer::Arena &A = r->arena[k];
-  CK(A.seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
-  CK(A.seg_item.reserve((size_t)max_seg * 4 + 256));
-  CK(A.path_rec.reserve((size_t)max_paths * sizeof(PathRec) + 256));
-  CK(A.paint_inst.reserve((size_t)max_paths * sizeof(PaintInst) + 256));
-  CK(A.path_slot_off.reserve(((size_t)max_paths + 1) * 4 + 256));
-  CK(A.path_rec_base.reserve(((size_t)max_paths + 1) * 4 + 256));
-  CK(A.big_chunk.reserve((size_t)max_paths * 4 + 256));
-  CK(A.small_chunk.reserve((size_t)max_paths * 4 + 256));
-  CK(A.path_item.reserve((size_t)max_paths * 4 + 256));
-  {
-    uint32_t max_items = 0;
-    for (const Pass &p : b.passes) max_items = std::max(max_items, p.n_items);
-    CK(A.item_alive.reserve((size_t)max_items * 4 + 256));
-    CK(A.alive_items.reserve((size_t)max_items * 4 + 256));
-  }
-  CK(A.path_alive.reserve((size_t)max_paths * 4 + 256));
-  CK(A.alive_paths.reserve((size_t)max_paths * 4 + 256));
-
-  {
-    uint32_t max_frames = 1;
-    for (const Pass &p : b.passes) max_frames = std::max(max_frames, p.n_frames);
-    CK(A.alive_count.reserve((size_t)max_frames * 4 + 256));
-    CK(A.tile_cover.reserve((size_t)max_frames * r->tiles_x * r->tiles_y * 4 + 256));
-    CK(A.cover_sat.reserve((size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256));
-  }
-  CK(A.scan_tmp.reserve(8192 * 4));
-  CK(A.chunk_edge.reserve(64 * 4));
-  }
-  CK(r->totals.reserve(std::max<size_t>(b.passes.size(), 1) * sizeof(Totals)));
-  CK(r->frames.reserve(std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256)));
   Caps want = r->caps;
-  if (r->tiny_arena) {  // SWFR_OPT_DEBUG_TINY_ARENA: no heuristics, every array has to grow through finish()
+  if (r->tiny_arena) {  // SWFR_OPT_DEBUG_TINY_ARENA: no heuristics, every array has to grow through settle()
     want.edges = std::max<uint32_t>(want.edges, 512);
     want.slots = std::max<uint32_t>(want.slots, 512);
     want.records = std::max<uint32_t>(want.records, 512);
@@ -622,43 +620,88 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     want.rows = std::max<uint32_t>(want.rows, 512);
     want.stage = std::max<uint32_t>(want.stage, 1024);
   } else {
-  want.edges = std::max<uint32_t>(want.edges, std::max<uint32_t>(1u << 16, max_seg * 4));
-  want.slots = std::max<uint32_t>(want.slots, std::max<uint32_t>(1u << 16, max_paths * 32));
-  want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
-  want.list = std::max<uint32_t>(want.list, std::max<uint32_t>(1u << 16, max_paths * 12));
-  want.rows = std::max<uint32_t>(want.rows, std::max<uint32_t>(1u << 16, max_paths * 8));
-  // staging: the records, plus one partly filled block per binning warp (at most kNumSM * 16 * 8 warps, one per 32 edges)
-  {
+    want.edges = std::max<uint32_t>(want.edges, std::max<uint32_t>(1u << 16, max_seg * 4));
+    want.slots = std::max<uint32_t>(want.slots, std::max<uint32_t>(1u << 16, max_paths * 32));
+    want.records = std::max<uint32_t>(want.records, std::max<uint32_t>(1u << 17, want.edges * 2));
+    want.list = std::max<uint32_t>(want.list, std::max<uint32_t>(1u << 16, max_paths * 12));
+    want.rows = std::max<uint32_t>(want.rows, std::max<uint32_t>(1u << 16, max_paths * 8));
+    // staging: the records, plus one partly filled block per binning warp (at most kNumSM * 16 * 8 warps, one per 32 edges)
     uint64_t warps = std::min<uint64_t>((uint64_t)kNumSM * 16 * 8, (uint64_t)want.edges / 32 + 1);
     uint64_t st = (uint64_t)want.records + want.records / 4 + warps * kStageBlock + 65535u;
     want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(st & ~255ull, 0xffffff00ull));
   }
-  }
-  uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
+  const uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
   size_t max_lists = (size_t)std::max<uint32_t>(1, r->frames_per_pass) * r->tiles_y * groups_x;
   for (const Pass &p : b.passes) max_lists = std::max(max_lists, (size_t)p.n_frames * r->tiles_y * groups_x);
-  size_t max_rows = max_lists / groups_x;
-  for (int k = 0; k < n_arenas; k++) {
-  swfr_renderer::Arena &A = r->arena[k];
-  CK(A.list_off.reserve((max_lists + 1) * 4 + 256));
-  CK(A.list_items.reserve((size_t)want.list * 4));
-  CK(A.row_count.reserve((max_rows + 1) * 4 + 256));
-  CK(A.row_off.reserve((max_rows + 1) * 4 + 256));
-  CK(A.row_items.reserve((size_t)want.rows * 8));
-  CK(A.edges.reserve((size_t)want.edges * 16));
-  CK(A.edge_pid.reserve((size_t)want.edges * 4));
-  CK(A.slot_count.reserve(((size_t)want.slots + 1) * 4));
-  CK(A.slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
-  CK(A.slot_off.reserve(((size_t)want.slots + 1) * 4));
-  CK(A.records.reserve((size_t)want.records * 8));
-  CK(A.stage.reserve((size_t)want.stage * 16));
-  CK(A.stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
+  const size_t max_rows = max_lists / groups_x;
+  const size_t tiles = (size_t)r->tiles_x * r->tiles_y;
+  for (int dry = 1; dry >= 0; dry--) {
+    bool grow = false;
+    cudaError_t err = cudaSuccess;
+    auto need = [&](DevBuf &d, size_t bytes) {
+      if (bytes <= d.cap || err != cudaSuccess) return;
+      if (dry)
+        grow = true;
+      else
+        err = d.reserve(bytes);
+    };
+    for (int k = 0; k < n_arenas; k++) {
+      swfr_renderer::Arena &A = r->arena[k];
+      need(A.seg_edge_off, ((size_t)max_seg + 1) * 4 + 256);
+      need(A.seg_item, (size_t)max_seg * 4 + 256);
+      need(A.path_rec, (size_t)max_paths * sizeof(PathRec) + 256);
+      need(A.paint_inst, (size_t)max_paths * sizeof(PaintInst) + 256);
+      need(A.path_slot_off, ((size_t)max_paths + 1) * 4 + 256);
+      need(A.path_rec_base, ((size_t)max_paths + 1) * 4 + 256);
+      need(A.big_chunk, (size_t)max_paths * 4 + 256);
+      need(A.small_chunk, (size_t)max_paths * 4 + 256);
+      need(A.path_item, (size_t)max_paths * 4 + 256);
+      need(A.item_alive, (size_t)max_items * 4 + 256);
+      need(A.alive_items, (size_t)max_items * 4 + 256);
+      need(A.path_alive, (size_t)max_paths * 4 + 256);
+      need(A.alive_paths, (size_t)max_paths * 4 + 256);
+      need(A.alive_count, (size_t)max_frames * 4 + 256);
+      need(A.tile_cover, (size_t)max_frames * tiles * 4 + 256);
+      need(A.cover_sat, (size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256);
+      need(A.scan_tmp, 8192 * 4);
+      need(A.chunk_edge, 64 * 4);
+      need(A.list_off, (max_lists + 1) * 4 + 256);
+      need(A.list_items, (size_t)want.list * 4);
+      need(A.row_count, (max_rows + 1) * 4 + 256);
+      need(A.row_off, (max_rows + 1) * 4 + 256);
+      need(A.row_items, (size_t)want.rows * 8);
+      need(A.edges, (size_t)want.edges * 16);
+      need(A.edge_pid, (size_t)want.edges * 4);
+      need(A.slot_count, ((size_t)want.slots + 1) * 4);
+      need(A.slot_backdrop, ((size_t)want.slots + 1) * 4);
+      need(A.slot_off, ((size_t)want.slots + 1) * 4);
+      need(A.records, (size_t)want.records * 8);
+      need(A.stage, (size_t)want.stage * 16);
+      need(A.stage_used, (size_t)(want.stage / 256 + 1) * 4);
+    }
+    for (int k = 0; k < swfr_renderer::kSlots; k++) need(r->totals[k], std::max<size_t>(b.passes.size(), 1) * sizeof(Totals));
+    need(r->frames, std::max<size_t>((size_t)b.n_frames * r->width * r->height * 4, 256));
+    for (int k = 0; k < swfr_renderer::kSlots; k++)  // pinned mirrors of the counters: a D2H copy may be in flight into them
+      if (std::max<size_t>(b.passes.size(), 1) * sizeof(Totals) > r->pin_totals[k].cap) {
+        if (dry)
+          grow = true;
+        else if (err == cudaSuccess)
+          err = r->pin_totals[k].reserve(std::max<size_t>(b.passes.size(), 16) * sizeof(Totals));
+      }
+    if (err != cudaSuccess)
+      return fail(r, err == cudaErrorMemoryAllocation ? SWFR_ERR_OOM : SWFR_ERR_CUDA,
+                  std::string("working memory: ") + cudaGetErrorString(err));
+    if (dry && !grow) break;
+    if (dry) {
+      int rc = finish(r);
+      if (rc != SWFR_OK) return rc;
+    }
   }
   r->caps = want;
   return SWFR_OK;
 }
 
-RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_t pass_index) {
+RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_t pass_index, int slot) {
   RenderArgs a{};
   const swfr_renderer::Arena &A = r->arena[pass_index % (size_t)r->n_arenas];
   a.width = (int)r->width;
@@ -717,21 +760,80 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.alive_items = A.alive_items.as<uint32_t>();
   a.alive_paths = A.alive_paths.as<uint32_t>();
   a.alive_count = A.alive_count.as<uint32_t>();
-  a.totals = r->totals.as<Totals>() + pass_index;
+  a.totals = r->totals[slot].as<Totals>() + pass_index;
   a.caps = r->caps;
   return a;
 }
 
-int finish(swfr_renderer *r);
+int settle(swfr_renderer *r, size_t keep);
+
+int ensure_streams(swfr_renderer *r, int n) {
+  for (int k = 0; k < n; k++)
+    if (!r->pass_stream[k]) {
+      CK(cudaStreamCreateWithFlags(&r->pass_stream[k], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&r->join_ev[k], cudaEventDisableTiming));
+    }
+  if (!r->render_done) CK(cudaEventCreateWithFlags(&r->render_done, cudaEventDisableTiming));
+  for (int k = 0; k < swfr_renderer::kSlots; k++)
+    if (!r->slot_done[k]) CK(cudaEventCreateWithFlags(&r->slot_done[k], cudaEventDisableTiming | cudaEventBlockingSync));
+  return SWFR_OK;
+}
+
+// Enqueues every pass of batch b.  `settled_first`: the caller has synchronised everything (re-run after an overflow):
+// all passes go to `stream` one after the other.
+int enqueue_passes(swfr_renderer *r, swfr_batch &b, int slot, bool serial, uint32_t *launches_out) {
+  uint32_t launches = 0;
+  const bool overlap = !serial && b.passes.size() > 1 && !r->profile && r->n_arenas > 1;
+  const int n_streams = overlap ? (int)std::min<size_t>(b.passes.size(), (size_t)r->n_arenas) : 1;
+  if (!serial) {
+    // a render laid out differently from its predecessor writes frame ranges from other streams than that one did
+    const uint32_t fpp = std::max<uint32_t>(1, r->frames_per_pass);
+    const bool same = r->layout_frames == b.n_frames && r->layout_fpp == (overlap ? fpp : 0u);
+    for (int k = 0; k < n_streams; k++) {
+      if (b.uploaded) CK(cudaStreamWaitEvent(r->pass_stream[k], b.uploaded, 0));
+      if (!same) CK(cudaStreamWaitEvent(r->pass_stream[k], r->render_done, 0));
+    }
+    r->layout_frames = b.n_frames;
+    r->layout_fpp = overlap ? fpp : 0u;
+  }
+  for (size_t i = 0; i < b.passes.size(); i++) {
+    const int sk = overlap ? (int)(i % (size_t)r->n_arenas) : 0;
+    cudaStream_t st = serial ? r->stream : r->pass_stream[sk];
+    if (!serial)  // a device->host copy of an earlier render may still be reading the frames this pass overwrites
+      for (const swfr_renderer::CopyFence &cf : r->copy_fences)
+        if (cf.first < b.passes[i].f0 + b.passes[i].n_frames && b.passes[i].f0 < cf.first + cf.count)
+          CK(cudaStreamWaitEvent(st, cf.done, 0));
+    launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i, slot), st,
+                                        (r->profile && !serial) ? r->prof_events.data() + i * (kNumStages + 1) : nullptr,
+                                        r->pass_done.data() + i * kMaxFineSlices);
+  }
+  if (!serial) {
+    for (int k = 0; k < n_streams; k++) {
+      CK(cudaEventRecord(r->join_ev[k], r->pass_stream[k]));
+      CK(cudaStreamWaitEvent(r->stream, r->join_ev[k], 0));
+    }
+    CK(cudaEventRecord(r->render_done, r->stream));
+    for (const swfr_renderer::CopyFence &cf : r->copy_fences) r->fence_pool.push_back(cf.done);
+    r->copy_fences.clear();
+  }
+  CK(cudaMemcpyAsync(r->pin_totals[slot].p, r->totals[slot].p, b.passes.size() * sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
+  CK(cudaEventRecord(r->slot_done[slot], r->stream));
+  CK(cudaGetLastError());
+  if (launches_out) *launches_out = launches;
+  return SWFR_OK;
+}
 
 int launch_batch(swfr_renderer *r, swfr_batch &b) {
-  int rc = finish(r);  // settle (and possibly retry) the previous render before reusing the arena
+  // The newest render in flight keeps the GPU busy while this one is enqueued behind it; older ones are settled now
+  // (their counters are usually back already).  Profiling runs read per-render events: nothing stays in flight.
+  int rc = settle(r, r->profile ? 0 : 1);
   if (rc != SWFR_OK) return rc;
   rc = flush_store(r);
   if (rc != SWFR_OK) return rc;
   rc = ensure_arena(r, b);
   if (rc != SWFR_OK) return rc;
-  uint32_t launches = 0;
+  rc = ensure_streams(r, r->n_arenas);
+  if (rc != SWFR_OK) return rc;
   r->prof_passes = 0;
   if (r->profile) {
     size_t need = b.passes.size() * (kNumStages + 1);
@@ -747,126 +849,30 @@ int launch_batch(swfr_renderer *r, swfr_batch &b) {
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     r->pass_done.push_back(e);
   }
-  r->copy_reqs.clear();
-  if (b.uploaded) CK(cudaStreamWaitEvent(r->stream, b.uploaded, 0));
-  // Consecutive passes alternate between two arenas and two streams (fork after the upload, join at the end), so
-  // that they overlap on the GPU; with SWFR_OPT_PROFILE the passes stay on one stream and the stage times are clean.
-  const bool overlap = b.passes.size() > 1 && !r->profile && r->n_arenas > 1;
-  const int n_streams = overlap ? (int)std::min<size_t>(b.passes.size(), (size_t)r->n_arenas) : 1;
-  if (overlap) {
-    if (!r->fork_ev) CK(cudaEventCreateWithFlags(&r->fork_ev, cudaEventDisableTiming));
-    CK(cudaEventRecord(r->fork_ev, r->stream));
-    for (int k = 1; k < n_streams; k++) {
-      if (!r->extra_stream[k - 1]) {
-        CK(cudaStreamCreateWithFlags(&r->extra_stream[k - 1], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&r->join_ev[k - 1], cudaEventDisableTiming));
-      }
-      CK(cudaStreamWaitEvent(r->extra_stream[k - 1], r->fork_ev, 0));
-    }
-  }
-  for (size_t i = 0; i < b.passes.size(); i++) {
-    const int sk = overlap ? (int)(i % (size_t)r->n_arenas) : 0;
-    cudaStream_t st = sk ? r->extra_stream[sk - 1] : r->stream;
-    // a device->host copy of the previous render may still be reading the frames this pass overwrites
-    for (const swfr_renderer::CopyFence &cf : r->copy_fences)
-      if (cf.first < b.passes[i].f0 + b.passes[i].n_frames && b.passes[i].f0 < cf.first + cf.count)
-        CK(cudaStreamWaitEvent(st, cf.done, 0));
-    launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), st,
-                                        r->profile ? r->prof_events.data() + i * (kNumStages + 1) : nullptr,
-                                        r->pass_done.data() + i * kMaxFineSlices);
-  }
-  for (int k = 1; k < n_streams; k++) {
-    CK(cudaEventRecord(r->join_ev[k - 1], r->extra_stream[k - 1]));
-    CK(cudaStreamWaitEvent(r->stream, r->join_ev[k - 1], 0));
-  }
-  for (const swfr_renderer::CopyFence &cf : r->copy_fences) r->fence_pool.push_back(cf.done);
-  r->copy_fences.clear();
-  CK(cudaGetLastError());
+  swfr_renderer::InFlight in;
+  in.b = &b;
+  in.slot = r->next_slot;
+  r->next_slot = (r->next_slot + 1) % swfr_renderer::kSlots;
+  rc = enqueue_passes(r, b, in.slot, false, &in.launches);
+  if (rc != SWFR_OK) return rc;
+  r->inflight.push_back(std::move(in));
   r->last = &b;
   r->arena_pass = b.passes.empty() ? 0 : b.passes.size() - 1;
-  r->pending = true;
   r->frames_rendered = b.n_frames;
-  memset(&r->stats, 0, sizeof r->stats);
-  r->stats.kernel_launches = launches;
   return SWFR_OK;
 }
 
-// Waits for the last render, grows working memory and re-runs passes that overflowed it.
-int finish(swfr_renderer *r) {
-  if (!r->pending) return SWFR_OK;
-  swfr_batch &b = *r->last;
-  size_t np = b.passes.size();
-  r->last_totals.assign(np, Totals{});
-  CK(cudaMemcpyAsync(r->last_totals.data(), r->totals.p, np * sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
-  CK(cudaStreamSynchronize(r->stream));
-  bool rerun = false;
-  for (size_t i = 0; i < np; i++) {
-    int guard = 0;
-    while (r->last_totals[i].overflow | r->last_totals[i].overflow_stage) {
-      if (++guard > 12) return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
-      const Totals &t = r->last_totals[i];
-      Caps want = r->caps;
-      auto grow = [](uint32_t need) { return (uint32_t)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0xfffffff0ull); };
-      if (t.overflow & 1u) want.edges = std::max(want.edges, grow(t.n_edges));
-      if (t.overflow & 2u) want.slots = std::max(want.slots, grow(t.n_slots));
-      if (t.overflow & 4u) want.records = std::max(want.records, grow(t.n_records));
-      if (t.overflow & 8u) want.list = std::max(want.list, grow(t.n_list));
-      if (t.overflow & 16u) want.rows = std::max(want.rows, grow(t.n_rowent));
-      if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
-      if (t.overflow_stage) {
-        uint64_t need = ((uint64_t)t.n_stage_blocks + t.n_stage_blocks / 8 + 64) * 256;
-        want.stage = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want.stage, need), 0xffffff00ull);
-      }
-      if (!r->tiny_arena)
-        want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
-      for (int k = 0; k < (int)std::min<size_t>(np, (size_t)r->n_arenas); k++) {
-        swfr_renderer::Arena &A = r->arena[k];
-        CK(A.list_items.reserve((size_t)want.list * 4));
-        CK(A.row_items.reserve((size_t)want.rows * 8));
-        CK(A.stage.reserve((size_t)want.stage * 16));
-        CK(A.stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
-        CK(A.edges.reserve((size_t)want.edges * 16));
-        CK(A.edge_pid.reserve((size_t)want.edges * 4));
-        CK(A.slot_count.reserve(((size_t)want.slots + 1) * 4));
-        CK(A.slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
-        CK(A.slot_off.reserve(((size_t)want.slots + 1) * 4));
-        CK(A.records.reserve((size_t)want.records * 8));
-      }
-      r->caps = want;
-      r->stats.retries++;
-      r->arena_pass = i;
-      if (!rerun && r->copy_pending) CK(cudaStreamSynchronize(r->copy_stream));  // copies of incomplete frames
-      rerun = true;
-      r->stats.kernel_launches += (uint32_t)launch_render(make_args(r, b, b.passes[i], i), r->stream);
-      CK(cudaMemcpyAsync(&r->last_totals[i], r->totals.as<Totals>() + i, sizeof(Totals), cudaMemcpyDeviceToHost, r->stream));
-      CK(cudaStreamSynchronize(r->stream));
-      }
-  }
-  r->pending = false;
-  if (rerun) {  // frames copied out before the re-run were incomplete: copy them again
-    size_t fb = (size_t)r->width * r->height * 4;
-    for (const swfr_renderer::CopyReq &q : r->copy_reqs)
-      CK(cudaMemcpyAsync(q.dst, (const char *)r->frames.p + (size_t)q.first * fb, (size_t)q.count * fb,
-                         cudaMemcpyDeviceToHost, r->stream));
-    CK(cudaStreamSynchronize(r->stream));
-  }
-  if (r->prof_passes) {
-    for (int k = 0; k < kNumStages; k++) r->stage_ms[k] = 0.f;
-    for (size_t i = 0; i < r->prof_passes; i++) {
-      cudaEvent_t *ev = r->prof_events.data() + i * (kNumStages + 1);
-      for (int k = 0; k < kNumStages; k++) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) r->stage_ms[k] += ms;
-      }
-    }
-    r->stage_launches = (uint32_t)r->prof_passes;
-  }
+// Statistics and device-reported errors of a render whose counters are in `tot`.
+int account(swfr_renderer *r, const swfr_batch &b, const std::vector<Totals> &tot, uint32_t launches, uint32_t retries) {
+  memset(&r->stats, 0, sizeof r->stats);
+  r->stats.kernel_launches = launches;
+  r->stats.retries = retries;
   uint32_t err = 0;
   r->stats.n_primitives = b.n_prims;
   r->stats.n_segments = b.n_seginst;
   r->stats.n_path_instances = b.n_paths;
   r->stats.n_tiles = (uint64_t)r->tiles_x * r->tiles_y * b.n_frames;
-  for (const Totals &t : r->last_totals) {
+  for (const Totals &t : tot) {
     r->stats.n_edges += t.n_edges;
     r->stats.n_slots += t.n_slots;
     r->stats.n_records += t.n_records;
@@ -881,6 +887,123 @@ int finish(swfr_renderer *r) {
   if (err & 1u) return fail(r, SWFR_ERR_INVALID_ID, "BitmapNotFound: a bitmap fill references an unregistered bitmap id");
   return SWFR_OK;
 }
+
+bool any_overflow(const Totals *t, size_t n) {
+  for (size_t i = 0; i < n; i++)
+    if (t[i].overflow | t[i].overflow_stage) return true;
+  return false;
+}
+
+// Working memory overflowed in the oldest render in flight (the later ones ran with the same arrays and have
+// overwritten its frames): everything is synchronised, then every render in flight is run again, in order and alone,
+// growing the arrays until it fits, and its read-back requests are served again.
+int recover(swfr_renderer *r) {
+  CK(cudaStreamSynchronize(r->stream));
+  if (r->copy_stream) CK(cudaStreamSynchronize(r->copy_stream));
+  const size_t fb = (size_t)r->width * r->height * 4;
+  int result = SWFR_OK;
+  while (!r->inflight.empty()) {
+    swfr_renderer::InFlight in = std::move(r->inflight.front());
+    r->inflight.pop_front();
+    swfr_batch &b = *in.b;
+    const size_t np = b.passes.size();
+    uint32_t retries = 0;
+    const Totals *pt = reinterpret_cast<const Totals *>(r->pin_totals[in.slot].p);
+    for (int guard = 0;; guard++) {
+      if (any_overflow(pt, np)) {
+        if (guard >= 12) {
+          r->inflight.clear();
+          return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
+        }
+        Caps want = r->caps;
+        auto grow = [](uint32_t need) { return (uint32_t)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0xfffffff0ull); };
+        for (size_t i = 0; i < np; i++) {
+          const Totals &t = pt[i];
+          if (t.overflow & 1u) want.edges = std::max(want.edges, grow(t.n_edges));
+          if (t.overflow & 2u) want.slots = std::max(want.slots, grow(t.n_slots));
+          if (t.overflow & 4u) want.records = std::max(want.records, grow(t.n_records));
+          if (t.overflow & 8u) want.list = std::max(want.list, grow(t.n_list));
+          if (t.overflow & 16u) want.rows = std::max(want.rows, grow(t.n_rowent));
+          if (t.overflow & 1u) want.records = std::max(want.records, want.edges * 2);
+          if (t.overflow_stage) {
+            uint64_t need = ((uint64_t)t.n_stage_blocks + t.n_stage_blocks / 8 + 64) * 256;
+            want.stage = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want.stage, need), 0xffffff00ull);
+          }
+        }
+        if (!r->tiny_arena)
+          want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
+        for (int k = 0; k < (int)std::min<size_t>(np, (size_t)r->n_arenas); k++) {
+          swfr_renderer::Arena &A = r->arena[k];
+          CK(A.list_items.reserve((size_t)want.list * 4));
+          CK(A.row_items.reserve((size_t)want.rows * 8));
+          CK(A.stage.reserve((size_t)want.stage * 16));
+          CK(A.stage_used.reserve((size_t)(want.stage / 256 + 1) * 4));
+          CK(A.edges.reserve((size_t)want.edges * 16));
+          CK(A.edge_pid.reserve((size_t)want.edges * 4));
+          CK(A.slot_count.reserve(((size_t)want.slots + 1) * 4));
+          CK(A.slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
+          CK(A.slot_off.reserve(((size_t)want.slots + 1) * 4));
+          CK(A.records.reserve((size_t)want.records * 8));
+        }
+        r->caps = want;
+        retries++;
+      } else if (guard > 0) {
+        break;  // this run fitted
+      }
+      uint32_t launches = 0;
+      int rc = enqueue_passes(r, b, in.slot, true, &launches);
+      if (rc != SWFR_OK) {
+        r->inflight.clear();
+        return rc;
+      }
+      in.launches += launches;
+      CK(cudaStreamSynchronize(r->stream));
+    }
+    for (const swfr_renderer::CopyReq &q : in.copy_reqs)
+      CK(cudaMemcpyAsync(q.dst, (const char *)r->frames.p + (size_t)q.first * fb, (size_t)q.count * fb, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    r->last_totals.assign(pt, pt + np);
+    r->arena_pass = np ? np - 1 : 0;
+    int rc = account(r, b, r->last_totals, in.launches, retries);
+    if (rc != SWFR_OK) result = rc;
+  }
+  return result;
+}
+
+// Settles the renders in flight, oldest first, until at most `keep` remain.
+int settle(swfr_renderer *r, size_t keep) {
+  int result = SWFR_OK;
+  while (r->inflight.size() > keep) {
+    swfr_renderer::InFlight &in = r->inflight.front();
+    CK(cudaEventSynchronize(r->slot_done[in.slot]));
+    const size_t np = in.b->passes.size();
+    const Totals *pt = reinterpret_cast<const Totals *>(r->pin_totals[in.slot].p);
+    if (any_overflow(pt, np)) {
+      int rc = recover(r);
+      return rc != SWFR_OK ? rc : result;
+    }
+    r->last_totals.assign(pt, pt + np);
+    int rc = account(r, *in.b, r->last_totals, in.launches, 0);
+    if (rc != SWFR_OK) result = rc;
+    if (r->prof_passes && r->inflight.size() == 1) {
+      for (int k = 0; k < kNumStages; k++) r->stage_ms[k] = 0.f;
+      for (size_t i = 0; i < r->prof_passes; i++) {
+        cudaEvent_t *ev = r->prof_events.data() + i * (kNumStages + 1);
+        for (int k = 0; k < kNumStages; k++) {
+          float ms = 0.f;
+          if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) r->stage_ms[k] += ms;
+        }
+      }
+      r->stage_launches = (uint32_t)r->prof_passes;
+      r->prof_passes = 0;
+    }
+    r->inflight.pop_front();
+  }
+  return result;
+}
+
+// Waits for every render in flight, grows working memory and re-runs what overflowed it.
+int finish(swfr_renderer *r) { return settle(r, 0); }
 
 int register_def(swfr_renderer *r, const swfr_define_shape *tag, bool morph, uint32_t *out_id) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
@@ -995,13 +1118,15 @@ void swfr_destroy(swfr_renderer *r) {
     cudaStreamSynchronize(r->copy_stream);
     cudaStreamDestroy(r->copy_stream);
   }
-  for (int k = 0; k < swfr_renderer::kArenas - 1; k++)
-    if (r->extra_stream[k]) {
-      cudaStreamSynchronize(r->extra_stream[k]);
-      cudaStreamDestroy(r->extra_stream[k]);
+  for (int k = 0; k < swfr_renderer::kArenas; k++)
+    if (r->pass_stream[k]) {
+      cudaStreamSynchronize(r->pass_stream[k]);
+      cudaStreamDestroy(r->pass_stream[k]);
       cudaEventDestroy(r->join_ev[k]);
     }
-  if (r->fork_ev) cudaEventDestroy(r->fork_ev);
+  if (r->render_done) cudaEventDestroy(r->render_done);
+  for (int k = 0; k < swfr_renderer::kSlots; k++)
+    if (r->slot_done[k]) cudaEventDestroy(r->slot_done[k]);
   if (r->up_stream) {
     cudaStreamSynchronize(r->up_stream);
     cudaStreamDestroy(r->up_stream);
@@ -1114,6 +1239,7 @@ int swfr_register_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, 
 int swfr_register_bitmap_xswfbmp(swfr_renderer *r, uint16_t id, const uint8_t *data, size_t len) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (!data) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL data");
+  return guarded(r, [&]() -> int {
   std::vector<uint8_t> inflated;
   uint32_t w = 0, h = 0, colors = 0, padded = 0;
   std::string err;
@@ -1128,9 +1254,12 @@ int swfr_register_bitmap_xswfbmp(swfr_renderer *r, uint16_t id, const uint8_t *d
   launch_xswfbmp_expand(r->scratch2.as<uint8_t>(), colors, w, h, padded, r->scratch.as<uint32_t>(), r->stream);
   CK(cudaStreamSynchronize(r->stream));  // `inflated` is pageable host memory
   return install_bitmap(r, id, w, h, true);
+  });
 }
 
 int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t cap, uint32_t *w, uint32_t *h) {
+  if (!data) return SWFR_ERR_INVALID_ARGUMENT;
+  return guarded(nullptr, [&]() -> int {
   std::vector<uint8_t> out;
   std::string err;
   uint32_t ww = 0, hh = 0;
@@ -1138,22 +1267,32 @@ int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t
   if (rc != SWFR_OK) return rc;
   if (w) *w = ww;
   if (h) *h = hh;
-  if (rgba && !out.empty() && cap >= out.size()) memcpy(rgba, out.data(), out.size());
+  if (rgba && cap < out.size()) return SWFR_ERR_INVALID_ARGUMENT;  // the caller's buffer is too small for w x h x 4 bytes
+  if (rgba && !out.empty()) memcpy(rgba, out.data(), out.size());
   return SWFR_OK;
+  });
 }
 
 int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (!stages || n == 0) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
   cudaSetDevice(r->device);
-  // The previous render (if any) is still on the GPU: flatten and upload this one's stages meanwhile, into the
-  // scratch batch the previous render does not use, and only then settle the previous render.
-  r->scratch_ix ^= 1;
+  // Earlier renders (up to two) are still on the GPU: flatten and upload this one's stages meanwhile, into the
+  // scratch batch none of them uses, and only then let the host catch up with all but the newest of them.
+  r->scratch_ix = (r->scratch_ix + 1) % swfr_renderer::kSlots;
   swfr_batch &b = r->scratch_batch[r->scratch_ix];
   return guarded(r, [&]() -> int {
-    if (r->last == &b) {  // only when finish() kept an older scratch alive: settle first
-      int rc0 = finish(r);
+    for (;;) {  // only when renders of caller-owned batches were interleaved: settle up to the last user of this scratch
+      size_t at = r->inflight.size();
+      for (size_t i = 0; i < r->inflight.size(); i++)
+        if (r->inflight[i].b == &b) at = i;
+      if (at == r->inflight.size()) break;
+      int rc0 = settle(r, r->inflight.size() - 1 - at);
       if (rc0 != SWFR_OK) return rc0;
+    }
+    if (r->last == &b) {  // the taps and frames_rendered describe a batch that is being rebuilt
+      r->last = nullptr;
+      r->frames_rendered = 0;
     }
     int rc = build_batch(r, stages, n, b);
     if (rc != SWFR_OK) return rc;
@@ -1168,6 +1307,7 @@ int swfr_render(swfr_renderer *r, const swfr_stage *stage) { return swfr_render_
 int swfr_render_display_stages(swfr_renderer *r, const swfr_display_stage *stages, uint32_t n) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (!stages || n == 0) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
+  return guarded(r, [&]() -> int {
   std::vector<std::vector<swfr_display_primitive>> prims(n);
   std::vector<swfr_stage> flat(n);
   for (uint32_t f = 0; f < n; f++) {
@@ -1185,6 +1325,7 @@ int swfr_render_display_stages(swfr_renderer *r, const swfr_display_stage *stage
     flat[f].display_root = prims[f].data();
   }
   return swfr_render_batch(r, flat.data(), n);
+  });
 }
 
 int swfr_render_display_stage(swfr_renderer *r, const swfr_display_stage *stage) {
@@ -1195,14 +1336,16 @@ int swfr_batch_create(swfr_renderer *r, const swfr_stage *stages, uint32_t n, sw
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (!stages || n == 0 || !out) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no stages");
   cudaSetDevice(r->device);
-  auto b = std::make_unique<swfr_batch>();
-  int rc = build_batch(r, stages, n, *b);
-  if (rc != SWFR_OK) return rc;
-  rc = upload_batch(r, *b);
-  if (rc != SWFR_OK) return rc;
-  CK(cudaStreamSynchronize(r->up_stream));
-  *out = b.release();
-  return SWFR_OK;
+  return guarded(r, [&]() -> int {
+    auto b = std::make_unique<swfr_batch>();
+    int rc = build_batch(r, stages, n, *b);
+    if (rc != SWFR_OK) return rc;
+    rc = upload_batch(r, *b);
+    if (rc != SWFR_OK) return rc;
+    CK(cudaStreamSynchronize(r->up_stream));
+    *out = b.release();
+    return SWFR_OK;
+  });
 }
 
 int swfr_batch_render(swfr_renderer *r, swfr_batch *b) {
@@ -1277,10 +1420,11 @@ int swfr_read_image(swfr_renderer *r, uint32_t frame, uint8_t *dst, size_t strid
 
 int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uint8_t *dst) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
-  if (!dst || first + count > r->frames_rendered) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad frame range");
+  if (!dst || count == 0 || first >= r->frames_rendered || count > r->frames_rendered - first)
+    return fail(r, SWFR_ERR_INVALID_ARGUMENT, "bad frame range");
   cudaSetDevice(r->device);
   size_t fb = (size_t)r->width * r->height * 4;
-  if (!r->pending || !r->last) {
+  if (r->inflight.empty() || !r->last) {
     CK(cudaMemcpyAsync(dst, (const char *)r->frames.p + (size_t)first * fb, (size_t)count * fb, cudaMemcpyDeviceToHost,
                        r->stream));
     return SWFR_OK;
@@ -1311,7 +1455,7 @@ int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uin
     }
   }
   r->copy_pending = true;
-  r->copy_reqs.push_back(swfr_renderer::CopyReq{first, count, dst});
+  r->inflight.back().copy_reqs.push_back(swfr_renderer::CopyReq{first, count, dst});
   return SWFR_OK;
 }
 
@@ -1409,8 +1553,10 @@ static int debug_pass(swfr_renderer *r, uint32_t frame, const Pass **pass, size_
   if (!r->last || frame >= r->frames_rendered) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no such frame");
   int rc = finish(r);
   if (rc != SWFR_OK) return rc;
+  if (!r->last) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no render to inspect");
   const swfr_batch &b = *r->last;
   // the arena holds the working set of one pass only (the last one launched)
+  if (r->arena_pass >= b.passes.size()) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no render to inspect");
   const Pass &p = b.passes[r->arena_pass];
   if (frame < p.f0 || frame >= p.f0 + p.n_frames)
     return fail(r, SWFR_ERR_INVALID_ARGUMENT, "debug taps need the frame to be in the last pass (render fewer frames)");
@@ -1429,8 +1575,8 @@ int swfr_debug_edges(swfr_renderer *r, uint32_t frame, int32_t *edges, int32_t *
   const Pass *p;
   size_t pi;
   int rc = debug_pass(r, frame, &p, &pi);
-  const swfr_renderer::Arena &A = r->arena[pi % (size_t)r->n_arenas];
   if (rc != SWFR_OK) return rc;
+  const swfr_renderer::Arena &A = r->arena[pi % (size_t)r->n_arenas];
   const swfr_batch &b = *r->last;
   // frame -> path range -> item range -> segment-instance range -> edge range
   uint32_t lf = frame - p->f0;
@@ -1469,7 +1615,7 @@ int swfr_debug_tile_counts(swfr_renderer *r, uint32_t frame, uint32_t *counts, u
   if (!counts || cap < nt) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "counts buffer too small");
   CK(r->scratch.reserve(std::max<size_t>(nt * 4, (size_t)r->width * r->height * 4)));
   CK(cudaMemsetAsync(r->scratch.p, 0, nt * 4, r->stream));
-  RenderArgs a = make_args(r, *r->last, *p, pi);
+  RenderArgs a = make_args(r, *r->last, *p, pi, 0);
   launch_tile_counts(a, frame - p->f0, r->scratch.as<uint32_t>(), r->stream);
   CK(cudaMemcpyAsync(counts, r->scratch.p, nt * 4, cudaMemcpyDeviceToHost, r->stream));
   CK(cudaStreamSynchronize(r->stream));

@@ -74,6 +74,12 @@ int inflate_xswfbmp(const uint8_t *data, size_t len, std::vector<uint8_t> &src, 
   uint32_t color_count = (uint32_t)data[5] + 1;
   size_t table = 3 * (size_t)color_count;
   size_t need = table + (size_t)padded * height;
+  // The header is untrusted: deflate expands at most ~1032 : 1, so a payload of `len - 6` bytes cannot fill more than
+  // that - a larger claim is truncated pixel data, found without allocating (or zero-filling) gigabytes.
+  if (need > ((size_t)(len - 6) + 1) * 1032 + 64) {
+    err = "x-swf-bmp: pixel data is truncated";
+    return SWFR_ERR_MALFORMED;
+  }
   src.resize(need);
   uLongf got = (uLongf)need;
   int zr = uncompress(src.data(), &got, data + 6, (uLong)(len - 6));

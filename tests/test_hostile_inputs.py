@@ -141,3 +141,27 @@ def test_display_tree_depth_is_bounded_not_a_stack_overflow(built_library):
             assert n == 1 and prims[0].id == 1
         except SwfrError as e:
             assert depth > 64 and e.status < 0
+
+
+def test_xswfbmp_header_cannot_make_the_decoder_allocate_gigabytes(built_library):
+    """A 6-byte header promising 65535 x 65535 pixels over a 20-byte payload: refused as truncated without sizing any
+    buffer from the header - checked in a child process whose address space is capped at 3 GB (the 4.3 GB
+    zero-fill of round 1 aborted there with std::bad_alloc crossing the C ABI)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import resource, zlib, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import swf_renderer_b200 as sw\n"
+        "resource.setrlimit(resource.RLIMIT_AS, (3 << 30, 3 << 30))\n"
+        "data = bytes([3, 255, 255, 255, 255, 255]) + zlib.compress(b'\\0' * 10)\n"
+        "try:\n"
+        "    sw.decode_x_swf_bmp(data)\n"
+        "    print('decoded')\n"
+        "except sw.SwfrError as e:\n"
+        "    print('status', e.status)\n"
+    ) % corpus.os.path.dirname(corpus.HERE)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-500:]
+    assert p.stdout.strip().startswith("status -"), p.stdout
