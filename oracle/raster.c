@@ -51,7 +51,7 @@ typedef struct {
   int32_t color_is_morph; /* colour goes through the morph lerp + css-color path (canvas-renderer.ts:241-250) */
   double matrix[6];   /* fill matrix scale_x, rotate_skew0, rotate_skew1, scale_y, tx, ty (fill space -> twips) */
   double focal;       /* focal point in [-1,1] */
-  const float *lut;   /* 257 x 4 straight RGBA ramp (gradients) */
+  const uint32_t *lut; /* SWFO_RAMP_SIZE premultiplied RGBA8 entries, entry k = the gradient at (k + 1/2) / size */
 } swfo_paint;
 
 typedef struct {
@@ -307,9 +307,7 @@ static void accumulate_record(const record_t *rc, int32_t acc[16][16]) {
     int32_t D = s * (ybm - yt) * 256;
     float Df = (float)D;
     float ytf = (float)yt * k, ybmf = (float)ybm * k;
-    float t0 = (ytf - yaf) * slope;
-    float t1 = (ybmf - yaf) * slope;
-    float xt = xaf + t0, xm = xaf + t1;
+    float xt = fmaf(ytf - yaf, slope, xaf), xm = fmaf(ybmf - yaf, slope, xaf);
     xt = fminf(fmaxf(xt, xlo), xhi);
     xm = fminf(fmaxf(xm, xlo), xhi);
     float xmin = fminf(xt, xm), xmax = fmaxf(xt, xm);
@@ -326,7 +324,7 @@ static void accumulate_record(const record_t *rc, int32_t acc[16][16]) {
         float u0 = fmaxf(fi - xmin, 0.0f);
         float u1 = fminf(fi1 - xmin, w);
         float a0 = (u0 * u0) * inv2w;
-        float a1 = (u1 * u1) * inv2w + fmaxf(fi1 - xmax, 0.0f);
+        float a1 = fmaf(u1 * u1, inv2w, fmaxf(fi1 - xmax, 0.0f));
         float f = a1 - a0;
         f = fminf(fmaxf(f, 0.0f), 1.0f);
         c = (int32_t)lrintf(Df * f);
@@ -345,8 +343,9 @@ typedef struct {
   uint32_t solid;       /* premultiplied, R | G<<8 | B<<16 | A<<24 */
   float inv[6];         /* device px -> fill space: ia, ib, ic, id, itx, ity   (gx = ia*X + ic*Y + itx) */
   float focal, omf;     /* focal point, 1 - focal^2 */
+  float inv_omf;        /* 1 / omf (float division) */
   float rx, ry;         /* bitmap footprint in texels */
-  const float *lut;
+  const uint32_t *lut;
   const swfo_bitmap *bmp;
   int valid;
 } paint_inst;
@@ -454,6 +453,7 @@ static void make_paint(const swfo_scene *sc, const swfo_paint *p, const double m
     if (fp < -0.98) fp = -0.98;
     out->focal = (float)fp;
     out->omf = (float)(1.0 - fp * fp);
+    out->inv_omf = 1.0f / out->omf;
     out->lut = p->lut;
   }
 }
@@ -463,11 +463,15 @@ static inline int32_t floormod(int32_t a, int32_t n) {
   return r < 0 ? r + n : r;
 }
 
+/* Every a*b+c below is a fused multiply-add (C fmaf is correctly rounded, the kernel's fmaf() compiles to FFMA): the
+ * same operations in the same order on both sides. */
+#define SWFO_RAMP_SIZE 1024
+
 static uint32_t eval_paint(const paint_inst *p, int X, int Y) {
   if (p->type == SWFO_PAINT_SOLID) return p->solid;
   float xc = (float)X + 0.5f, yc = (float)Y + 0.5f;
-  float gx = (p->inv[0] * xc + p->inv[2] * yc) + p->inv[4];
-  float gy = (p->inv[1] * xc + p->inv[3] * yc) + p->inv[5];
+  float gx = fmaf(p->inv[0], xc, fmaf(p->inv[2], yc, p->inv[4]));
+  float gy = fmaf(p->inv[1], xc, fmaf(p->inv[3], yc, p->inv[5]));
   if (p->type == SWFO_PAINT_BITMAP) {
     const swfo_bitmap *bm = p->bmp;
     float hrx = p->rx * 0.5f, hry = p->ry * 0.5f;
@@ -493,10 +497,10 @@ static uint32_t eval_paint(const paint_inst *p, int X, int Y) {
           continue;
         const uint8_t *t = bm->rgba + 4 * ((size_t)jj * bm->w + ii);
         float wgt = wx * wy;
-        acc[0] = acc[0] + wgt * (float)t[0];
-        acc[1] = acc[1] + wgt * (float)t[1];
-        acc[2] = acc[2] + wgt * (float)t[2];
-        acc[3] = acc[3] + wgt * (float)t[3];
+        acc[0] = fmaf(wgt, (float)t[0], acc[0]);
+        acc[1] = fmaf(wgt, (float)t[1], acc[1]);
+        acc[2] = fmaf(wgt, (float)t[2], acc[2]);
+        acc[3] = fmaf(wgt, (float)t[3], acc[3]);
       }
     }
     uint32_t o = 0;
@@ -509,17 +513,15 @@ static uint32_t eval_paint(const paint_inst *p, int X, int Y) {
   /* gradients: canvas-renderer.ts:320-331 (focal/radial, GRAD_RADIUS 16384); linear per SWF gradient square */
   float t;
   if (p->type == SWFO_PAINT_LINEAR) {
-    t = gx * (1.0f / 32768.0f) + 0.5f;
+    t = fmaf(gx, 1.0f / 32768.0f, 0.5f);
   } else {
     float nx = gx * (1.0f / 16384.0f), ny = gy * (1.0f / 16384.0f);
     float dx = nx - p->focal;
-    float a = dx * dx;
-    float b = ny * ny;
-    float c = p->omf * b;
-    float disc = a + c;
+    float c = p->omf * (ny * ny);
+    float disc = fmaf(dx, dx, c);
     float s = sqrtf(disc);
-    float num = p->focal * dx + s;
-    t = num / p->omf;
+    float num = fmaf(p->focal, dx, s);
+    t = num * p->inv_omf;
   }
   if (p->spread == SWFO_SPREAD_PAD) {
     t = fminf(fmaxf(t, 0.0f), 1.0f);
@@ -533,27 +535,10 @@ static uint32_t eval_paint(const paint_inst *p, int X, int Y) {
     t = u > 1.0f ? 2.0f - u : u;
     t = fminf(fmaxf(t, 0.0f), 1.0f);
   }
-  float pos = t * 256.0f;
-  int i = (int)floorf(pos);
+  int i = (int)floorf(t * (float)SWFO_RAMP_SIZE);
   if (i < 0) i = 0;
-  if (i > 255) i = 255;
-  float fr = pos - (float)i;
-  const float *l0 = p->lut + 4 * i, *l1 = l0 + 4;
-  float v[4];
-  for (int c = 0; c < 4; c++) {
-    float d = l1[c] - l0[c];
-    float e = d * fr;
-    v[c] = l0[c] + e;
-  }
-  float A = v[3];
-  uint32_t a8 = (uint32_t)lrintf(fminf(fmaxf(A * 255.0f, 0.0f), 255.0f));
-  uint32_t o = a8 << 24;
-  for (int c = 0; c < 3; c++) {
-    float pm = v[c] * A;
-    float q = fminf(fmaxf(pm * 255.0f, 0.0f), 255.0f);
-    o |= (uint32_t)lrintf(q) << (8 * c);
-  }
-  return o;
+  if (i > SWFO_RAMP_SIZE - 1) i = SWFO_RAMP_SIZE - 1;
+  return p->lut[i];
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -46,7 +46,7 @@ class Paint(C.Structure):
         ("color_is_morph", C.c_int32),
         ("matrix", C.c_double * 6),
         ("focal", C.c_double),
-        ("lut", C.POINTER(C.c_float)),
+        ("lut", C.POINTER(C.c_uint32)),
     ]
 
 
@@ -122,10 +122,21 @@ def _linear_to_srgb(c):
     return 12.92 * c if c <= 0.0031308 else 1.055 * math.pow(c, 1.0 / 2.4) - 0.055
 
 
+RAMP_SIZE = 1024
+
+
+def _q8(v):
+    """float32 v in 0..1 -> 8 bits: rint(clamp(v * 255)), in float32 like the C side."""
+    return int(np.rint(np.minimum(np.maximum(np.float32(v) * np.float32(255.0), np.float32(0.0)), np.float32(255.0))))
+
+
 def gradient_lut(colors, color_space="s-rgb") -> np.ndarray:
-    """257 x 4 straight-RGBA ramp.  ``colors`` = [{"ratio": 0..1, "color": {r,g,b,a in 0..1}}] as compiled
-    (decode-swf-shape.ts:99-105).  Canvas addColorStop semantics: clamp outside the first/last stop, stops kept in
-    insertion order after a stable sort by ratio; at coincident stops the later one wins for t >= ratio."""
+    """RAMP_SIZE premultiplied RGBA8 entries (R | G << 8 | B << 16 | A << 24); entry k is the gradient at
+    t = (k + 1/2) / RAMP_SIZE, looked up without interpolation.  ``colors`` = [{"ratio": 0..1, "color": {r,g,b,a in
+    0..1}}] as compiled (decode-swf-shape.ts:99-105).  Canvas addColorStop semantics: clamp outside the first/last
+    stop, stops kept in insertion order after a stable sort by ratio; at coincident stops the later one wins for
+    t >= ratio.  The straight colour is interpolated in double, rounded to float32, premultiplied and quantised in
+    float32."""
     stops = sorted(
         [(s["ratio"], [s["color"]["r"], s["color"]["g"], s["color"]["b"], s["color"]["a"]]) for s in colors],
         key=lambda s: s[0],
@@ -133,9 +144,9 @@ def gradient_lut(colors, color_space="s-rgb") -> np.ndarray:
     linear = color_space == "linear-rgb"
     if linear:
         stops = [(r, [_srgb_to_linear(c[0]), _srgb_to_linear(c[1]), _srgb_to_linear(c[2]), c[3]]) for r, c in stops]
-    lut = np.zeros((257, 4), dtype=np.float32)
-    for k in range(257):
-        t = k / 256.0
+    lut = np.zeros(RAMP_SIZE, dtype=np.uint32)
+    for k in range(RAMP_SIZE):
+        t = (k + 0.5) / RAMP_SIZE
         j = -1
         for idx, (r, _) in enumerate(stops):
             if r <= t:
@@ -153,7 +164,11 @@ def gradient_lut(colors, color_space="s-rgb") -> np.ndarray:
             col = [c0[i] + (c1[i] - c0[i]) * u for i in range(4)]
         if linear:
             col = [_linear_to_srgb(col[0]), _linear_to_srgb(col[1]), _linear_to_srgb(col[2]), col[3]]
-        lut[k] = col
+        a = np.float32(col[3])
+        o = _q8(a) << 24
+        for c in range(3):
+            o |= _q8(np.float32(col[c]) * a) << (8 * c)
+        lut[k] = o
     return lut
 
 
@@ -222,7 +237,7 @@ class _Builder:
             p.spread = SPREAD[fill["gradient"]["spread"]]
             lut = gradient_lut(fill["gradient"]["colors"], fill["gradient"]["colorSpace"])
             self.keep.append(lut)
-            p.lut = lut.ctypes.data_as(C.POINTER(C.c_float))
+            p.lut = lut.ctypes.data_as(C.POINTER(C.c_uint32))
         else:
             raise NotImplementedError("NotImplementedFillStyle")
         return p

@@ -130,7 +130,7 @@ DefPaint paint_from_fill(const swfr_fill_style &f, bool morph, CompiledDef &def)
       p.type = f.type == SWFR_FILL_LINEAR_GRADIENT ? PAINT_LINEAR : PAINT_FOCAL;
       p.spread = f.gradient.spread;
       p.focal = f.type == SWFR_FILL_FOCAL_GRADIENT ? (double)f.focal_point / 256.0 : 0.0;
-      std::vector<float> ramp;
+      std::vector<uint32_t> ramp;
       bool opaque = false;
       build_ramp(f.gradient.colors, f.gradient.n_colors, f.gradient.color_space == SWFR_COLOR_LINEAR_RGB, false, ramp,
                  &opaque);

@@ -37,7 +37,7 @@ struct DefPaint {
   uint8_t color1[4];
   double matrix[6];  // scale_x, rotate_skew0, rotate_skew1, scale_y, tx, ty  (fill space -> twips)
   double focal;
-  int32_t lut;       // index of the 257-entry ramp in the ramp store, -1 if none
+  int32_t lut;       // index of the gradient's ramp (kRampSize entries) in the ramp store, -1 if none
   uint32_t bitmap_id;
   float bounds[4];   // x_min, y_min, x_max, y_max of the path's control points in twips, both morph states
                      // (x_min > x_max: no segments); the device derives the instance's tile bbox from its corners
@@ -109,7 +109,7 @@ struct CompiledDef {
   // device form
   std::vector<SegMorph> segs;            // static defs use s only
   std::vector<DefPaint> paints;          // one per emitted device path
-  std::vector<std::vector<float>> luts;  // ramps referenced by paints[].lut (local indices)
+  std::vector<std::vector<uint32_t>> luts;  // ramps referenced by paints[].lut (local indices)
   bool has_visible_morph_stroke = false;
   std::vector<MorphLine> morph_lines;    // every line path of a morph shape, in paint order (also invisible ones:
                                          // a zero width keeps the previous one, canvas-renderer.ts:253-256)
@@ -127,8 +127,9 @@ struct StrokeSeg {
 };
 void stroke_commands(const std::vector<Command> &cmds, double width, bool round_style, std::vector<StrokeSeg> &out);
 
-// 257 x 4 straight-RGBA ramp for a gradient.
-void build_ramp(const swfr_color_stop *stops, uint32_t n, bool linear_rgb, bool morph_end, std::vector<float> &out,
+// Gradient ramp: kRampSize premultiplied RGBA8 entries, looked up without interpolation.
+constexpr int kRampSize = 1024;
+void build_ramp(const swfr_color_stop *stops, uint32_t n, bool linear_rgb, bool morph_end, std::vector<uint32_t> &out,
                 bool *all_opaque);
 
 // image/x-swf-bmp format 3 -> straight RGBA8.  Returns a swfr_status.

@@ -772,6 +772,8 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
             pi.ry = (float)dy;
             pi.focal = 1.0f / pi.rx;  // bitmaps: focal / omf carry 1 / rx, 1 / ry
             pi.omf = 1.0f / pi.ry;
+            pi.inv_bw = 1.0f / (float)bm.w;
+            pi.inv_bh = 1.0f / (float)bm.h;
             if (bm.opaque && dp.repeating) flags |= 1u;
           }
         } else {
@@ -780,7 +782,8 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
           if (fp < -0.98) fp = -0.98;
           pi.focal = (float)fp;
           pi.omf = (float)(1.0 - fp * fp);
-          pi.ptr = (unsigned long long)(a.ramps + (size_t)dp.lut * 257 * 4);
+          pi.rx = 1.0f / pi.omf;  // gradients: rx carries 1 / omf
+          pi.ptr = (unsigned long long)(a.ramps + (size_t)dp.lut * kRampSize);
           if (dp.flags & PF_OPAQUE_RAMP) flags |= 1u;
         }
       }
@@ -1410,9 +1413,7 @@ __device__ __forceinline__ void accumulate_row(int xa, int ya, int xb, int yb, i
   float slope = (xbf - xaf) / (ybf - yaf);
   float xlo = fminf(xaf, xbf), xhi = fmaxf(xaf, xbf);
   float ytf = (float)yt * k, ybmf = (float)ybm * k;
-  float t0 = (ytf - yaf) * slope;
-  float t1 = (ybmf - yaf) * slope;
-  float xt = xaf + t0, xm = xaf + t1;
+  float xt = fmaf(ytf - yaf, slope, xaf), xm = fmaf(ybmf - yaf, slope, xaf);
   xt = fminf(fmaxf(xt, xlo), xhi);
   xm = fminf(fmaxf(xm, xlo), xhi);
   float xmin = fminf(xt, xm), xmax = fmaxf(xt, xm);
@@ -1426,7 +1427,7 @@ __device__ __forceinline__ void accumulate_row(int xa, int ya, int xb, int yb, i
     float u0 = fmaxf(fi - xmin, 0.0f);
     float u1 = fminf(fi1 - xmin, w);
     float a0 = (u0 * u0) * inv2w;
-    float a1 = (u1 * u1) * inv2w + fmaxf(fi1 - xmax, 0.0f);
+    float a1 = fmaf(u1 * u1, inv2w, fmaxf(fi1 - xmax, 0.0f));
     float f = a1 - a0;
     f = fminf(fmaxf(f, 0.0f), 1.0f);
     int c = __float2int_rn(Df * f);
@@ -1436,15 +1437,29 @@ __device__ __forceinline__ void accumulate_row(int xa, int ya, int xb, int yb, i
   if (iend < 16) atomicAdd(&acc_row[iend], D - prev);
 }
 
-__device__ __forceinline__ int floormod(int a, int n) {
-  int r = a % n;
+// a mod n in [0, n) for n > 0.  The quotient is estimated in float (inv_n = 1 / n from path setup) and corrected
+// against the exact integer remainder: for |a| < 2^22 the estimate is off by at most one, so the result is the
+// mathematical floor-mod (the oracle's floormod) without the integer division subroutine.
+__device__ __forceinline__ int floormod(int a, int n, float inv_n) {
+  if (a >= 0 && a < n) return a;
+  if (abs(a) < (1 << 22)) {
+    const int q = __float2int_rd((float)a * inv_n);
+    int r = a - q * n;
+    if (r < 0) r += n;
+    if (r >= n) r -= n;
+    return r;
+  }
+  const int r = a % n;
   return r < 0 ? r + n : r;
 }
 
+// Paint of device pixel (X, Y).  Every a*b+c is an explicit fused multiply-add, in the same places as the oracle's
+// eval_paint (C fmaf is correctly rounded, fmaf() here compiles to FFMA; the rest of this file is compiled without
+// contraction), so the colours are the oracle's bit for bit.
 __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) {
-  float xc = (float)X + 0.5f, yc = (float)Y + 0.5f;
-  float gx = (p.inv[0] * xc + p.inv[2] * yc) + p.inv[4];
-  float gy = (p.inv[1] * xc + p.inv[3] * yc) + p.inv[5];
+  const float xc = (float)X + 0.5f, yc = (float)Y + 0.5f;
+  const float gx = fmaf(p.inv[0], xc, fmaf(p.inv[2], yc, p.inv[4]));
+  const float gy = fmaf(p.inv[1], xc, fmaf(p.inv[3], yc, p.inv[5]));
   if (type == PAINT_BITMAP) {
     // box(rx) x box(ry) footprint around the sample point, texel by texel, rows outer / columns inner (the oracle's
     // summation order).  Wrapped texel indices are carried along instead of taking a modulo per tap; 1 / rx and
@@ -1455,8 +1470,8 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
     const float lox = gx - hrx, hix = gx + hrx, loy = gy - hry, hiy = gy + hry;
     const int i0 = (int)floorf(lox), j0 = (int)floorf(loy);
     const bool rep = p.repeating != 0;
-    const int ii0 = rep ? floormod(i0, p.bw) : i0;
-    int jj = rep ? floormod(j0, p.bh) : j0;
+    const int ii0 = rep ? floormod(i0, p.bw, p.inv_bw) : i0;
+    int jj = rep ? floormod(j0, p.bh, p.inv_bh) : j0;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     const int ncol = (int)ceilf(hix) - i0;  // texel columns i0 .. i0 + ncol - 1 are those with (float)i < hix
     if (ncol <= 3) {
@@ -1464,15 +1479,15 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
       // computed once per pixel instead of once per tap; the taps are visited in the same order (rows outer, columns
       // inner) with the same operands, so the sums are the oracle's
       float wxc[3];
-      int ic[3];
+      float xcs[3];
       bool vc[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const int i = i0 + c;
         int t = ii0 + c;
-        if (rep)
-          while (t >= p.bw) t -= p.bw;
-        ic[c] = t;
+        if (rep && t >= p.bw) t -= p.bw;  // bw >= 1 and c <= 2: at most two wraps
+        if (rep && t >= p.bw) t -= p.bw;
+        xcs[c] = (float)t + 0.5f;
         vc[c] = c < ncol && (rep || (i >= 0 && i < p.bw));
         const float vl = fmaxf(lox, (float)i), vh = fminf(hix, (float)(i + 1));
         wxc[c] = fmaxf(vh - vl, 0.0f) * irx;
@@ -1482,44 +1497,44 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
         jj++;
         if (rep && jj == p.bh) jj = 0;
         if (!rep && (j < 0 || j >= p.bh)) continue;
-        float wl = fmaxf(loy, (float)j), wh = fminf(hiy, (float)(j + 1));
-        float wy = fmaxf(wh - wl, 0.0f) * iry;
-        const float yc = (float)jcur + 0.5f;
+        const float wl = fmaxf(loy, (float)j), wh = fminf(hiy, (float)(j + 1));
+        const float wy = fmaxf(wh - wl, 0.0f) * iry;
+        const float ycs = (float)jcur + 0.5f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           if (!vc[c]) continue;
-          uchar4 t = tex2D<uchar4>(tex, (float)ic[c] + 0.5f, yc);
-          float wgt = wxc[c] * wy;
-          acc0 = acc0 + wgt * (float)t.x;
-          acc1 = acc1 + wgt * (float)t.y;
-          acc2 = acc2 + wgt * (float)t.z;
-          acc3 = acc3 + wgt * (float)t.w;
+          const uchar4 t = tex2D<uchar4>(tex, xcs[c], ycs);
+          const float wgt = wxc[c] * wy;
+          acc0 = fmaf(wgt, (float)t.x, acc0);
+          acc1 = fmaf(wgt, (float)t.y, acc1);
+          acc2 = fmaf(wgt, (float)t.z, acc2);
+          acc3 = fmaf(wgt, (float)t.w, acc3);
         }
       }
     } else {
-    for (int j = j0; (float)j < hiy; j++) {
-      const int jcur = jj;
-      jj++;
-      if (rep && jj == p.bh) jj = 0;
-      if (!rep && (j < 0 || j >= p.bh)) continue;
-      float wl = fmaxf(loy, (float)j), wh = fminf(hiy, (float)(j + 1));
-      float wy = fmaxf(wh - wl, 0.0f) * iry;
-      int ii = ii0;
-      for (int i = i0; (float)i < hix; i++) {
-        const int icur = ii;
-        ii++;
-        if (rep && ii == p.bw) ii = 0;
-        if (!rep && (i < 0 || i >= p.bw)) continue;
-        float vl = fmaxf(lox, (float)i), vh = fminf(hix, (float)(i + 1));
-        float wx = fmaxf(vh - vl, 0.0f) * irx;
-        uchar4 t = tex2D<uchar4>(tex, (float)icur + 0.5f, (float)jcur + 0.5f);
-        float wgt = wx * wy;
-        acc0 = acc0 + wgt * (float)t.x;
-        acc1 = acc1 + wgt * (float)t.y;
-        acc2 = acc2 + wgt * (float)t.z;
-        acc3 = acc3 + wgt * (float)t.w;
+      for (int j = j0; (float)j < hiy; j++) {
+        const int jcur = jj;
+        jj++;
+        if (rep && jj == p.bh) jj = 0;
+        if (!rep && (j < 0 || j >= p.bh)) continue;
+        const float wl = fmaxf(loy, (float)j), wh = fminf(hiy, (float)(j + 1));
+        const float wy = fmaxf(wh - wl, 0.0f) * iry;
+        int ii = ii0;
+        for (int i = i0; (float)i < hix; i++) {
+          const int icur = ii;
+          ii++;
+          if (rep && ii == p.bw) ii = 0;
+          if (!rep && (i < 0 || i >= p.bw)) continue;
+          const float vl = fmaxf(lox, (float)i), vh = fminf(hix, (float)(i + 1));
+          const float wx = fmaxf(vh - vl, 0.0f) * irx;
+          const uchar4 t = tex2D<uchar4>(tex, (float)icur + 0.5f, (float)jcur + 0.5f);
+          const float wgt = wx * wy;
+          acc0 = fmaf(wgt, (float)t.x, acc0);
+          acc1 = fmaf(wgt, (float)t.y, acc1);
+          acc2 = fmaf(wgt, (float)t.z, acc2);
+          acc3 = fmaf(wgt, (float)t.w, acc3);
+        }
       }
-    }
     }
     uint32_t o = (uint32_t)__float2int_rn(fminf(fmaxf(acc0, 0.0f), 255.0f));
     o |= (uint32_t)__float2int_rn(fminf(fmaxf(acc1, 0.0f), 255.0f)) << 8;
@@ -1529,17 +1544,15 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
   }
   float t;
   if (type == PAINT_LINEAR) {
-    t = gx * (1.0f / 32768.0f) + 0.5f;
+    t = fmaf(gx, 1.0f / 32768.0f, 0.5f);
   } else {
-    float nx = gx * (1.0f / 16384.0f), ny = gy * (1.0f / 16384.0f);
-    float dx = nx - p.focal;
-    float a = dx * dx;
-    float b = ny * ny;
-    float c = p.omf * b;
-    float disc = a + c;
-    float s = sqrtf(disc);
-    float num = p.focal * dx + s;
-    t = num / p.omf;
+    const float nx = gx * (1.0f / 16384.0f), ny = gy * (1.0f / 16384.0f);
+    const float dx = nx - p.focal;
+    const float c = p.omf * (ny * ny);
+    const float disc = fmaf(dx, dx, c);
+    const float s = sqrtf(disc);
+    const float num = fmaf(p.focal, dx, s);
+    t = num * p.rx;  // gradients: rx carries 1 / omf
   }
   if (p.spread == SWFR_SPREAD_PAD) {
     t = fminf(fmaxf(t, 0.0f), 1.0f);
@@ -1553,21 +1566,9 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
     t = u > 1.0f ? 2.0f - u : u;
     t = fminf(fmaxf(t, 0.0f), 1.0f);
   }
-  float pos = t * 256.0f;
-  int i = (int)floorf(pos);
-  i = min(max(i, 0), 255);
-  float fr = pos - (float)i;
-  const float4 *lut = (const float4 *)p.ptr;
-  float4 l0 = __ldg(lut + i), l1 = __ldg(lut + i + 1);
-  float v0 = l0.x + (l1.x - l0.x) * fr;
-  float v1 = l0.y + (l1.y - l0.y) * fr;
-  float v2 = l0.z + (l1.z - l0.z) * fr;
-  float A = l0.w + (l1.w - l0.w) * fr;
-  uint32_t o = (uint32_t)__float2int_rn(fminf(fmaxf(A * 255.0f, 0.0f), 255.0f)) << 24;
-  o |= (uint32_t)__float2int_rn(fminf(fmaxf((v0 * A) * 255.0f, 0.0f), 255.0f));
-  o |= (uint32_t)__float2int_rn(fminf(fmaxf((v1 * A) * 255.0f, 0.0f), 255.0f)) << 8;
-  o |= (uint32_t)__float2int_rn(fminf(fmaxf((v2 * A) * 255.0f, 0.0f), 255.0f)) << 16;
-  return o;
+  // the ramp holds premultiplied RGBA8 at t = (k + 1/2) / kRampSize: one load, no interpolation
+  const int i = min(max(__float2int_rd(t * (float)kRampSize), 0), kRampSize - 1);
+  return __ldg(reinterpret_cast<const uint32_t *>(p.ptr) + i);
 }
 
 struct Probe {
@@ -1691,7 +1692,9 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
   if (a.totals->overflow | a.totals->overflow_stage) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
+  __shared__ uint4 paint_sh[kFineWarps][sizeof(PaintInst) / 16];  // the paint instance the warp is compositing
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t n_hits = 0, n_recs = 0;  // statistics (swfr_stats.fine_*): per warp, posted once at the end
   int *acc = acc_sh[warp];
   int *cross = cross_sh[warp];
   for (int i = lane; i < 16 * kAccStride; i += 32) acc[i] = 0;
@@ -1735,7 +1738,6 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
 
     // ---- pass 2: composite in paint order ----
     uint32_t px[8];
-    uint32_t n_hits = 0, n_recs = 0;
     const uint32_t bg = __ldg(a.frame_bg + frame);
 #pragma unroll
     for (int i = 0; i < 8; i++) px[i] = bg;
@@ -1782,7 +1784,11 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
           // One copy of the paint code, eight trips.  px[] and the masks are only ever indexed statically (the pixels
           // rotate through px[0], the masks are packed into two words), so both stay in registers: a dynamic index
           // would put them in local memory for the whole kernel.
-          const PaintInst &pi = a.paint_inst[cur_pid];
+          // (staged in shared memory: one 16-byte load by each of five lanes instead of sixteen global loads per pixel)
+          if (lane < (int)(sizeof(PaintInst) / 16))
+            paint_sh[warp][lane] = __ldg(reinterpret_cast<const uint4 *>(a.paint_inst + cur_pid) + lane);
+          __syncwarp();
+          const PaintInst &pi = *reinterpret_cast<const PaintInst *>(paint_sh[warp]);
           uint32_t mlo = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
           uint32_t mhi = m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
 #pragma unroll 1
@@ -1796,14 +1802,11 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
             mlo = __funnelshift_r(mlo, mhi, 8);
             mhi >>= 8;
           }
+          __syncwarp();  // the next paint instance overwrites paint_sh
         }
       }
     }
 
-    if (lane == 0) {  // statistics: what this tile composited (swfr_stats.fine_*)
-      atomicAdd(&a.totals->fine_hits, n_hits);
-      atomicAdd(&a.totals->fine_records, n_recs);
-    }
     // ---- store: 8 pixels = 32 bytes per lane ----
     if (Y < a.height) {
       uint32_t *dst = a.frames + ((size_t)frame * a.height + Y) * a.width + X0;
@@ -1816,6 +1819,10 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
           if (X0 + i < a.width) dst[i] = px[i];
       }
     }
+  }
+  if (lane == 0 && n_hits) {
+    atomicAdd(&a.totals->fine_hits, n_hits);
+    atomicAdd(&a.totals->fine_records, n_recs);
   }
 }
 

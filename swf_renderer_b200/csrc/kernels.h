@@ -44,15 +44,19 @@ struct PathRec {
   uint32_t color;  // premultiplied RGBA8 of a solid paint
 };
 
-// Per path instance paint parameters for non-solid paints: 64 bytes.
+// Per path instance paint parameters for non-solid paints: 80 bytes (five 16-byte words: k_fine stages the
+// instance it composites in shared memory with one load per lane).
 struct PaintInst {
   float inv[6];  // device px -> fill space
   float focal, omf;  // gradients: focal point, 1 - focal^2; bitmaps: 1 / rx, 1 / ry
-  float rx, ry;
+  float rx, ry;      // bitmaps: footprint in texels; gradients: rx = 1 / omf
   unsigned long long ptr;  // ramp pointer (gradients) or texture object (bitmaps)
   int32_t bw, bh;          // bitmap size
   uint32_t spread, repeating;
+  float inv_bw, inv_bh;    // bitmaps: 1 / bw, 1 / bh (float division)
+  uint32_t pad[2];
 };
+static_assert(sizeof(PaintInst) == 80, "PaintInst is staged as five uint4");
 
 struct BitmapDev {
   unsigned long long tex;
@@ -98,7 +102,7 @@ struct RenderArgs {
   const DefPaint *def_paints;
   const SegStatic *segs_dynamic;   // per batch (ITEM_DYNAMIC)
   const DefPaint *paints_dynamic;  // per batch (ITEM_DYNAMIC)
-  const float *ramps;
+  const uint32_t *ramps;  // kRampSize premultiplied RGBA8 entries per gradient
   const BitmapDev *bitmaps;
   uint32_t *seg_edge_off;   // n_seginst + 1 (piece counts, then exclusive scan)
   uint32_t *seg_item;       // n_seginst: draw item of each segment instance

@@ -133,7 +133,7 @@ struct swfr_renderer {
   std::vector<SegStatic> h_static;
   std::vector<SegMorph> h_morph;
   std::vector<DefPaint> h_paints;
-  std::vector<float> h_ramps;
+  std::vector<uint32_t> h_ramps;
   std::vector<DefEntry> shape_defs, morph_defs;
   std::vector<std::shared_ptr<std::vector<MorphLine>>> morph_strokes;  // non-null: the morph shape has visible strokes
   std::vector<std::unique_ptr<CompiledDef>> shape_dbg, morph_dbg;
@@ -259,7 +259,7 @@ int flush_store(swfr_renderer *r) {
   CK(up(r->d_static, r->h_static.data(), sizeof(SegStatic), r->h_static.size(), r->up_static));
   CK(up(r->d_morph, r->h_morph.data(), sizeof(SegMorph), r->h_morph.size(), r->up_morph));
   CK(up(r->d_paints, r->h_paints.data(), sizeof(DefPaint), r->h_paints.size(), r->up_paints));
-  CK(up(r->d_ramps, r->h_ramps.data(), sizeof(float), r->h_ramps.size(), r->up_ramps));
+  CK(up(r->d_ramps, r->h_ramps.data(), sizeof(uint32_t), r->h_ramps.size(), r->up_ramps));
   CK(r->d_static.reserve(256));
   CK(r->d_morph.reserve(256));
   CK(r->d_paints.reserve(256));
@@ -728,7 +728,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.chunk_edge = A.chunk_edge.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
-  a.ramps = r->d_ramps.as<float>();
+  a.ramps = r->d_ramps.as<uint32_t>();
   a.bitmaps = r->d_bitmaps.as<BitmapDev>();
   a.seg_edge_off = A.seg_edge_off.as<uint32_t>();
   a.seg_item = A.seg_item.as<uint32_t>();
@@ -1017,7 +1017,7 @@ int register_def(swfr_renderer *r, const swfr_define_shape *tag, bool morph, uin
   de.paint_first = (uint32_t)r->h_paints.size();
   de.path_count = (uint32_t)def->paints.size();
   de.seg_count = (uint32_t)def->segs.size();
-  size_t ramp_base = r->h_ramps.size() / (257 * 4);
+  size_t ramp_base = r->h_ramps.size() / kRampSize;
   for (auto &l : def->luts) r->h_ramps.insert(r->h_ramps.end(), l.begin(), l.end());
   for (DefPaint p : def->paints) {
     if (p.lut >= 0) p.lut += (int32_t)ramp_base;

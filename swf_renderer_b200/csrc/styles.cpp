@@ -15,7 +15,10 @@ namespace swfr {
 static double srgb_to_linear(double c) { return c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4); }
 static double linear_to_srgb(double c) { return c <= 0.0031308 ? 12.92 * c : 1.055 * std::pow(c, 1.0 / 2.4) - 0.055; }
 
-void build_ramp(const swfr_color_stop *stops_in, uint32_t n, bool linear_rgb, bool morph_end, std::vector<float> &out,
+// kRampSize premultiplied RGBA8 entries; entry k is the gradient at t = (k + 1/2) / kRampSize: straight colour
+// interpolated between the stops in double (linear light for linear-RGB gradients), rounded to float, premultiplied
+// and quantised in float - the arithmetic the oracle's builder repeats (oracle/raster.py: gradient_lut).
+void build_ramp(const swfr_color_stop *stops_in, uint32_t n, bool linear_rgb, bool morph_end, std::vector<uint32_t> &out,
                 bool *all_opaque) {
   struct Stop {
     double ratio;
@@ -32,10 +35,12 @@ void build_ramp(const swfr_color_stop *stops_in, uint32_t n, bool linear_rgb, bo
     stops.push_back(s);
   }
   std::stable_sort(stops.begin(), stops.end(), [](const Stop &a, const Stop &b) { return a.ratio < b.ratio; });
-  out.assign(257 * 4, 0.0f);
+  out.assign(kRampSize, 0u);
   bool opaque = n > 0;
-  for (int k = 0; k <= 256; k++) {
-    double t = k / 256.0;
+  for (const Stop &st : stops)
+    if (st.c[3] != 1.0) opaque = false;
+  for (int k = 0; k < kRampSize; k++) {
+    double t = (k + 0.5) / (double)kRampSize;
     int j = -1;
     for (size_t i = 0; i < stops.size(); i++)
       if (stops[i].ratio <= t) j = (int)i;
@@ -53,8 +58,11 @@ void build_ramp(const swfr_color_stop *stops_in, uint32_t n, bool linear_rgb, bo
     }
     if (linear_rgb)
       for (int c = 0; c < 3; c++) col[c] = linear_to_srgb(col[c]);
-    for (int c = 0; c < 4; c++) out[4 * k + c] = (float)col[c];
-    if (out[4 * k + 3] != 1.0f) opaque = false;
+    const float A = (float)col[3];
+    auto q8 = [](float v) { return (uint32_t)lrintf(fminf(fmaxf(v * 255.0f, 0.0f), 255.0f)); };
+    uint32_t o = q8(A) << 24;
+    for (int c = 0; c < 3; c++) o |= q8((float)col[c] * A) << (8 * c);
+    out[k] = o;
   }
   if (all_opaque) *all_opaque = opaque;
 }

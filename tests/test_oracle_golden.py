@@ -109,10 +109,16 @@ def test_gradient_ramp_endpoints():
         {"ratio": 1.0, "color": {"r": 0, "g": 0, "b": 1, "a": 0.5}},
     ]
     lut = raster.gradient_lut(stops)
-    assert lut.shape == (257, 4)
-    np.testing.assert_allclose(lut[0], [1, 0, 0, 1])
-    np.testing.assert_allclose(lut[256], [0, 0, 1, 0.5])
-    np.testing.assert_allclose(lut[128], [0.5, 0, 0.5, 0.75], atol=1e-6)
+    assert lut.shape == (raster.RAMP_SIZE,) and lut.dtype == np.uint32
+
+    def rgba(v):
+        return [int(v) & 255, (int(v) >> 8) & 255, (int(v) >> 16) & 255, int(v) >> 24]
+
+    # premultiplied RGBA8 at t = (k + 1/2) / size: red -> half-transparent blue
+    assert rgba(lut[0]) == [255, 0, 0, 255]
+    assert rgba(lut[-1]) == [0, 0, 128, 128] or rgba(lut[-1]) == [0, 0, 127, 128]
+    mid = rgba(lut[raster.RAMP_SIZE // 2])
+    assert abs(mid[3] - 191) <= 1 and abs(mid[0] - 95) <= 1 and abs(mid[2] - 96) <= 1 and mid[1] == 0
 
 
 def test_render_morph_golden_at_float_ratio_one_half():

@@ -22,7 +22,7 @@ for V in "$@"; do
   NAME=${V%%:*}
   ENVS=${V#*:}
   [ "$ENVS" = "$V" ] && ENVS=""
-  ( IFS=','; for kv in $ENVS; do export "$kv"; done; timeout 600 python bench.py $SHORT > gpurun_out/bench_${TAG}_$NAME.log 2>&1 )
+  ( for kv in ${ENVS//,/ }; do export "$kv"; done; timeout 600 python bench.py $SHORT > gpurun_out/bench_${TAG}_$NAME.log 2>&1 )
   echo "variant $NAME rc=$?"
   python - gpurun_out/bench_${TAG}_$NAME.log <<'PY'
 import json, sys
