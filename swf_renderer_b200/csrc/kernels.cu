@@ -18,6 +18,19 @@ namespace swfr {
 namespace {
 
 // ======================================================================================================
+// programmatic dependent launch (sm_90+): every kernel of a render is launched with the programmatic stream
+// serialization attribute, so that its blocks may be scheduled while the tail of its predecessor is still running.
+// pdl_enter() is the first statement of such a kernel: it lets the successor be scheduled early in turn
+// (launch_dependents) and then waits until the predecessor grid has completed and its writes are visible (wait) -
+// nothing before it may touch global memory.  Launched without the attribute both instructions do nothing.
+// ======================================================================================================
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  pdl_wait();
+}
+
+// ======================================================================================================
 // integer helpers (same definitions as the oracle)
 // ======================================================================================================
 
@@ -238,6 +251,7 @@ __device__ __forceinline__ uint32_t segment_pid(const RenderArgs &a, const ItemR
 }
 
 __global__ void k_init(RenderArgs a) {
+  pdl_enter();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t stride = gridDim.x * blockDim.x;
   if (i == 0) {
@@ -246,9 +260,7 @@ __global__ void k_init(RenderArgs a) {
     a.totals->error = 0;
     for (int k = 0; k < kMaxFineSlices; k++) a.totals->work[k] = 0;
     a.totals->n_list = 0;
-    a.totals->n_big_chunk = 0;
-    a.totals->n_small_chunk = 0;
-    a.totals->n_alive_items = 0;
+    for (int k = 0; k < kMaxChunks; k++) a.totals->n_big_chunk[k] = a.totals->n_small_chunk[k] = a.totals->n_alive_items[k] = 0;
     a.totals->n_rowent = 0;
     a.totals->n_stage_blocks = 0;
     a.totals->overflow_stage = 0;
@@ -258,6 +270,7 @@ __global__ void k_init(RenderArgs a) {
   for (uint32_t l = i; l < a.n_frames * (uint32_t)a.tiles_y; l += stride) a.row_count[l] = 0;
   for (uint32_t l = i; l < a.caps.stage / kStageBlock; l += stride) a.stage_used[l] = 0;
   for (uint32_t l = i; l < a.n_frames * (uint32_t)(a.tiles_x * a.tiles_y); l += stride) a.tile_cover[l] = 0;
+  for (uint32_t l = i; l < a.n_frames * (uint32_t)a.tiles_y * a.cover_words; l += stride) a.cover_bits[l] = 0;
   for (uint32_t l = i; l < a.n_items; l += stride) a.item_alive[l] = 0;
 }
 
@@ -267,6 +280,7 @@ __global__ void k_init(RenderArgs a) {
 // (With occlusion culling only visible segments are flattened, in no particular order, and k_flatten_emit<false>
 // counts their pieces itself.)
 __global__ void k_flatten_count(RenderArgs a) {
+  pdl_enter();
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t it = warp; it < a.n_items; it += nwarps) {
@@ -286,59 +300,19 @@ __global__ void k_flatten_count(RenderArgs a) {
 
 // Occlusion culling, per depth chunk (chunks are processed from the top one down).  tile_cover[tile] = 1 + the highest
 // path instance found so far that covers the tile completely and opaquely (0 = none); every such path belongs to a
-// chunk above the one being processed, so for the paths of this chunk "covered" is simply tile_cover != 0.
-// k_cover_sat builds, per frame, the summed-area table of OPEN (uncovered) tiles, (tiles_x + 1) x (tiles_y + 1)
-// entries with a zero first row and column: one block per frame, row prefixes then column prefixes.
-__global__ void __launch_bounds__(1024) k_cover_sat(RenderArgs a) {
-  if (a.totals->overflow) return;
-  const uint32_t frame = blockIdx.x;
-  if (frame == 0 && threadIdx.x == 0) {  // the lists of the chunk about to be processed
-    a.totals->n_big_chunk = 0;
-    a.totals->n_small_chunk = 0;
-    a.totals->n_alive_items = 0;
-  }
-  const int tx = a.tiles_x, ty = a.tiles_y, sw = tx + 1;
-  const uint32_t *cover = a.tile_cover + frame * (uint32_t)(tx * ty);
-  uint32_t *sat = a.cover_sat + (size_t)frame * (size_t)sw * (size_t)(ty + 1);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int x = threadIdx.x; x < sw; x += blockDim.x) sat[x] = 0;
-  for (int y = w; y < ty; y += nw) {  // row prefixes: one warp per row, 32 tiles per step
-    uint32_t *row = sat + (size_t)(y + 1) * sw;
-    if (lane == 0) row[0] = 0;
-    uint32_t carry = 0;
-    for (int x0 = 0; x0 < tx; x0 += 32) {
-      const int x = x0 + lane;
-      uint32_t v = (x < tx && cover[y * tx + x] == 0) ? 1u : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-      }
-      v += carry;
-      if (x < tx) row[x + 1] = v;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-    }
-  }
-  __syncthreads();
-  for (int x = threadIdx.x + 1; x < sw; x += blockDim.x) {  // column prefixes: coalesced across threads, 8 loads in flight
-    uint32_t run = 0;
-    for (int y0 = 1; y0 <= ty; y0 += 8) {
-      uint32_t v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = y0 + k <= ty ? sat[(size_t)(y0 + k) * sw + x] : 0u;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        run += v[k];
-        if (y0 + k <= ty) sat[(size_t)(y0 + k) * sw + x] = run;
-      }
-    }
-  }
-}
-
-// A path of this chunk is still alive when at least one tile of its bbox is open (one summed-area query).  Alive paths
-// get their slots cleared here (one warp per path, coalesced); dead paths are not flattened, not binned, get no
-// records, and their slots are never read (k_fine checks path_alive first).
-__global__ void k_path_alive(RenderArgs a, uint32_t c) {
+// chunk above the one being processed, so for the paths of this chunk "covered" is simply tile_cover != 0.  The same
+// fact is kept as one bit per tile (cover_bits: cover_words 32-bit words per tile row, bit set = covered), which is
+// what the visibility test of a whole path reads.
+//
+// k_path_alive, one THREAD per path instance of the chunk: the path is alive when at least one tile of its bbox is
+// open, and its tile grid shrinks to the bounding box of its open tiles - what lies outside is clipped exactly like
+// geometry outside the viewport (edges left of the grid still post their winding, see band_setup), so fewer slots are
+// cleared, scanned and probed.  Dead paths are not flattened, not binned, get no records, and their slots are never
+// read (k_fine checks path_alive first).  The lists of the chunk (draw items with a visible path for the flattener,
+// visible paths with small / large grids for k_cover) are appended with one atomic per warp and list; the slots of the
+// visible paths are then cleared by the whole warp, path by path (coalesced).
+__global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
+  pdl_enter();
   if (a.totals->overflow) return;
   const uint32_t frame = blockIdx.y;
   const uint32_t i0 = chunk_first(a, c, frame), i1 = chunk_first(a, c + 1, frame);
@@ -346,38 +320,86 @@ __global__ void k_path_alive(RenderArgs a, uint32_t c) {
   if (blockIdx.x == 0 && frame == 0 && threadIdx.x == 0) a.chunk_edge[c] = a.totals->n_edges;
   const uint32_t p0 = __ldg(a.item_path_off + i0), p1 = __ldg(a.item_path_off + i1);
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int sw = a.tiles_x + 1;
-  const uint32_t *sat = a.cover_sat + (size_t)frame * (size_t)sw * (size_t)(a.tiles_y + 1);
-  for (uint32_t pid = p0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); pid < p1; pid += nwarps) {
-    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));
-    const int bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
-    // without culling (one chunk) every path is emitted, also those outside the viewport: the edge tap lists them all
-    bool alive = bw > 0 || a.n_chunks == 1;
-    if (alive && c + 1 != a.n_chunks) {  // nothing has been binned above the top chunk
-      const uint32_t open = __ldg(sat + (size_t)(by0 + bh) * sw + bx0 + bw) - __ldg(sat + (size_t)by0 * sw + bx0 + bw) -
-                            __ldg(sat + (size_t)(by0 + bh) * sw + bx0) + __ldg(sat + (size_t)by0 * sw + bx0);
-      alive = open != 0;
-    }
-    if (lane == 0) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t *bits = a.cover_bits + (size_t)frame * (size_t)a.tiles_y * a.cover_words;
+  const bool top = c + 1 == a.n_chunks;  // nothing has been binned above the top chunk
+  for (uint32_t base = p0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p1; base += stride) {
+    const uint32_t pid = base + lane;
+    bool alive = false;
+    uint32_t s0 = 0, n = 0, it = 0;
+    if (pid < p1) {
+      const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));
+      int bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
+      // without culling (one chunk) every path is emitted, also those outside the viewport: the edge tap lists them all
+      alive = bw > 0 || a.n_chunks == 1;
+      if (alive && !top) {
+        int cmin = INT_MAX, cmax = -1, rmin = INT_MAX, rmax = -1;
+        const int w0 = bx0 >> 5, w1 = (bx0 + bw - 1) >> 5;
+        for (int y = by0; y < by0 + bh; y++) {
+          const uint32_t *row = bits + (size_t)y * a.cover_words;
+          bool any = false;
+          for (int w = w0; w <= w1; w++) {
+            uint32_t open = ~__ldg(row + w);
+            if (w == w0) open &= 0xffffffffu << (bx0 & 31);
+            if (w == w1) open &= 0xffffffffu >> (31 - ((bx0 + bw - 1) & 31));
+            if (open) {
+              any = true;
+              cmin = min(cmin, w * 32 + __ffs(open) - 1);
+              cmax = max(cmax, w * 32 + 31 - __clz(open));
+            }
+          }
+          if (any) {
+            rmin = min(rmin, y);
+            rmax = y;
+          }
+        }
+        alive = cmax >= 0;
+        if (alive && (cmin != bx0 || rmin != by0 || cmax - cmin + 1 != bw || rmax - rmin + 1 != bh)) {
+          bx0 = cmin, by0 = rmin, bw = cmax - cmin + 1, bh = rmax - rmin + 1;
+          *reinterpret_cast<uint2 *>(a.path_rec + pid) = make_uint2((uint32_t)bx0 | ((uint32_t)by0 << 16), (uint32_t)bw | ((uint32_t)bh << 16));
+        }
+      }
       a.path_alive[pid] = alive ? 1u : 0u;
       a.path_rec_base[pid] = 0;
       if (alive) {
-        // the draw items with something visible: k_flatten_emit<false> walks this list (one entry per item)
-        const uint32_t it = a.path_item[pid];
-        if (atomicExch(&a.item_alive[it], 1u) == 0u) a.alive_items[atomicAdd(&a.totals->n_alive_items, 1u)] = it;
-        // the chunk's visible paths for k_cover: small tile grids are scanned by one warp each, large ones by a block
-        if (bw * bh > kBackdropSmall)
-          a.big_chunk[atomicAdd(&a.totals->n_big_chunk, 1u)] = pid;
-        else if (bw * bh > 0)
-          a.small_chunk[atomicAdd(&a.totals->n_small_chunk, 1u)] = pid;
+        n = (uint32_t)(bw * bh);
+        s0 = a.path_slot_off[pid];
+        it = a.path_item[pid];
       }
     }
+    const uint32_t amask = __ballot_sync(0xffffffffu, alive);
+    if (amask == 0) continue;
+    // the draw items with something visible: k_flatten_emit<false> walks this list (one entry per item).  The paths of
+    // an item are neighbours: one lane per distinct item of the warp claims it.
+    bool claim = false;
     if (alive) {
-      const uint32_t s0 = a.path_slot_off[pid], n = (uint32_t)(bw * bh);
-      for (uint32_t i = lane; i < n; i += 32) {
-        a.slot_count[s0 + i] = 0;
-        a.slot_backdrop[s0 + i] = 0;
+      const uint32_t same = __match_any_sync(amask, it);
+      if ((uint32_t)(__ffs(same) - 1) == lane) claim = atomicExch(&a.item_alive[it], 1u) == 0u;
+    }
+    // the chunk's visible paths for k_cover: small tile grids are scanned by one warp each, large ones by a block
+    const bool big = alive && n > (uint32_t)kBackdropSmall, small = alive && n > 0 && !big;
+    const uint32_t m_item = __ballot_sync(0xffffffffu, claim), m_big = __ballot_sync(0xffffffffu, big),
+                   m_small = __ballot_sync(0xffffffffu, small);
+    uint32_t b_item = 0, b_big = 0, b_small = 0;
+    if (lane == 0) {
+      if (m_item) b_item = atomicAdd(&a.totals->n_alive_items[c], (uint32_t)__popc(m_item));
+      if (m_big) b_big = atomicAdd(&a.totals->n_big_chunk[c], (uint32_t)__popc(m_big));
+      if (m_small) b_small = atomicAdd(&a.totals->n_small_chunk[c], (uint32_t)__popc(m_small));
+    }
+    b_item = __shfl_sync(0xffffffffu, b_item, 0);
+    b_big = __shfl_sync(0xffffffffu, b_big, 0);
+    b_small = __shfl_sync(0xffffffffu, b_small, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (claim) a.alive_items[b_item + __popc(m_item & below)] = it;
+    if (big) a.big_chunk[b_big + __popc(m_big & below)] = pid;
+    if (small) a.small_chunk[b_small + __popc(m_small & below)] = pid;
+    // clear the slots of the visible paths
+    for (uint32_t m = amask; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      const uint32_t ps0 = __shfl_sync(0xffffffffu, s0, src), pn = __shfl_sync(0xffffffffu, n, src);
+      for (uint32_t i = lane; i < pn; i += 32) {
+        a.slot_count[ps0 + i] = 0;
+        a.slot_backdrop[ps0 + i] = 0;
       }
     }
   }
@@ -488,6 +510,7 @@ __device__ __forceinline__ void emit_segments(const RenderArgs &a, int (*sh_p)[6
 
 template <bool ORDERED>
 __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, uint32_t c) {
+  pdl_enter();
   if (a.totals->overflow) return;
   __shared__ int sh_p[kEmitWarps][32][6];
   __shared__ double sh_inv[kEmitWarps][32];
@@ -502,7 +525,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
       emit_segments<true>(a, sh_p[w], sh_inv[w], sh_pid[w], lane, base + lane, base + lane < s_end, 0u);
   } else {
     // the draw items of the chunk with a visible path (listed by k_path_alive), one warp per item
-    const uint32_t n_alive = a.totals->n_alive_items;
+    const uint32_t n_alive = a.totals->n_alive_items[c];
     const uint32_t nwarps = gridDim.x * gridDim.y * kEmitWarps;
     for (uint32_t ai = (blockIdx.y * gridDim.x + blockIdx.x) * kEmitWarps + w; ai < n_alive; ai += nwarps) {
       const uint32_t it = a.alive_items[ai];
@@ -539,6 +562,7 @@ __device__ __forceinline__ uint32_t block_reduce(uint32_t v, uint32_t *sh) {
 // n = n_ptr ? min(*n_ptr, n_cap) : n_cap.  src and dst may alias (in-place scan).
 __global__ void k_scan_partials(const uint32_t *__restrict__ src, const uint32_t *n_ptr, uint32_t n_cap,
                                 uint32_t *partials) {
+  pdl_enter();
   __shared__ uint32_t sh[32];
   uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
   uint32_t chunk = scan_chunk(n);
@@ -576,6 +600,7 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *sh, ui
 __global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *partials, uint32_t *dst, const uint32_t *n_ptr,
                                                     uint32_t n_cap, uint32_t *total_out, uint32_t total_cap,
                                                     uint32_t *overflow, uint32_t overflow_bit) {
+  pdl_enter();
   __shared__ uint32_t sh[32];
   uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
   uint32_t v = threadIdx.x < (uint32_t)kScanBlocks ? partials[threadIdx.x] : 0u;
@@ -591,6 +616,7 @@ __global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *partials, uint32_
 
 __global__ void k_scan_apply(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, uint32_t n_cap,
                              const uint32_t *partials) {
+  pdl_enter();
   __shared__ uint32_t sh[32];
   uint32_t n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
   uint32_t chunk = scan_chunk(n);
@@ -617,6 +643,7 @@ __global__ void k_scan_apply(const uint32_t *src, uint32_t *dst, const uint32_t 
 constexpr uint32_t kScanSmallMax = 16384;
 __global__ void __launch_bounds__(1024) k_scan_small(const uint32_t *src, uint32_t *dst, uint32_t n, uint32_t *total_out,
                                                     uint32_t total_cap, uint32_t *overflow, uint32_t overflow_bit) {
+  pdl_enter();
   __shared__ uint32_t sh[32];
   uint32_t carry = 0;
   for (uint32_t base = 0; base < n; base += 4096) {
@@ -671,6 +698,7 @@ __device__ uint32_t morph_solid(const uint8_t *c0, const uint8_t *c1, double r) 
 constexpr int kMaxTileRows = 1024;  // frames up to 16384 px high
 
 __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
+  pdl_enter();
   // candidate lists, step 0: how many path instances touch each tile row of the frame.  Counted in shared memory
   // for the frame of the block's first path (a block of consecutive paths rarely spans two frames; the others go
   // straight to global memory), then flushed with one atomic per non-empty row.
@@ -821,6 +849,7 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
 // The visible path instances of every frame, in paint order (ordered compaction, one block per frame): what the row
 // lists are built from.
 __global__ void __launch_bounds__(1024) k_alive_paths(RenderArgs a) {
+  pdl_enter();
   if (a.totals->overflow) return;
   __shared__ uint32_t sh_warp[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -853,6 +882,7 @@ constexpr int kRowThreads = 256;
 constexpr int kMaxGroups = 512;  // tile columns <= 4096: frames up to 65536 px wide
 
 __global__ void __launch_bounds__(kRowThreads) k_row_lists(RenderArgs a) {
+  pdl_enter();
   if (a.totals->overflow) return;
   __shared__ uint32_t sh_warp[kRowThreads / 32];
   __shared__ uint32_t sh_grp[kMaxGroups];
@@ -902,6 +932,7 @@ __global__ void __launch_bounds__(kRowThreads) k_row_lists(RenderArgs a) {
 }
 
 __global__ void k_group_lists(RenderArgs a) {
+  pdl_enter();
   if (a.totals->overflow) return;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1045,6 +1076,7 @@ constexpr int kBinWarps = 8;
 
 template <bool ORDERED>
 __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c) {
+  pdl_enter();
   if (a.totals->overflow) return;
   __shared__ uint32_t sh_cover[kBinWarps][32];  // per edge: first tile of its frame in the cover map
   __shared__ int4 sh_edge[kBinWarps][32];
@@ -1066,6 +1098,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
   }
   const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
   uint32_t blk = 0, blk_used = kStageBlock;  // current staging block of this warp (none yet)
+  uint32_t next_blk = 0;                     // lane 0: the block taken in advance
   bool have_blk = false, stage_full = false;
   for (uint32_t base = e_begin + (blockIdx.x * kBinWarps + w) * 32; base < e_end; base += stride) {
     const uint32_t e = base + lane;
@@ -1169,9 +1202,11 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
         const uint32_t kcount = __popc(kmask);
         if (!have_blk || blk_used + kcount > kStageBlock) {  // next staging block of this warp
           if (have_blk && !stage_full && lane == 0) a.stage_used[blk] = blk_used;
-          uint32_t nb2 = 0;
-          if (lane == 0) nb2 = atomicAdd(&a.totals->n_stage_blocks, 1u);
-          blk = __shfl_sync(0xffffffffu, nb2, 0);
+          // the block after the first one was asked for when its predecessor was taken (lane 0 holds the answer in
+          // next_blk): the round trip of the returning atomic is over by the time the block is needed
+          if (lane == 0 && !have_blk) next_blk = atomicAdd(&a.totals->n_stage_blocks, 1u);
+          blk = __shfl_sync(0xffffffffu, next_blk, 0);
+          if (lane == 0) next_blk = atomicAdd(&a.totals->n_stage_blocks, 1u);
           if (blk >= cap_blocks) {
             if (lane == 0) atomicOr(&a.totals->overflow_stage, 1u);
             stage_full = true;
@@ -1200,6 +1235,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
 // path's base); the counts of pass 1 double as cursors and run back down to zero (order inside a slot is irrelevant:
 // coverage accumulation is integer).
 __global__ void k_scatter(RenderArgs a) {
+  pdl_enter();
   if (a.totals->overflow | a.totals->overflow_stage) return;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1236,7 +1272,8 @@ __device__ __forceinline__ uint32_t alloc_records(const RenderArgs &a, uint32_t 
 //             tile_cover for every slot without records and with a non-zero winding number (a full-tile cover);
 //   COUNT:    inclusive prefix of the record counts -> slot_off, total -> record allocation.
 template <bool BACKDROP, bool COUNT>
-__device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pid, const uint4 rec, uint32_t lane, uint32_t *cover) {
+__device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pid, const uint4 rec, uint32_t lane, uint32_t *cover,
+                                                uint32_t *cover_bits) {
   const int bx0 = rec.x & 0xffff, by0 = rec.x >> 16, bw = rec.y & 0xffff, bh = rec.y >> 16;
   const bool opaque = (rec.z >> 8) & 1u;
   const int n = bw * bh;
@@ -1287,7 +1324,10 @@ __device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pi
           carry_row = __shfl_sync(0xffffffffu, row, 31);
         }
         // an opaque path covers this tile completely: it hides the chunks below
-        if (ok && opaque && c4[u] == 0 && v != 0) atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + col, pid + 1u);
+        if (ok && opaque && c4[u] == 0 && v != 0) {
+          atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + col, pid + 1u);
+          atomicOr(cover_bits + (size_t)(by0 + row) * a.cover_words + ((bx0 + col) >> 5), 1u << ((bx0 + col) & 31));
+        }
       }
     }
   }
@@ -1297,7 +1337,8 @@ __device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pi
 // The same for a path instance with a larger tile grid, by one block: warps over rows for the backdrop, a block-wide
 // prefix for the counts.
 template <bool BACKDROP, bool COUNT>
-__device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid, const uint4 rec, uint32_t *cover, uint32_t *sh) {
+__device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid, const uint4 rec, uint32_t *cover, uint32_t *cover_bits,
+                                              uint32_t *sh) {
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int bx0 = rec.x & 0xffff, by0 = rec.x >> 16, bw = rec.y & 0xffff, bh = rec.y >> 16;
   const bool opaque = (rec.z >> 8) & 1u;
@@ -1318,7 +1359,10 @@ __device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid,
         v += carry;
         if (x < bw) {
           q[x] = v;
-          if (opaque && v != 0 && cq[x] == 0) atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + x, pid + 1u);
+          if (opaque && v != 0 && cq[x] == 0) {
+            atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + x, pid + 1u);
+            atomicOr(cover_bits + (size_t)(by0 + row) * a.cover_words + ((bx0 + x) >> 5), 1u << ((bx0 + x) & 31));
+          }
         }
         carry = __shfl_sync(0xffffffffu, v, 31);
       }
@@ -1354,25 +1398,28 @@ constexpr int kCoverBigBlocks = kNumSM * 8;  // blocks that serve the large-grid
 // (alloc_records): record space is allocated path by path, so there is no global scan over the (much longer) slot
 // array.  grid = small-path blocks + kCoverBigBlocks.
 __global__ void __launch_bounds__(256) k_cover(RenderArgs a, uint32_t c) {
+  pdl_enter();
   if (a.totals->overflow) return;
   __shared__ uint32_t sh[32];
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
   const uint32_t small_blocks = gridDim.x - kCoverBigBlocks;
   if (blockIdx.x < small_blocks) {
-    const uint32_t n_small = a.totals->n_small_chunk;  // the chunk's visible paths with small grids (k_path_alive)
+    const uint32_t n_small = a.totals->n_small_chunk[c];  // the chunk's visible paths with small grids (k_path_alive)
     const uint32_t nwarps = (small_blocks * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_small; i += nwarps) {
       const uint32_t pid = a.small_chunk[i];
       const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
-      small_path_scan<true, true>(a, pid, rec, lane, a.tile_cover + (rec.z >> 16) * tiles);
+      small_path_scan<true, true>(a, pid, rec, lane, a.tile_cover + (rec.z >> 16) * tiles,
+                                  a.cover_bits + (size_t)(rec.z >> 16) * a.tiles_y * a.cover_words);
     }
   } else {
-    const uint32_t n_big = a.totals->n_big_chunk;  // ... with large grids
+    const uint32_t n_big = a.totals->n_big_chunk[c];  // ... with large grids
     for (uint32_t bi = blockIdx.x - small_blocks; bi < n_big; bi += kCoverBigBlocks) {
       const uint32_t pid = a.big_chunk[bi];
       const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(a.path_rec + pid));
-      big_path_scan<true, true>(a, pid, rec, a.tile_cover + (rec.z >> 16) * tiles, sh);
+      big_path_scan<true, true>(a, pid, rec, a.tile_cover + (rec.z >> 16) * tiles,
+                                a.cover_bits + (size_t)(rec.z >> 16) * a.tiles_y * a.cover_words, sh);
     }
   }
 }
@@ -1689,6 +1736,7 @@ __device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, 
 // Four resident blocks per SM (64 registers per thread): measured best - 3 blocks at 80 registers 0.75 ms per launch,
 // 4 at 64 0.54, 5 at 48 and 6 at 40 0.56 (1080p / 10 k shapes, 16 frames per launch).
 __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
+  pdl_wait();  // (no launch_dependents: the successor's blocks would only squat in the slots the tail frees)
   if (a.totals->overflow | a.totals->overflow_stage) return;
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
@@ -1901,17 +1949,37 @@ __global__ void k_tile_counts(RenderArgs a, uint32_t frame, uint32_t *counts) {
 // launchers
 // ======================================================================================================
 
+// Launch with the programmatic stream serialization attribute (see pdl_enter); SWFR_PDL=0 launches plainly.
+static const bool g_pdl = [] {
+  const char *e = getenv("SWFR_PDL");
+  return !(e && atoi(e) == 0);
+}();
+template <class... P, class... A>
+static void launch_k(void (*kern)(P...), dim3 grid, dim3 block, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, P(args)...);
+}
+
 static void scan_u32(const uint32_t *src, uint32_t *dst, const uint32_t *n_ptr, uint32_t n_cap, uint32_t *tmp,
                      uint32_t *total_out, uint32_t total_cap, uint32_t *overflow, uint32_t bit, cudaStream_t st,
                      int &launches) {
   if (!n_ptr && n_cap <= kScanSmallMax) {
-    k_scan_small<<<1, 1024, 0, st>>>(src, dst, n_cap, total_out, total_cap, overflow, bit);
+    launch_k(k_scan_small, dim3(1), dim3(1024), st, src, dst, n_cap, total_out, total_cap, overflow, bit);
     launches += 1;
     return;
   }
-  k_scan_partials<<<kScanBlocks, kScanThreads, 0, st>>>(src, n_ptr, n_cap, tmp);
-  k_scan_spine<<<1, 1024, 0, st>>>(tmp, dst, n_ptr, n_cap, total_out, total_cap, overflow, bit);
-  k_scan_apply<<<kScanBlocks, kScanThreads, 0, st>>>(src, dst, n_ptr, n_cap, tmp);
+  launch_k(k_scan_partials, dim3(kScanBlocks), dim3(kScanThreads), st, src, n_ptr, n_cap, tmp);
+  launch_k(k_scan_spine, dim3(1), dim3(1024), st, tmp, dst, n_ptr, n_cap, total_out, total_cap, overflow, bit);
+  launch_k(k_scan_apply, dim3(kScanBlocks), dim3(kScanThreads), st, src, dst, n_ptr, n_cap, tmp);
   launches += 3;
 }
 
@@ -1934,14 +2002,14 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   };
   const unsigned wide = kNumSM * 16;
   mark(0);
-  k_init<<<grid_for(a.n_paths), T, 0, st>>>(a);
+  launch_k(k_init, dim3(grid_for(a.n_paths)), dim3(T), st, a);
   launches++;
   // One depth chunk: every path is flattened, edges in segment order (the taps' mode).  More: only what is visible is
   // flattened, unordered, chunk by chunk.
   const bool ordered = a.n_chunks == 1;
   if (a.n_seginst) {
     if (ordered) {
-      k_flatten_count<<<grid_for((uint64_t)a.n_items * 32), T, 0, st>>>(a);
+      launch_k(k_flatten_count, dim3(grid_for((uint64_t)a.n_items * 32)), dim3(T), st, a);
       launches++;
     }
   }
@@ -1952,7 +2020,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
              1u, st, launches);
   mark(2);
   if (a.n_paths) {
-    k_path_setup<<<grid_for(a.n_paths), T, 0, st>>>(a);
+    launch_k(k_path_setup, dim3(grid_for(a.n_paths)), dim3(T), st, a);
     launches++;
   }
   scan_u32(a.path_slot_off, a.path_slot_off, nullptr, a.n_paths, a.scan_tmp, &a.totals->n_slots, a.caps.slots, &a.totals->overflow, 2u,
@@ -1964,34 +2032,30 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
     const unsigned per_frame = std::max(1u, wide / std::max(1u, a.n_frames));
     const dim3 g2(per_frame, a.n_frames);
     for (uint32_t c = a.n_chunks; c-- > 0;) {
-      if (c + 1 != a.n_chunks) {
-        k_cover_sat<<<a.n_frames, 1024, 0, st>>>(a);
-        launches++;
-      }
-      k_path_alive<<<g2, T, 0, st>>>(a, c);
+      launch_k(k_path_alive, dim3(g2), dim3(T), st, a, c);
       if (ordered) {
-        k_flatten_emit<true><<<g2, kEmitWarps * 32, 0, st>>>(a, c);
-        k_bin<true><<<g2, kBinWarps * 32, 0, st>>>(a, c);
+        launch_k(k_flatten_emit<true>, dim3(g2), dim3(kEmitWarps * 32), st, a, c);
+        launch_k(k_bin<true>, dim3(g2), dim3(kBinWarps * 32), st, a, c);
       } else {
-        k_flatten_emit<false><<<g2, kEmitWarps * 32, 0, st>>>(a, c);
-        k_bin<false><<<wide, kBinWarps * 32, 0, st>>>(a, c);
+        launch_k(k_flatten_emit<false>, dim3(g2), dim3(kEmitWarps * 32), st, a, c);
+        launch_k(k_bin<false>, dim3(wide), dim3(kBinWarps * 32), st, a, c);
       }
-      k_cover<<<wide + kCoverBigBlocks, T, 0, st>>>(a, c);
+      launch_k(k_cover, dim3(wide + kCoverBigBlocks), dim3(T), st, a, c);
       launches += 4;
     }
-    k_scatter<<<wide, T, 0, st>>>(a);
+    launch_k(k_scatter, dim3(wide), dim3(T), st, a);
     launches++;
   }
   mark(4);
   // candidate lists of the visible paths (for k_fine): row counts (from path setup) -> row lists -> group counts -> group lists
   scan_u32(a.row_count, a.row_off, nullptr, a.n_frames * (uint32_t)a.tiles_y, a.scan_tmp, &a.totals->n_rowent, a.caps.rows,
            &a.totals->overflow, 16u, st, launches);
-  k_alive_paths<<<(unsigned)std::min<uint32_t>(a.n_frames, kNumSM * 8), 1024, 0, st>>>(a);
-  k_row_lists<<<(unsigned)std::min<uint32_t>(a.n_frames * (uint32_t)a.tiles_y, kNumSM * 8), kRowThreads, 0, st>>>(a);
+  launch_k(k_alive_paths, dim3((unsigned)std::min<uint32_t>(a.n_frames, kNumSM * 8)), dim3(1024), st, a);
+  launch_k(k_row_lists, dim3((unsigned)std::min<uint32_t>(a.n_frames * (uint32_t)a.tiles_y, kNumSM * 8)), dim3(kRowThreads), st, a);
   launches += 2;
   scan_u32(a.list_off, a.list_off, nullptr, a.n_lists, a.scan_tmp, &a.totals->n_list, a.caps.list, &a.totals->overflow, 8u, st,
            launches);
-  k_group_lists<<<grid_for((uint64_t)a.n_lists * 32), T, 0, st>>>(a);
+  launch_k(k_group_lists, dim3(grid_for((uint64_t)a.n_lists * 32)), dim3(T), st, a);
   launches++;
   mark(5);
   static const int fine_blocks = [] {
@@ -2002,7 +2066,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   {
     const uint32_t fs = fine_slice_frames(a.n_frames), ns = fine_slices(a.n_frames);
     for (uint32_t k = 0; k < ns; k++) {
-      k_fine<<<kNumSM * fine_blocks, kFineWarps * 32, 0, st>>>(a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
+      launch_k(k_fine, dim3(kNumSM * fine_blocks), dim3(kFineWarps * 32), st, a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
       launches++;
       if (slice_done) cudaEventRecord(slice_done[k], st);
     }

@@ -15,6 +15,7 @@ constexpr int kMaxLenFx = 16384;   // flattened edges span at most 64 px per axi
 constexpr int kNumSM = 148;        // B200
 constexpr int kGroupTiles = 8;     // tile columns per candidate list (128 px)
 constexpr int kStageBlock = 256;   // staging entries per block (blocks are private to one warp of the binning pass)
+constexpr int kMaxChunks = 8;      // depth chunks for occlusion culling
 constexpr int kBackdropSmall = 1024;  // grids up to this many slots get their backdrop prefix from one warp
 
 // One draw item after host flattening of the stage: 48 bytes.
@@ -74,9 +75,9 @@ struct Totals {
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work[kMaxFineSlices];  // fine-kernel tile queues, one per slice of frames
   uint32_t n_list;    // candidate-list entries
-  uint32_t n_big_chunk;  // visible path instances with large tile grids in the depth chunk being processed
-  uint32_t n_small_chunk;  // ... with small tile grids
-  uint32_t n_alive_items;  // draw items with a visible path in the depth chunk being processed
+  uint32_t n_big_chunk[8];    // per depth chunk: visible path instances with large tile grids
+  uint32_t n_small_chunk[8];  // ... with small tile grids
+  uint32_t n_alive_items[8];  // ... draw items with a visible path
   uint32_t n_rowent;  // row-list entries
   uint32_t n_stage_blocks;  // staging blocks handed out by the binning pass
   uint32_t overflow_stage;  // the staging buffer was too small (found while binning, after the scans)
@@ -125,7 +126,8 @@ struct RenderArgs {
   const uint32_t *chunk_items;  // (n_chunks + 1) * n_frames: first item of chunk c in frame f at [c * n_frames + f]
   uint32_t *tile_cover;         // n_frames * tiles: 1 + the highest path instance that covers the tile opaquely, 0 = none
   uint32_t *path_alive;         // n_paths: 0 when every tile of the path's bbox is covered from above
-  uint32_t *cover_sat;          // n_frames * (tiles_x + 1) * (tiles_y + 1): summed-area table of uncovered tiles
+  uint32_t *cover_bits;         // n_frames * tiles_y * cover_words: one bit per tile, set when tile_cover != 0
+  uint32_t cover_words;         // host-known: 32-bit words per tile row = ceil(tiles_x / 32)
   uint32_t *chunk_edge;         // kMaxChunks + 1: edge cursor at the start of each depth chunk (unordered edges)
   uint32_t *frames;         // n_frames * width * height
   uint32_t *scan_tmp;       // >= 4096 words
@@ -149,10 +151,10 @@ struct RenderArgs {
 };
 
 // Pipeline stages as seen by the profiler hooks (swfr_get_stage_times).
+static_assert(kMaxChunks == 8, "Totals holds 8 per-chunk counters");
 constexpr int kNumStages = 6;
 const char *stage_name(int i);
 
-constexpr int kMaxChunks = 8;
 
 // Enqueues every kernel of one render on `stream`; returns the number of kernels launched.
 // `ev` (optional) points at kNumStages + 1 events recorded at the stage boundaries.

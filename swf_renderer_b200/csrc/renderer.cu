@@ -146,7 +146,7 @@ struct swfr_renderer {
   // Arenas: consecutive passes of a batch alternate between them and between the pass streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
-    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_sat, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
+    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_bits, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
@@ -627,7 +627,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
     want.rows = std::max<uint32_t>(want.rows, std::max<uint32_t>(1u << 16, max_paths * 8));
     // staging: the records, plus one partly filled block per binning warp (at most kNumSM * 16 * 8 warps, one per 32 edges)
     uint64_t warps = std::min<uint64_t>((uint64_t)kNumSM * 16 * 8, (uint64_t)want.edges / 32 + 1);
-    uint64_t st = (uint64_t)want.records + want.records / 4 + warps * kStageBlock + 65535u;
+    uint64_t st = (uint64_t)want.records + want.records / 4 + 2 * warps * kStageBlock + 65535u;  // a partly filled block + one taken in advance per warp
     want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(st & ~255ull, 0xffffff00ull));
   }
   const uint32_t groups_x = (r->tiles_x + kGroupTiles - 1) / kGroupTiles;
@@ -662,7 +662,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
       need(A.alive_paths, (size_t)max_paths * 4 + 256);
       need(A.alive_count, (size_t)max_frames * 4 + 256);
       need(A.tile_cover, (size_t)max_frames * tiles * 4 + 256);
-      need(A.cover_sat, (size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256);
+      need(A.cover_bits, (size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256);
       need(A.scan_tmp, 8192 * 4);
       need(A.chunk_edge, 64 * 4);
       need(A.list_off, (max_lists + 1) * 4 + 256);
@@ -724,7 +724,8 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.chunk_items = b.d_chunk_items.as<uint32_t>() + p.chunk_at;
   a.tile_cover = A.tile_cover.as<uint32_t>();
   a.path_alive = A.path_alive.as<uint32_t>();
-  a.cover_sat = A.cover_sat.as<uint32_t>();
+  a.cover_bits = A.cover_bits.as<uint32_t>();
+  a.cover_words = (r->tiles_x + 31) / 32;
   a.chunk_edge = A.chunk_edge.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
