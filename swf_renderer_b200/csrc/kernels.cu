@@ -1658,45 +1658,52 @@ __device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, 
   const int row = lane & 15, half = lane >> 4;
   const uint32_t nrec = o1 - o0;
   bool any_cross = false;
-  if (nrec >= 16) {
-    // many records: one lane per record, rows in a loop
-    for (uint32_t k = lane; k < nrec; k += 32) {
-      unsigned long long rc = __ldg(a.records + o0 + k);
-      int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff),
-          yb = (int)((rc >> 39) & 0x1fff);
-      int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
-      if (fs | fe) {
-        int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
-        int r0 = min(yc >> 8, 15);
-        int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
+  // Warp-cooperative expansion: 32 records per round; every record counts the pixel rows it touches, and the
+  // (record, row) pairs of the round are spread evenly over the lanes (prefix sum + shuffle search for the owner), so a
+  // short piece of a flattened curve does not leave the lanes of its fifteen other rows idle.
+  for (uint32_t base = 0; base < nrec; base += 32) {
+    unsigned long long rc = 0;
+    int cnt = 0, r_first = 0;
+    if (base + lane < nrec) {
+      rc = __ldg(a.records + o0 + base + lane);
+      const int ya = (int)((rc >> 13) & 0x1fff), yb = (int)((rc >> 39) & 0x1fff);
+      const int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
+      if (fs | fe) {  // the record enters or leaves through the tile's left boundary: crossing term of that height
+        const int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
+        const int r0 = min(yc >> 8, 15);
+        const int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
         atomicAdd(&cross[r0], sgn * hq);
         atomicAdd(&cross[r0 + 1], sgn * (65536 - hq));
         any_cross = true;
       }
       if (ya != yb) {
-        int ylo = min(ya, yb), yhi = max(ya, yb);
-        for (int r = ylo >> 8; r <= ((yhi - 1) >> 8); r++) accumulate_row(xa, ya, xb, yb, r, acc + r * kAccStride);
+        const int ylo = min(ya, yb), yhi = max(ya, yb);
+        r_first = ylo >> 8;
+        cnt = ((yhi - 1) >> 8) - r_first + 1;
       }
     }
-  } else {
-    // few records: one lane per (record, row)
-    for (uint32_t k = lane; k < nrec * 16; k += 32) {
-      unsigned long long rc = __ldg(a.records + o0 + (k >> 4));
-      int r = (int)(k & 15);
-      int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff),
-          yb = (int)((rc >> 39) & 0x1fff);
-      int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
-      if (fs | fe) {
-        int yc = fs ? ya : yb, sgn = fs ? -1 : 1;
-        int r0 = min(yc >> 8, 15);
-        if (r == r0) {  // one lane per record posts the crossing term
-          int hq = min(max((r0 + 1) * 256 - yc, 0), 256) * 256;
-          atomicAdd(&cross[r0], sgn * hq);
-          atomicAdd(&cross[r0 + 1], sgn * (65536 - hq));
-        }
-        any_cross = true;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    for (int k0 = 0; k0 < total; k0 += 32) {
+      const int k = min(k0 + (int)lane, total - 1);
+      int o = 0;  // owner = the last lane whose first pair is <= k
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, excl, o + step);
+        if (v <= k) o += step;
       }
-      if (ya != yb) accumulate_row(xa, ya, xb, yb, r, acc + r * kAccStride);
+      const int first = __shfl_sync(0xffffffffu, excl, o);
+      const int r = __shfl_sync(0xffffffffu, r_first, o) + (k - first);
+      const unsigned long long orc = __shfl_sync(0xffffffffu, rc, o);
+      if (k0 + (int)lane < total)
+        accumulate_row((int)(orc & 0x1fff), (int)((orc >> 13) & 0x1fff), (int)((orc >> 26) & 0x1fff), (int)((orc >> 39) & 0x1fff), r,
+                       acc + r * kAccStride);
     }
   }
   any_cross = __any_sync(0xffffffffu, any_cross);
