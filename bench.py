@@ -31,11 +31,60 @@ sys.path.insert(0, ROOT)
 METRIC = "rasterized_Mpixel_per_s"
 UNIT = "Mpixel/s"
 
+# BASELINE.json configs[1..3]: workloads.py builds the scenes the parity tests check
+EXTRA_CONFIGS = {
+    "gradients1080": {"frames_per_pass": 0,
+                      "workload": "60 frames at 1920x1080, one full-frame gradient shape each: linear / radial / focal x pad / "
+                                  "reflect / repeat x sRGB / linear-RGB, 2-15 stops (SURVEY 8d config 2, BASELINE configs[1])"},
+    "morphsweep": {"frames_per_pass": 64,
+                   "workload": "flat-morph-shapes/homestuck-beta-29 at x8 (1072x720), 256 morph ratios r = 257 k in one batch "
+                               "(SURVEY 8d config 3, BASELINE configs[2])"},
+    "textured4k": {"frames_per_pass": 8,
+                   "workload": "32 frames at 3840x2160, one full-frame bitmap-filled quad each: clipped / repeating, texel:pixel "
+                               "0.25 / 1 / 2.58 / 8, corpus and 1024x1024 noise textures (SURVEY 8d config 4, BASELINE configs[3])"},
+}
+
+
+def hbm_peak():
+    peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    return peak, src
+
+
+def kernels_sha():
+    """Identity of the kernel sources this run was built from (profiles/ncu_summary.json carries the same hash for the
+    build its figures were captured on)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ("kernels.cu", "kernels.h"):
+        with open(os.path.join(ROOT, "swf_renderer_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_figures():
+    """k_fine DRAM traffic and warp instructions per launch from the committed ncu capture - only when that capture
+    was taken on the kernel sources this run uses."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            j = json.load(f)
+        if j.get("kernels_sha") != kernels_sha():
+            return None, None, "profiles/ncu_summary.json was captured on other kernel sources (%s): not quoted" % j.get("kernels_sha")
+        return j.get("k_fine_dram_bytes_per_launch"), j.get("k_fine_warp_instructions_per_launch"), \
+            "profiles/%s_kernels.md (ncu --set full, 16 frames per launch)" % j.get("tag")
+    except Exception as e:
+        return None, None, "no ncu summary (%s)" % type(e).__name__
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="distinct frames per step and per GPU")
@@ -48,7 +97,10 @@ def parse():
     ap.add_argument("--gather", action="store_true",
                     help="N > 1 only: also time the optional gather of the ranks' finished frames onto rank 0, GPU to GPU "
                          "(NCCL over NVLink; SURVEY 8e - off the hot path, reported as its own object)")
-    ap.add_argument("--quick", action="store_true", help="experiments: skip the sync-every-step leg of e2e")
+    ap.add_argument("--quick", action="store_true", help="experiments: skip the sync-every-step leg of e2e and the extra configs")
+    ap.add_argument("--config", default="stream", choices=["stream"] + list(EXTRA_CONFIGS),
+                    help="workload of the line: stream = BASELINE configs[4] (the headline, with the other configs as extra "
+                         "objects under `configs`); gradients1080 / morphsweep / textured4k = BASELINE configs[1] / [2] / [3] alone")
     ap.add_argument("--uhd-frames", type=int, default=16,
                     help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
     return ap.parse_args()
@@ -253,6 +305,137 @@ def pin_to_gpu_numa_node(local):
         return None
 
 
+def run_extra_config(name, a, local, stream, rank, world, barrier, max_over_ranks, with_cpu):
+    """One of BASELINE configs[1..3] (few, large shapes - the regime SURVEY 8d expects closest to the HBM bound): the
+    scene the parity test of the same name checks, all frames in one resident batch.  Returns the config's object:
+    value (device-timed, stages resident), e2e (host stages in, frames out to pinned host memory), roofline of k_fine,
+    cpu_baseline and parity (oracle on a sample of the frames; N = 1 only)."""
+    import numpy as np
+    import torch
+
+    import workloads
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import _stage_arrays
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import corpus
+
+    spec = EXTRA_CONFIGS[name]
+    sc = getattr(workloads, name)()
+    W, H, F = sc.width, sc.height, len(sc.frames)
+    r, stages = corpus.make_product(sc, device=local, cuda_stream=stream.cuda_stream)
+    if spec["frames_per_pass"]:
+        r.set_option(capi.OPT_FRAMES_PER_PASS, spec["frames_per_pass"])
+    arr, keep = _stage_arrays(stages)
+    batch = r.create_batch((arr, keep))
+    for _ in range(3):
+        batch.render()
+    r.sync()
+    # size the timed region to ~0.5 s
+    t0 = time.perf_counter()
+    batch.render()
+    r.sync()
+    steps = int(min(2000, max(10, 0.5 / max(time.perf_counter() - t0, 1e-4))))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        batch.render()
+    e1.record(stream)
+    r.sync()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    stats = r.stats()
+    frame_sample = r.get_image(frame=F // 2, premultiplied=True).data.copy()
+    r.set_option(capi.OPT_PROFILE, 1)
+    acc, passes = {}, 1
+    for _ in range(3):
+        batch.render()
+        st = r.stage_times()
+        passes = max(st["passes"], 1)
+        for k, v in st["ms"].items():
+            acc[k] = acc.get(k, 0.0) + v / 3
+    r.set_option(capi.OPT_PROFILE, 0)
+    batch.close()
+    px = F * W * H
+    # algorithmic bytes (SURVEY 8d): segments and draw items read once, binned records written + read once, style
+    # tables (4 KB ramp per gradient fill, distinct texels at most once), the frame stored once (it starts from a clear)
+    n_items = stats["n_primitives"]
+    style_bytes = 4096 * sum(1 for t in sc.shapes for f in t["shape"]["initial_styles"]["fill"] if f["type"].endswith("gradient"))
+    tex_bytes = sum(int(b.shape[0]) * int(b.shape[1]) * 4 for b in sc.bitmaps.values())
+    seg_bytes = (52 if sc.morphs else 28) * stats["n_segments"]
+    alg = seg_bytes + 48 * n_items + 16 * stats["n_records"] + style_bytes + tex_bytes + 4 * px
+    fine_ms = acc.get("fine", 0.0) / passes
+    fine_bytes = (8 * stats["n_records"] + 4 * px + style_bytes + tex_bytes) / passes
+    peak, peak_src = hbm_peak()
+    out = {
+        "workload": spec["workload"],
+        "resolution": [W, H],
+        "frames_per_step_per_gpu": F,
+        "steps": steps,
+        "ms_per_step": ms,
+        "value": world * px / (ms / 1e3) / 1e6,
+        "unit": UNIT,
+        "frames_per_s": world * F / (ms / 1e3),
+        "launches_per_step": stats["kernel_launches"],
+        "roofline": {
+            "bound": "hbm",
+            "kernel": "k_fine (per-tile coverage + paint + blend)",
+            "achieved": fine_bytes / (fine_ms / 1e3) / 1e9 if fine_ms else None,
+            "peak": peak,
+            "peak_source": peak_src,
+            "unit": "GB/s",
+            "frac": fine_bytes / (fine_ms / 1e3) / 1e9 / peak if fine_ms else None,
+            "traffic": None,
+            "algorithmic_bytes_per_launch": fine_bytes,
+            "launch_ms": fine_ms,
+            "launches_per_step": passes,
+            "stage_ms_per_step": acc,
+            "pipeline": {"algorithmic_bytes_per_step": alg, "achieved": alg / (ms / 1e3) / 1e9, "frac": alg / (ms / 1e3) / 1e9 / peak},
+        },
+        "per_step": {k: stats[k] for k in ("n_primitives", "n_segments", "n_edges", "n_records", "fine_slots", "fine_records")},
+    }
+    # end to end: host stage arrays in, every frame out to pinned host memory, streamed over two buffers
+    fb = W * H * 4
+    host_out = [torch.empty(F * fb, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    for i in range(2):
+        r.render_stage_array(arr, F)
+        r.read_frames_async(0, F, host_out[i & 1].data_ptr())
+    r.sync()
+    n_e2e = int(min(200, max(4, 0.5 / max(ms / 1e3 * 3, 1e-4))))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        r.render_stage_array(arr, F)
+        r.read_frames_async(0, F, host_out[i & 1].data_ptr())
+    r.sync()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    out["e2e"] = {"value": world * px * n_e2e / e2e_s / 1e6, "unit": UNIT, "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e,
+                  "h2d_bytes_per_step": 52 * n_items, "d2h_bytes_per_step": F * fb}
+    e2e_sample = host_out[(n_e2e - 1) & 1][(F // 2) * fb:(F // 2 + 1) * fb].numpy().reshape(H, W, 4).copy()
+    del host_out
+    r.close()
+    if with_cpu:
+        # the oracle renders frames of the same scene for about ten seconds: CPU baseline, and the checker of frame F/2
+        want = corpus.render_oracle(sc, frame=F // 2)
+        d1 = int((frame_sample != want).any(axis=2).sum())
+        d2 = int((e2e_sample != want).any(axis=2).sum())
+        out["parity"] = {"frame": F // 2, "equal": d1 == 0 and d2 == 0, "px_diff": d1, "px_diff_e2e": d2,
+                         "against": "oracle/raster.c, premultiplied RGBA8, bit-exact"}
+        t0, n_cpu = time.perf_counter(), 0
+        for f in range(F):
+            corpus.render_oracle(sc, frame=f)
+            n_cpu += 1
+            if time.perf_counter() - t0 > 8.0:
+                break
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu * W * H / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "frames 0..%d of the same scene (%d of %d), C restatement of the reference CPU path, "
+                                         "1 thread, %.1f s" % (n_cpu - 1, n_cpu, F, dt)}
+    return out
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -273,6 +456,46 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with_cpu = world == 1 and not a.no_cpu_baseline
+    if a.config != "stream":
+        # one of BASELINE configs[1..3] as the line's workload
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        obj = run_extra_config(a.config, a, local, stream, rank, world, barrier, max_over_ranks, with_cpu)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            line = {"metric": METRIC, "value": obj["value"], "unit": UNIT, "n_gpus": world, "steps": obj["steps"], "warmup": 3,
+                    "ms_per_step": obj["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "u8 (Q16 integer coverage, f32 paint)", "data": "synthetic",
+                    "config": {"workload": obj["workload"], "frames_per_step_per_gpu": obj["frames_per_step_per_gpu"],
+                               "resolution": obj["resolution"], "sharding": "replicas of the batch over %d rank(s)" % world,
+                               "cache": "%.0f MB of output per step (larger than L2)"
+                               % (obj["frames_per_step_per_gpu"] * obj["resolution"][0] * obj["resolution"][1] * 4 / 1e6)},
+                    "clocks": clocks, "gpu_launches": obj["launches_per_step"] * obj["steps"]}
+            for k in ("e2e", "roofline", "per_step", "frames_per_s", "cpu_baseline", "parity"):
+                if k in obj:
+                    line[k] = obj[k]
+            print(json.dumps(line), flush=True)
+            if "parity" in obj and not obj["parity"]["equal"]:
+                raise SystemExit("bench.py: the timed configuration differs from the oracle (see `parity` in the line)")
+        if world > 1:
+            dist.destroy_process_group()
+        return
     r = sw.HeadlessRenderer(a.width, a.height, device=local, cuda_stream=stream.cuda_stream)
     r.set_option(capi.OPT_RETAIN_COMPILED, 0)
     if a.frames_per_pass:
@@ -296,19 +519,6 @@ def run_ours(a):
     h2d_bytes = a.frames * a.shapes * 52  # 48 B draw item + 4 B offsets per primitive
     d2h_bytes = a.frames * a.width * a.height * 4
     px_per_step = a.frames * a.width * a.height
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # ---- value: stages resident in HBM ----
     # E_tile of SURVEY 8(d) - the records the path's algorithm bins, the sum of the bit-exact tile bin counts - comes
@@ -341,6 +551,21 @@ def run_ours(a):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches_per_render = r.stats()["kernel_launches"]
     launches = launches_per_render * a.steps
+    # the same measurement over at least one second (clock and thermal behaviour), when K steps are shorter than that
+    sustained = None
+    if ms < 1000.0 and not a.quick:
+        n_long = int(1000.0 / max(ms / a.steps, 1e-3)) + 1
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for _ in range(n_long):
+            batch.render()
+        l1.record(stream)
+        r.sync()
+        barrier()
+        lms = max_over_ranks(l0.elapsed_time(l1))
+        sustained = {"steps": n_long, "ms_per_step": lms / n_long, "value": world * px_per_step * n_long / (lms / 1e3) / 1e6,
+                     "unit": UNIT, "timed_region_s": lms / 1e3}
     # frame 0 of the batch the timed loop just rendered (compared with the oracle's frame 0 below: `parity`)
     timed_frame0 = r.get_image(frame=0, premultiplied=True).data.copy() if rank == 0 else None
     value = world * px_per_step * a.steps / (ms / 1e3) / 1e6
@@ -362,19 +587,13 @@ def run_ours(a):
     fine_bytes_per_launch = (8 * n_records_full + 4 * px_per_step) / max(passes, 1)
     # B = 28 B x segments + 48 B x draw items + 2 x 8 B x E_tile + 4 x W x H per frame
     algorithmic_bytes = 28 * stats["n_segments"] + 48 * stats["n_primitives"] + 16 * n_records_full + 4 * px_per_step
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        pass
+    peak, peak_src = hbm_peak()
     achieved = fine_bytes_per_launch / (fine_ms_per_launch / 1e3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            traffic = json.load(f).get("k_fine_dram_bytes_per_launch")
-    except Exception:
-        pass
+    # ncu figures are per launch of 16 frames of this stream (tools/gpu_exp.sh): scaled to this run's frames per launch
+    traffic16, winst16, ncu_src = ncu_figures()
+    frames_per_launch = a.frames / max(passes, 1)
+    traffic = traffic16 * frames_per_launch / 16.0 if traffic16 else None
+    winst = winst16 * frames_per_launch / 16.0 if winst16 else None
     roofline = {
         "bound": "hbm",
         "kernel": "k_fine (per-tile coverage + paint + blend)",
@@ -384,6 +603,9 @@ def run_ours(a):
         "unit": "GB/s",
         "frac": achieved / peak,
         "traffic": traffic,
+        "traffic_source": ncu_src,
+        "kernels_sha": kernels_sha(),
+        "warp_instructions_per_launch": winst,
         "algorithmic_bytes_per_launch": fine_bytes_per_launch,
         "launch_ms": fine_ms_per_launch,
         "launches_per_step": passes,
@@ -433,30 +655,48 @@ def run_ours(a):
 
     # ---- optional: gather the finished frames of all ranks onto rank 0, device to device (not part of `value` / `e2e`) ----
     gather = None
-    if a.gather and world > 1:
+    if a.gather:
         try:
             from swf_renderer_b200 import sharding
 
             r.sync()
             local_frames = r.device_frames()
-            n_global = world * int(local_frames.shape[0])
             for _ in range(2):
-                sharding.gather_frames(local_frames, n_global, dst=0)
+                sharding.peer_gather_frames(r, dst=0)
             barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_g = 5
-            g0.record()
-            for _ in range(n_g):
-                out = sharding.gather_frames(local_frames, n_global, dst=0)
-            g1.record()
+            times = []
+            out = None
+            for _ in range(5):
+                out, gms = sharding.peer_gather_frames(r, dst=0)
+                if rank == 0:
+                    times.append(gms)
             barrier()
-            gms = max_over_ranks(g0.elapsed_time(g1)) / n_g
-            moved = (world - 1) * local_frames.numel()
-            gather = {"ms": gms, "bytes_into_rank0": moved, "GB/s": moved / (gms / 1e3) / 1e9, "frames": n_global,
-                      "how": "torch.distributed.gather (NCCL) of the renderers' frame stores + interleave into frame order on rank 0"}
             if rank == 0:
-                gather["first_frame_matches_rank0"] = bool(torch.equal(out[0], local_frames[0]))
+                gms = sorted(times)[len(times) // 2]
+                moved = (world - 1) * local_frames.numel()
+                total = world * local_frames.numel()
+                gather = {"ms": gms, "frames": int(out.shape[0]), "bytes_from_peers": moved, "bytes_total": total,
+                          "GB/s_from_peers": moved / (gms / 1e3) / 1e9 if world > 1 else None,
+                          "GB/s_total": total / (gms / 1e3) / 1e9,
+                          "how": "swfr_gather_frames: one strided cudaMemcpy2DAsync per rank (CUDA IPC peer pointers) on the "
+                                 "gathering renderer's copy stream, device-timed with CUDA events; frames land in global order",
+                          "first_frame_matches_rank0": bool(torch.equal(out[0], local_frames[0])),
+                          "frame_of_last_rank_nonzero": bool(out[world - 1].any().item())}
             del out
+            if world > 1:  # the same gather through torch.distributed (NCCL), for comparison
+                n_global = world * int(local_frames.shape[0])
+                sharding.gather_frames(local_frames, n_global, dst=0)
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(3):
+                    o2 = sharding.gather_frames(local_frames, n_global, dst=0)
+                g1.record()
+                barrier()
+                nms = max_over_ranks(g0.elapsed_time(g1)) / 3
+                if rank == 0:
+                    gather["nccl_gather_ms"] = nms
+                del o2
         except Exception as e:  # the optional line must never cost the bench line
             gather = {"error": "%s: %s" % (type(e).__name__, e)}
 
@@ -504,6 +744,20 @@ def run_ours(a):
         ru.close()
         batch = None
 
+    # ---- BASELINE configs[1..3] as extra objects of the line ----
+    extra = {}
+    if not a.quick:
+        if batch is not None:
+            batch.close()
+            batch = None
+        r.close()
+        r = None
+        for name in EXTRA_CONFIGS:
+            try:
+                extra[name] = run_extra_config(name, a, local, stream, rank, world, barrier, max_over_ranks, with_cpu)
+            except Exception as e:  # an extra object must never cost the headline
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
         line = {
             "metric": METRIC,
@@ -534,6 +788,7 @@ def run_ours(a):
                 "numa": numa,
                 "checksum": checksum,
             },
+            "sustained": sustained,
             "gpu_launches": launches,
             "launches_per_render": launches_per_render,
             "roofline": roofline,
@@ -542,6 +797,8 @@ def run_ours(a):
         }
         if uhd is not None:
             line["uhd"] = uhd
+        if extra:
+            line["configs"] = extra
         if gather is not None:
             line["gather"] = gather
         parity_ok = True
@@ -551,7 +808,7 @@ def run_ours(a):
             want, line["cpu_baseline"] = cpu_baseline_single(a)
             d_timed = int((timed_frame0 != want).any(axis=2).sum())
             d_e2e = int((e2e_frame0 != want).any(axis=2).sum())
-            parity_ok = d_timed == 0 and d_e2e == 0
+            parity_ok = d_timed == 0 and d_e2e == 0 and all(c.get("parity", {}).get("equal", True) for c in extra.values())
             line["parity"] = {"frame0_equal": parity_ok, "px_diff": d_timed, "px_diff_e2e": d_e2e,
                               "against": "oracle/raster.c, frame 0 of the timed batch and of the e2e host buffer, "
                                          "premultiplied RGBA8, bit-exact"}
@@ -560,7 +817,8 @@ def run_ours(a):
             raise SystemExit("bench.py: the timed configuration differs from the oracle (see `parity` in the line)")
     if batch is not None:
         batch.close()
-    r.close()
+    if r is not None:
+        r.close()
     if world > 1:
         dist.destroy_process_group()
 

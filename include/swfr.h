@@ -284,6 +284,33 @@ int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uin
 /* Device pointer of frame 0 of the last render (premultiplied RGBA8, frames width*height*4 bytes apart). */
 int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n_frames);
 
+/* ---- optional gather of finished frames onto one GPU (off the hot path) --------------------
+ * Frames shard over renderers (one per GPU, frame f -> renderer f mod N) with no collective; a caller that wants all
+ * of them on one GPU afterwards moves them GPU to GPU over NVLink / NVSwitch with plain asynchronous peer copies:
+ *   1. every source renderer:   swfr_sync(src); swfr_export_frames(src, &exp[k]);   (then any barrier / message)
+ *   2. the gathering renderer:  swfr_gather_frames(dst, exp, N, &ptr, &n);  swfr_sync(dst);
+ * exp[k] may come from another process (one process per GPU: it carries a CUDA IPC memory handle; the bytes of the
+ * struct are what the processes exchange) or from the same process (one thread per GPU: the pointer is used directly
+ * and peer access is enabled).  Frame slot s of exp[k] lands in slot s * N + k of the gather buffer, i.e. in global
+ * frame order; one strided copy (cudaMemcpy2DAsync, row = one frame) per source, on the gathering renderer's copy
+ * stream.  The exported store must stay untouched (no render on the source) until the gatherer's swfr_sync. */
+typedef struct swfr_frames_export {
+  uint8_t ipc_handle[64];  /* cudaIpcMemHandle_t of the frame store */
+  uint64_t pid;            /* exporting process */
+  uint64_t device_ptr;     /* frame 0 in the exporting process' address space */
+  uint64_t offset;         /* of frame 0 inside the exported allocation */
+  uint64_t frame_bytes;    /* width * height * 4 */
+  int32_t device;          /* CUDA ordinal of the exporting renderer */
+  uint32_t n_frames;       /* frames of its last render */
+  uint32_t width, height;
+} swfr_frames_export;
+int swfr_export_frames(swfr_renderer *r, swfr_frames_export *out);
+/* `*out_ptr` = the gather buffer on this renderer's device (premultiplied RGBA8, frames in global order), `*out_n` =
+ * the frames it holds; valid after swfr_sync().  `*out_ms` (optional) is filled by the NEXT swfr_sync with the device
+ * time of the copies (CUDA events on the copy stream). */
+int swfr_gather_frames(swfr_renderer *r, const swfr_frames_export *sources, uint32_t n_sources, void **out_ptr, uint32_t *out_n);
+int swfr_gather_last_ms(swfr_renderer *r, float *out_ms);
+
 /* Renderer.render(stage) of the TypeScript API (ts/src/lib/renderer.ts:4-8, canvas-renderer.ts:61-78): flattens the
  * display tree and renders it into frame 0 (n trees into frames 0..n-1).  stage.width / height must equal the
  * renderer's viewport. */

@@ -252,6 +252,32 @@ PROTOTYPES = {
     "swfr_debug_tile_counts": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
 }
 
+
+
+class FramesExport(C.Structure):
+    """swfr_frames_export: what a renderer hands to the renderer that gathers its frames (plain bytes; other processes
+    receive them through any control-plane message)."""
+
+    _fields_ = [
+        ("ipc_handle", C.c_uint8 * 64),
+        ("pid", C.c_uint64),
+        ("device_ptr", C.c_uint64),
+        ("offset", C.c_uint64),
+        ("frame_bytes", C.c_uint64),
+        ("device", C.c_int32),
+        ("n_frames", C.c_uint32),
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+    ]
+
+
+PROTOTYPES["swfr_export_frames"] = (C.c_int, [C.c_void_p, C.POINTER(FramesExport)])
+PROTOTYPES["swfr_gather_frames"] = (
+    C.c_int,
+    [C.c_void_p, C.POINTER(FramesExport), C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)],
+)
+PROTOTYPES["swfr_gather_last_ms"] = (C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
+
 _LIB = None
 
 

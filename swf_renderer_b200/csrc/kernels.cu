@@ -266,6 +266,9 @@ __global__ void k_init(RenderArgs a) {
     a.totals->overflow_stage = 0;
     a.totals->fine_hits = 0;
     a.totals->fine_records = 0;
+    // the render before this one was aborted in this arena (working memory overflow): the self-cleaning arrays are
+    // dirty until the host has zeroed them (recover), so this render stands down as well and is re-run with it
+    if (*a.arena_dirty) a.totals->overflow = 32u;
   }
   for (uint32_t l = i; l < a.n_frames * (uint32_t)a.tiles_y; l += stride) a.row_count[l] = 0;
   for (uint32_t l = i; l < a.caps.stage / kStageBlock; l += stride) a.stage_used[l] = 0;
@@ -309,8 +312,9 @@ __global__ void k_flatten_count(RenderArgs a) {
 // geometry outside the viewport (edges left of the grid still post their winding, see band_setup), so fewer slots are
 // cleared, scanned and probed.  Dead paths are not flattened, not binned, get no records, and their slots are never
 // read (k_fine checks path_alive first).  The lists of the chunk (draw items with a visible path for the flattener,
-// visible paths with small / large grids for k_cover) are appended with one atomic per warp and list; the slots of the
-// visible paths are then cleared by the whole warp, path by path (coalesced).
+// visible paths with small / large grids for k_cover) are appended with one atomic per warp and list.  Nothing is
+// cleared here: the per-slot record counters and winding deltas clean themselves (k_scatter counts the former back to
+// zero, k_cover zeroes the latter as it reads them), so they are all zero whenever a chunk starts binning.
 __global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
   pdl_enter();
   if (a.totals->overflow) return;
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
   for (uint32_t base = p0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < p1; base += stride) {
     const uint32_t pid = base + lane;
     bool alive = false;
-    uint32_t s0 = 0, n = 0, it = 0;
+    uint32_t n = 0, it = 0;
     if (pid < p1) {
       const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));
       int bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
@@ -363,7 +367,6 @@ __global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
       a.path_rec_base[pid] = 0;
       if (alive) {
         n = (uint32_t)(bw * bh);
-        s0 = a.path_slot_off[pid];
         it = a.path_item[pid];
       }
     }
@@ -393,15 +396,6 @@ __global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
     if (claim) a.alive_items[b_item + __popc(m_item & below)] = it;
     if (big) a.big_chunk[b_big + __popc(m_big & below)] = pid;
     if (small) a.small_chunk[b_small + __popc(m_small & below)] = pid;
-    // clear the slots of the visible paths
-    for (uint32_t m = amask; m; m &= m - 1) {
-      const int src = __ffs(m) - 1;
-      const uint32_t ps0 = __shfl_sync(0xffffffffu, s0, src), pn = __shfl_sync(0xffffffffu, n, src);
-      for (uint32_t i = lane; i < pn; i += 32) {
-        a.slot_count[ps0 + i] = 0;
-        a.slot_backdrop[ps0 + i] = 0;
-      }
-    }
   }
 }
 
@@ -1097,8 +1091,12 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
     e_end = min(a.totals->n_edges, a.caps.edges);
   }
   const uint32_t tiles = (uint32_t)(a.tiles_x * a.tiles_y);
+  // staging blocks: a thread block that has edges takes one block per warp with a single atomic (19 000 warps asking
+  // one counter each is what the kernel used to wait for); a warp that fills its block takes further ones itself
+  __shared__ uint32_t sh_first_blk;
+  if (threadIdx.x == 0 && e_begin + blockIdx.x * kBinWarps * 32 < e_end) sh_first_blk = atomicAdd(&a.totals->n_stage_blocks, (uint32_t)kBinWarps);
+  __syncthreads();
   uint32_t blk = 0, blk_used = kStageBlock;  // current staging block of this warp (none yet)
-  uint32_t next_blk = 0;                     // lane 0: the block taken in advance
   bool have_blk = false, stage_full = false;
   for (uint32_t base = e_begin + (blockIdx.x * kBinWarps + w) * 32; base < e_end; base += stride) {
     const uint32_t e = base + lane;
@@ -1202,11 +1200,13 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin(RenderArgs a, uint32_t c
         const uint32_t kcount = __popc(kmask);
         if (!have_blk || blk_used + kcount > kStageBlock) {  // next staging block of this warp
           if (have_blk && !stage_full && lane == 0) a.stage_used[blk] = blk_used;
-          // the block after the first one was asked for when its predecessor was taken (lane 0 holds the answer in
-          // next_blk): the round trip of the returning atomic is over by the time the block is needed
-          if (lane == 0 && !have_blk) next_blk = atomicAdd(&a.totals->n_stage_blocks, 1u);
-          blk = __shfl_sync(0xffffffffu, next_blk, 0);
-          if (lane == 0) next_blk = atomicAdd(&a.totals->n_stage_blocks, 1u);
+          if (!have_blk) {
+            blk = sh_first_blk + w;  // the first block of every warp came from one atomic per thread block
+          } else {
+            uint32_t nb2 = 0;
+            if (lane == 0) nb2 = atomicAdd(&a.totals->n_stage_blocks, 1u);
+            blk = __shfl_sync(0xffffffffu, nb2, 0);
+          }
           if (blk >= cap_blocks) {
             if (lane == 0) atomicOr(&a.totals->overflow_stage, 1u);
             stage_full = true;
@@ -1278,7 +1278,8 @@ __device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pi
   const bool opaque = (rec.z >> 8) & 1u;
   const int n = bw * bh;
   const uint32_t s0 = a.path_slot_off[pid];
-  int32_t *bd = a.slot_backdrop + s0;
+  int32_t *bd = a.slot_backdrop + s0;  // winding deltas posted by k_bin: read, then zeroed again (self-cleaning)
+  int32_t *wind = a.slot_wind + s0;    // winding number at the left edge of every tile (what k_fine reads)
   const uint32_t *cnt = a.slot_count + s0;
   uint32_t *end = a.slot_off + s0;
   int carry = 0, carry_row = -1;
@@ -1319,9 +1320,12 @@ __device__ __forceinline__ void small_path_scan(const RenderArgs &a, uint32_t pi
             if ((int)lane >= o && col >= o) v += t;
           }
           if (row == carry_row) v += carry;
-          if (ok) bd[i] = v;
           carry = __shfl_sync(0xffffffffu, v, 31);
           carry_row = __shfl_sync(0xffffffffu, row, 31);
+        }
+        if (ok) {
+          wind[i] = v;
+          if (v4[u] != 0) bd[i] = 0;
         }
         // an opaque path covers this tile completely: it hides the chunks below
         if (ok && opaque && c4[u] == 0 && v != 0) {
@@ -1350,7 +1354,8 @@ __device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid,
       int carry = 0;
       for (int x0 = 0; x0 < bw; x0 += 32) {
         int x = x0 + (int)lane;
-        int v = x < bw ? q[x] : 0;
+        const int delta = x < bw ? q[x] : 0;
+        int v = delta;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           int t = __shfl_up_sync(0xffffffffu, v, o);
@@ -1358,7 +1363,8 @@ __device__ __forceinline__ void big_path_scan(const RenderArgs &a, uint32_t pid,
         }
         v += carry;
         if (x < bw) {
-          q[x] = v;
+          a.slot_wind[s0 + row * bw + x] = v;
+          if (delta != 0) q[x] = 0;  // self-cleaning
           if (opaque && v != 0 && cq[x] == 0) {
             atomicMax(cover + (by0 + row) * a.tiles_x + bx0 + x, pid + 1u);
             atomicOr(cover_bits + (size_t)(by0 + row) * a.cover_words + ((bx0 + x) >> 5), 1u << ((bx0 + x) & 31));
@@ -1642,7 +1648,7 @@ __device__ __forceinline__ Probe probe_slot(const RenderArgs &a, uint32_t pid, b
   const uint32_t rec_base = __ldg(a.path_rec_base + pid);
   pr.o0 = rec_base + (local ? __ldg(a.slot_off + slot - 1) : 0u);
   pr.o1 = rec_base + __ldg(a.slot_off + slot);
-  pr.bd = __ldg(a.slot_backdrop + slot);
+  pr.bd = __ldg(a.slot_wind + slot);
   pr.info = rc.z;
   pr.color = rc.w;
   pr.hit = (pr.o1 > pr.o0) || (pr.bd != 0);
@@ -1744,7 +1750,10 @@ __device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, 
 // 4 at 64 0.54, 5 at 48 and 6 at 40 0.56 (1080p / 10 k shapes, 16 frames per launch).
 __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
   pdl_wait();  // (no launch_dependents: the successor's blocks would only squat in the slots the tail frees)
-  if (a.totals->overflow | a.totals->overflow_stage) return;
+  if (a.totals->overflow | a.totals->overflow_stage) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.arena_dirty = 1u;  // see k_init
+    return;
+  }
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
   __shared__ uint4 paint_sh[kFineWarps][sizeof(PaintInst) / 16];  // the paint instance the warp is compositing

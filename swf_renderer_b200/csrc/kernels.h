@@ -71,7 +71,7 @@ constexpr int kMaxFineSlices = 16;    // leave for the host while the rest of th
 
 struct Totals {
   uint32_t n_edges, n_slots, n_records;
-  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists, bit4 row lists
+  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists, bit4 row lists, bit5 arena dirty (see k_init)
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work[kMaxFineSlices];  // fine-kernel tile queues, one per slice of frames
   uint32_t n_list;    // candidate-list entries
@@ -113,8 +113,9 @@ struct RenderArgs {
   uint32_t *path_rec_base;  // n_paths: first record of the path instance
   int4 *edges;              // caps.edges
   uint32_t *edge_pid;       // caps.edges: path instance of each edge
-  uint32_t *slot_count;     // caps.slots (+1)
-  int32_t *slot_backdrop;   // caps.slots
+  uint32_t *slot_count;     // caps.slots (+1): records per slot while binning; all zero between renders (k_scatter counts back down)
+  int32_t *slot_backdrop;   // caps.slots: winding deltas posted while binning; all zero between chunks (k_cover zeroes what it reads)
+  int32_t *slot_wind;       // caps.slots: winding number at the left edge of the slot's tile (k_cover -> k_fine)
   uint32_t *slot_off;       // caps.slots + 1: end of the slot's record range, relative to path_rec_base
   unsigned long long *records;  // caps.records
   uint4 *stage;             // caps.stage: (record lo, record hi, slot, path instance) in binning order
@@ -146,6 +147,7 @@ struct RenderArgs {
   uint32_t *alive_items;       // n_items: those draw items, listed per depth chunk
   uint32_t *alive_paths;       // n_paths: the visible path instances of frame f, in paint order, at [frame_path_off[f] ..)
   uint32_t *alive_count;       // n_frames: how many
+  uint32_t *arena_dirty;       // 1 word per arena: set when a render was aborted (its self-cleaning arrays are dirty)
   Totals *totals;
   Caps caps;
 };

@@ -7,6 +7,7 @@
 //   rs/src/headless_renderer.rs:60-64, 229-244, 725-868   new / define_shape / get_image / download_image
 // There is no CPU fallback: every entry point that renders needs a CUDA device.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -146,7 +147,7 @@ struct swfr_renderer {
   // Arenas: consecutive passes of a batch alternate between them and between the pass streams, so that the many
   // short, latency-bound kernels at the front of one pass run under the long coverage kernel of its neighbour.
   struct Arena {
-    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_off, records, scan_tmp, list_off, list_items, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_bits, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge;
+    DevBuf seg_edge_off, seg_item, path_rec, paint_inst, path_slot_off, path_rec_base, edges, edge_pid, slot_count, slot_backdrop, slot_wind, slot_off, records, scan_tmp, list_off, list_items, row_count, row_off, row_items, stage, stage_used, tile_cover, path_alive, cover_bits, big_chunk, small_chunk, path_item, item_alive, alive_items, alive_paths, alive_count, chunk_edge, dirty;
   };
   static constexpr int kArenas = 4;
   Arena arena[kArenas];
@@ -213,6 +214,16 @@ struct swfr_renderer {
   };
   std::vector<CopyFence> copy_fences;
   std::vector<cudaEvent_t> fence_pool;
+  // optional gather of other renderers' frames (swfr_gather_frames)
+  DevBuf gathered;
+  cudaEvent_t gather_ev[2] = {nullptr, nullptr};
+  bool gather_timed = false;
+  float gather_ms = 0.f;
+  struct Import {
+    uint8_t handle[64];
+    void *base;
+  };
+  std::vector<Import> imports;  // IPC allocations opened so far (kept open: opening is expensive)
 };
 
 namespace {
@@ -638,12 +649,15 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
   for (int dry = 1; dry >= 0; dry--) {
     bool grow = false;
     cudaError_t err = cudaSuccess;
-    auto need = [&](DevBuf &d, size_t bytes) {
+    auto need = [&](DevBuf &d, size_t bytes, bool zeroed = false) {
       if (bytes <= d.cap || err != cudaSuccess) return;
-      if (dry)
+      if (dry) {
         grow = true;
-      else
-        err = d.reserve(bytes);
+        return;
+      }
+      err = d.reserve(bytes);
+      // self-cleaning arrays (slot record counters, winding deltas) start from zero
+      if (zeroed && err == cudaSuccess) err = cudaMemset(d.p, 0, d.cap);
     };
     for (int k = 0; k < n_arenas; k++) {
       swfr_renderer::Arena &A = r->arena[k];
@@ -665,6 +679,7 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
       need(A.cover_bits, (size_t)max_frames * (r->tiles_x + 1) * (r->tiles_y + 1) * 4 + 256);
       need(A.scan_tmp, 8192 * 4);
       need(A.chunk_edge, 64 * 4);
+      need(A.dirty, 256, true);
       need(A.list_off, (max_lists + 1) * 4 + 256);
       need(A.list_items, (size_t)want.list * 4);
       need(A.row_count, (max_rows + 1) * 4 + 256);
@@ -672,8 +687,9 @@ int ensure_arena(swfr_renderer *r, const swfr_batch &b) {
       need(A.row_items, (size_t)want.rows * 8);
       need(A.edges, (size_t)want.edges * 16);
       need(A.edge_pid, (size_t)want.edges * 4);
-      need(A.slot_count, ((size_t)want.slots + 1) * 4);
-      need(A.slot_backdrop, ((size_t)want.slots + 1) * 4);
+      need(A.slot_count, ((size_t)want.slots + 1) * 4, true);
+      need(A.slot_backdrop, ((size_t)want.slots + 1) * 4, true);
+      need(A.slot_wind, ((size_t)want.slots + 1) * 4);
       need(A.slot_off, ((size_t)want.slots + 1) * 4);
       need(A.records, (size_t)want.records * 8);
       need(A.stage, (size_t)want.stage * 16);
@@ -727,6 +743,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.cover_bits = A.cover_bits.as<uint32_t>();
   a.cover_words = (r->tiles_x + 31) / 32;
   a.chunk_edge = A.chunk_edge.as<uint32_t>();
+  a.arena_dirty = A.dirty.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
   a.ramps = r->d_ramps.as<uint32_t>();
@@ -741,6 +758,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.edge_pid = A.edge_pid.as<uint32_t>();
   a.slot_count = A.slot_count.as<uint32_t>();
   a.slot_backdrop = A.slot_backdrop.as<int32_t>();
+  a.slot_wind = A.slot_wind.as<int32_t>();
   a.slot_off = A.slot_off.as<uint32_t>();
   a.records = A.records.as<unsigned long long>();
   a.stage = A.stage.as<uint4>();
@@ -943,6 +961,7 @@ int recover(swfr_renderer *r) {
           CK(A.edge_pid.reserve((size_t)want.edges * 4));
           CK(A.slot_count.reserve(((size_t)want.slots + 1) * 4));
           CK(A.slot_backdrop.reserve(((size_t)want.slots + 1) * 4));
+          CK(A.slot_wind.reserve(((size_t)want.slots + 1) * 4));
           CK(A.slot_off.reserve(((size_t)want.slots + 1) * 4));
           CK(A.records.reserve((size_t)want.records * 8));
         }
@@ -950,6 +969,13 @@ int recover(swfr_renderer *r) {
         retries++;
       } else if (guard > 0) {
         break;  // this run fitted
+      }
+      // an aborted render leaves the self-cleaning arrays dirty
+      for (int k = 0; k < r->n_arenas; k++) {
+        swfr_renderer::Arena &A = r->arena[k];
+        if (A.slot_count.p) CK(cudaMemsetAsync(A.slot_count.p, 0, A.slot_count.cap, r->stream));
+        if (A.slot_backdrop.p) CK(cudaMemsetAsync(A.slot_backdrop.p, 0, A.slot_backdrop.cap, r->stream));
+        if (A.dirty.p) CK(cudaMemsetAsync(A.dirty.p, 0, A.dirty.cap, r->stream));
       }
       uint32_t launches = 0;
       int rc = enqueue_passes(r, b, in.slot, true, &launches);
@@ -1126,6 +1152,9 @@ void swfr_destroy(swfr_renderer *r) {
       cudaEventDestroy(r->join_ev[k]);
     }
   if (r->render_done) cudaEventDestroy(r->render_done);
+  for (const swfr_renderer::Import &im : r->imports) cudaIpcCloseMemHandle(im.base);
+  for (int k = 0; k < 2; k++)
+    if (r->gather_ev[k]) cudaEventDestroy(r->gather_ev[k]);
   for (int k = 0; k < swfr_renderer::kSlots; k++)
     if (r->slot_done[k]) cudaEventDestroy(r->slot_done[k]);
   if (r->up_stream) {
@@ -1376,6 +1405,10 @@ int swfr_sync(swfr_renderer *r) {
     CK(cudaStreamSynchronize(r->copy_stream));
     r->copy_pending = false;
   }
+  if (r->gather_timed) {
+    r->gather_timed = false;
+    if (cudaEventElapsedTime(&r->gather_ms, r->gather_ev[0], r->gather_ev[1]) != cudaSuccess) r->gather_ms = 0.f;
+  }
   return SWFR_OK;
 }
 
@@ -1464,6 +1497,116 @@ int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n) {
   if (!r) return SWFR_ERR_INVALID_HANDLE;
   if (out_ptr) *out_ptr = r->frames.p;
   if (out_n) *out_n = r->frames_rendered;
+  return SWFR_OK;
+}
+
+// ---- optional peer gather of finished frames -----------------------------------------------
+
+int swfr_export_frames(swfr_renderer *r, swfr_frames_export *out) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!out) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL out");
+  cudaSetDevice(r->device);
+  int rc = swfr_sync(r);
+  if (rc != SWFR_OK) return rc;
+  if (!r->frames.p || r->frames_rendered == 0) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "no rendered frames to export");
+  memset(out, 0, sizeof *out);
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, r->frames.p));
+  static_assert(sizeof(h) == sizeof(out->ipc_handle), "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out->ipc_handle, &h, sizeof h);
+  out->pid = (uint64_t)getpid();
+  out->device_ptr = (uint64_t)(uintptr_t)r->frames.p;
+  out->offset = 0;  // cudaMalloc'd on its own: the handle opens at frame 0
+  out->frame_bytes = (uint64_t)r->width * r->height * 4;
+  out->device = r->device;
+  out->n_frames = r->frames_rendered;
+  out->width = r->width;
+  out->height = r->height;
+  return SWFR_OK;
+}
+
+int swfr_gather_frames(swfr_renderer *r, const swfr_frames_export *src, uint32_t n_src, void **out_ptr, uint32_t *out_n) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!src || n_src == 0 || !out_ptr || !out_n) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL argument");
+  cudaSetDevice(r->device);
+  return guarded(r, [&]() -> int {
+    const uint64_t fb = (uint64_t)r->width * r->height * 4;
+    uint64_t total = 0;
+    uint32_t slots = 0;
+    for (uint32_t k = 0; k < n_src; k++) {
+      if (src[k].width != r->width || src[k].height != r->height || src[k].frame_bytes != fb)
+        return fail(r, SWFR_ERR_INVALID_ARGUMENT, "a source renders another viewport size");
+      // frame f lives on source f mod N in slot f div N: source k holds ceil((total - k) / N) frames
+      slots = std::max(slots, src[k].n_frames);
+      total += src[k].n_frames;
+    }
+    for (uint32_t k = 0; k < n_src; k++) {
+      const uint64_t want = (total + n_src - 1 - k) / n_src;
+      if (src[k].n_frames != want)
+        return fail(r, SWFR_ERR_INVALID_ARGUMENT, "source " + std::to_string(k) + " holds " + std::to_string(src[k].n_frames) +
+                                                      " frames, round-robin sharding of " + std::to_string(total) + " expects " +
+                                                      std::to_string(want));
+    }
+    if (total > 0xffffffffull) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "too many frames");
+    CK(r->gathered.reserve(std::max<size_t>((size_t)slots * n_src * fb, 256)));
+    if (!r->copy_stream) CK(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++)
+      if (!r->gather_ev[k]) CK(cudaEventCreate(&r->gather_ev[k]));
+    std::vector<const void *> ptrs(n_src);
+    for (uint32_t k = 0; k < n_src; k++) {
+      if (src[k].pid == (uint64_t)getpid()) {  // same process (one thread per GPU): the pointer itself
+        ptrs[k] = (const void *)(uintptr_t)src[k].device_ptr;
+        if (src[k].device != r->device) {
+          int can = 0;
+          CK(cudaDeviceCanAccessPeer(&can, r->device, src[k].device));
+          if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(src[k].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+          }  // without peer access the copy is staged through the host by the driver
+        }
+      } else {  // another process: open its allocation (once)
+        void *base = nullptr;
+        for (const swfr_renderer::Import &im : r->imports)
+          if (memcmp(im.handle, src[k].ipc_handle, 64) == 0) base = im.base;
+        if (!base) {
+          cudaIpcMemHandle_t h;
+          memcpy(&h, src[k].ipc_handle, sizeof h);
+          CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+          swfr_renderer::Import im;
+          memcpy(im.handle, src[k].ipc_handle, 64);
+          im.base = base;
+          r->imports.push_back(im);
+        }
+        ptrs[k] = (const char *)base + src[k].offset;
+      }
+    }
+    // the copies: one strided copy per source (row = one frame, destination pitch = N frames), after this renderer's
+    // own work (its frame store may be one of the sources)
+    if (!r->render_done) CK(cudaEventCreateWithFlags(&r->render_done, cudaEventDisableTiming));
+    CK(cudaEventRecord(r->render_done, r->stream));
+    CK(cudaStreamWaitEvent(r->copy_stream, r->render_done, 0));
+    CK(cudaEventRecord(r->gather_ev[0], r->copy_stream));
+    for (uint32_t k = 0; k < n_src; k++) {
+      if (src[k].n_frames == 0) continue;
+      CK(cudaMemcpy2DAsync((char *)r->gathered.p + (size_t)k * fb, (size_t)n_src * fb, ptrs[k], (size_t)fb, (size_t)fb, src[k].n_frames,
+                           cudaMemcpyDefault, r->copy_stream));
+    }
+    CK(cudaEventRecord(r->gather_ev[1], r->copy_stream));
+    r->copy_pending = true;
+    r->gather_timed = true;
+    *out_ptr = r->gathered.p;
+    *out_n = (uint32_t)total;
+    return SWFR_OK;
+  });
+}
+
+int swfr_gather_last_ms(swfr_renderer *r, float *out_ms) {
+  if (!r) return SWFR_ERR_INVALID_HANDLE;
+  if (!out_ms) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "NULL out");
+  int rc = swfr_sync(r);
+  if (rc != SWFR_OK) return rc;
+  *out_ms = r->gather_ms;
   return SWFR_OK;
 }
 

@@ -205,6 +205,35 @@ class HeadlessRenderer:
             return torch.empty((0, self.height, self.width, 4), dtype=torch.uint8, device="cuda:%d" % self.device)
         return torch.as_tensor(_Frames(), device="cuda:%d" % self.device)
 
+    # -- optional gather of finished frames onto one GPU (off the hot path) --------------------
+    def export_frames(self) -> bytes:
+        """swfr_export_frames: the bytes another renderer (same or other process) needs to copy this renderer's
+        finished frames GPU to GPU.  Waits for the last render."""
+        exp = capi.FramesExport()
+        self._check(self._lib.swfr_export_frames(self._h, C.byref(exp)))
+        return bytes(exp)
+
+    def gather_frames(self, exports: Sequence[bytes]):
+        """swfr_gather_frames: copies the frames of every exporting renderer (in rank order; frame f was rendered by
+        renderer f mod N in slot f div N) into this renderer's gather buffer, in global frame order - one strided
+        asynchronous peer copy per source on the copy stream.  Returns (torch uint8 tensor [frames, H, W, 4] over the
+        gather buffer, device milliseconds of the copies)."""
+        import torch
+
+        arr = (capi.FramesExport * len(exports))()
+        for k, b in enumerate(exports):
+            C.memmove(C.byref(arr[k]), b, C.sizeof(capi.FramesExport))
+        ptr, n = C.c_void_p(), C.c_uint32()
+        self._check(self._lib.swfr_gather_frames(self._h, arr, len(exports), C.byref(ptr), C.byref(n)))
+        ms = C.c_float()
+        self._check(self._lib.swfr_gather_last_ms(self._h, C.byref(ms)))  # waits for the copies
+        shape = (int(n.value), self.height, self.width, 4)
+
+        class _Frames:
+            __cuda_array_interface__ = {"shape": shape, "typestr": "|u1", "data": (int(ptr.value or 0), False), "version": 2}
+
+        return torch.as_tensor(_Frames(), device="cuda:%d" % self.device), float(ms.value)
+
     def stats(self) -> dict:
         st = capi.Stats()
         self._check(self._lib.swfr_get_stats(self._h, C.byref(st)))

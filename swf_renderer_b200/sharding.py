@@ -62,6 +62,25 @@ def gather_frames(local_frames, n_frames: int, dst: int = 0, group=None):
     return out[:n_frames]
 
 
+def peer_gather_frames(renderer, dst: int = 0, group=None):
+    """The same gather inside the library (`swfr_gather_frames`): every rank exports its renderer's frame store (a CUDA
+    IPC handle, 128 bytes over the control plane), rank ``dst`` copies the stores GPU to GPU with one strided
+    asynchronous peer copy per rank (NVLink / NVSwitch; no NCCL, no staging tensor) into its gather buffer, in global
+    frame order.  Returns (frames tensor [n_frames, H, W, 4], device ms of the copies) on ``dst`` and (None, None)
+    elsewhere.  The sources must not render again before the barrier at the end."""
+    import torch.distributed as dist
+
+    exp = renderer.export_frames()  # waits for this rank's render
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return renderer.gather_frames([exp])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    exports = [None] * world
+    dist.all_gather_object(exports, exp, group=group)  # control plane only: 128 bytes per rank
+    out = renderer.gather_frames(exports) if rank == dst else (None, None)
+    dist.barrier(group=group)  # the sources' stores are free again
+    return out
+
+
 def reduce_max_time(ms: float, group=None) -> float:
     """MAX over ranks of a device time, as the benchmark contract requires (never a wall clock)."""
     import torch

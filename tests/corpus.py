@@ -113,11 +113,11 @@ def render_oracle(scene: Scene, frame=0, want_debug=False):
     return raster.render_scene(b.scene(scene.width, scene.height), want_debug)
 
 
-def make_product(scene: Scene):
+def make_product(scene: Scene, device=0, cuda_stream=None):
     """Registers everything of the scene in a new product renderer; returns (renderer, stages)."""
     import swf_renderer_b200 as sw
 
-    r = sw.HeadlessRenderer(scene.width, scene.height)
+    r = sw.HeadlessRenderer(scene.width, scene.height, device=device, cuda_stream=cuda_stream)
     for bid, rgba in scene.bitmaps.items():
         r.register_bitmap(bid, rgba)
     shape_ids = [r.register_shape(t) for t in scene.shapes]

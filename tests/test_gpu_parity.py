@@ -250,3 +250,30 @@ def test_xswfbmp_expanded_on_the_device(built_library):
     out = r.get_image(premultiplied=True).data
     r.close()
     np.testing.assert_array_equal(out, want)
+
+
+def test_gather_frames_between_renderers_in_one_process(built_library):
+    """swfr_export_frames / swfr_gather_frames (optional): two renderers of one process shard five frames
+    round-robin (frame f -> renderer f mod 2); the first one gathers both stores into global frame order with strided
+    asynchronous copies and the result equals rendering all five frames on one renderer."""
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200.renderer import SwfrError
+
+    sc = corpus.morph_scene([0, 13107, 26214, 39321, 65535])
+    r_all, stages = corpus.make_product(sc)
+    r_all.render_batch(stages)
+    want = np.stack([r_all.get_image(frame=f, premultiplied=True).data.copy() for f in range(5)])
+    r_all.close()
+    ra, st_a = corpus.make_product(sc)
+    rb, st_b = corpus.make_product(sc)
+    ra.render_batch([st_a[f] for f in (0, 2, 4)])
+    rb.render_batch([st_b[f] for f in (1, 3)])
+    out, ms = ra.gather_frames([ra.export_frames(), rb.export_frames()])
+    assert out.shape == (5, sc.height, sc.width, 4) and ms >= 0.0
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    # counts that do not fit round-robin sharding are refused
+    rb.render_batch([st_b[1]])
+    with pytest.raises(SwfrError):
+        ra.gather_frames([ra.export_frames(), rb.export_frames()])
+    ra.close()
+    rb.close()
