@@ -219,7 +219,7 @@ const char *swfr_status_string(int status);
 uint32_t swfr_abi_version(void);
 
 /* Options: SWFR_OPT_RETAIN_COMPILED (default 1) keeps the compiled paths of every definition on the host for
- * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 16) bounds how many frames
+ * the swfr_debug_compiled / swfr_debug_segments taps; SWFR_OPT_FRAMES_PER_PASS (default 32) bounds how many frames
  * share one set of launches and one working set; SWFR_OPT_PROFILE = 1 records CUDA events at stage boundaries;
  * SWFR_OPT_HOST_THREADS = threads that flatten stages into draw items (0 = default: min(8, hardware threads)). */
 typedef enum swfr_option {

@@ -52,6 +52,8 @@ typedef struct {
   double matrix[6];   /* fill matrix scale_x, rotate_skew0, rotate_skew1, scale_y, tx, ty (fill space -> twips) */
   double focal;       /* focal point in [-1,1] */
   const uint32_t *lut; /* SWFO_RAMP_SIZE premultiplied RGBA8 entries, entry k = the gradient at (k + 1/2) / size */
+  int32_t sampled;    /* != 0: stroke outline - coverage by 15 sub-scanlines per pixel row with the non-zero rule applied
+                         per sub-scanline (sampled_coverage), because the outline overlaps itself */
 } swfo_paint;
 
 typedef struct {
@@ -330,6 +332,71 @@ static void accumulate_record(const record_t *rc, int32_t acc[16][16]) {
         c = (int32_t)lrintf(Df * f);
       }
       acc[r][i] += c;
+    }
+  }
+}
+
+/* Coverage of a path that may overlap itself (stroke outlines: joins, caps and inner loops are separate pieces of
+ * one contour).  The signed-area integral clamped per pixel over-covers where two parts of the path overlap inside a
+ * partly covered pixel; Cairo's scan converter (cairo-tor-scan-converter.c, GRID_Y = 15, GRID_X = 256) applies the
+ * fill rule per sub-scanline instead, and so does this: every pixel row is sampled on 15 lines y = row + k / 15 (the
+ * top of each sub-row, like tor), a record covers the sample lines in [y_lo, y_hi) of its own extent (half open, so
+ * the pieces of one edge in neighbouring tiles never count a line twice), the crossings of a line are walked from
+ * left to right with the non-zero rule, and each covered span adds its exact horizontal extent (1/256 px) to the pixels
+ * it touches.  mask = coverage in 1/(15 * 256) of a pixel -> 8 bits with tor's GRID_AREA_TO_ALPHA for a 2*256*15 grid. */
+#define SWFO_SUBROWS 15
+#define SWFO_MAX_SAMPLED 96 /* more records than this in one slot: the area integral is used (a blob of tiny edges) */
+
+static void sampled_coverage(const record_t *rec, int32_t nrec, int32_t backdrop, uint32_t mask[16][16]) {
+  int32_t cov[16][18];
+  memset(cov, 0, sizeof cov);
+  for (int k = 0; k < 16 * SWFO_SUBROWS; k++) {
+    const int32_t Yk = k * 256 + 128; /* sample line (centre of the sub-row) in units of 1/(256 * 15) px */
+    const int row = k / SWFO_SUBROWS;
+    int32_t w = backdrop;
+    for (int32_t i = 0; i < nrec; i++) { /* winding at the tile's left edge on this line */
+      const record_t *r = &rec[i];
+      if (r->flag_s || r->flag_e) {
+        int32_t yc15 = (r->flag_s ? r->ya : r->yb) * SWFO_SUBROWS;
+        if (Yk >= yc15) w += r->flag_s ? -1 : 1;
+      }
+    }
+    if (w != 0) cov[row][0] += 256;
+    int32_t last_x = -1, last_i = -1;
+    for (;;) { /* the crossings of this line in ascending (x, record index) order */
+      int32_t best_x = INT32_MAX, best_i = -1;
+      for (int32_t i = 0; i < nrec; i++) {
+        const record_t *r = &rec[i];
+        if (r->ya == r->yb) continue;
+        int32_t lo15 = imin32(r->ya, r->yb) * SWFO_SUBROWS, hi15 = imax32(r->ya, r->yb) * SWFO_SUBROWS;
+        if (Yk < lo15 || Yk >= hi15) continue;
+        float slope = (float)(r->xb - r->xa) / (float)((r->yb - r->ya) * SWFO_SUBROWS);
+        float x = fmaf((float)(Yk - r->ya * SWFO_SUBROWS), slope, (float)r->xa);
+        float xlo = (float)imin32(r->xa, r->xb), xhi = (float)imax32(r->xa, r->xb);
+        x = fminf(fmaxf(x, xlo), xhi);
+        int32_t xi = (int32_t)lrintf(x);
+        if (!(xi > last_x || (xi == last_x && i > last_i))) continue;
+        if (xi < best_x) best_x = xi, best_i = i;
+      }
+      if (best_i < 0) break;
+      int32_t s = rec[best_i].yb > rec[best_i].ya ? 1 : -1;
+      int32_t w2 = w + s;
+      int32_t e = (w == 0 && w2 != 0) ? 1 : ((w != 0 && w2 == 0) ? -1 : 0);
+      if (e) {
+        int32_t p = best_x >> 8, f = best_x & 255;
+        cov[row][p] += e * (256 - f);
+        cov[row][p + 1] += e * f;
+      }
+      w = w2;
+      last_x = best_x, last_i = best_i;
+    }
+  }
+  for (int r = 0; r < 16; r++) {
+    int32_t run = 0;
+    for (int i = 0; i < 16; i++) {
+      run += cov[r][i];
+      int32_t c = run < 0 ? 0 : (run > 256 * SWFO_SUBROWS ? 256 * SWFO_SUBROWS : run);
+      mask[r][i] = (uint32_t)(34 * c + 256) >> 9;
     }
   }
 }
@@ -692,9 +759,16 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
             if (g.count[slot] == 0 && g.backdrop[slot] == 0) continue;
             if (dbg) dbg->n_slots_drawn++;
             int32_t acc[16][16];
-            for (int r = 0; r < 16; r++)
-              for (int i = 0; i < 16; i++) acc[r][i] = g.backdrop[slot] * 65536;
-            for (int32_t k = g.offset[slot]; k < g.offset[slot + 1]; k++) accumulate_record(&g.records[k], acc);
+            uint32_t smask[16][16];
+            const int32_t nrec = g.offset[slot + 1] - g.offset[slot];
+            const int sampled = sc->paints[def->first_path + lp].sampled && nrec > 0 && nrec <= SWFO_MAX_SAMPLED;
+            if (sampled) {
+              sampled_coverage(&g.records[g.offset[slot]], nrec, g.backdrop[slot], smask);
+            } else {
+              for (int r = 0; r < 16; r++)
+                for (int i = 0; i < 16; i++) acc[r][i] = g.backdrop[slot] * 65536;
+              for (int32_t k = g.offset[slot]; k < g.offset[slot + 1]; k++) accumulate_record(&g.records[k], acc);
+            }
             int X0 = (g.bx0 + lx) * SWFO_TILE, Y0 = (g.by0 + ly) * SWFO_TILE;
             for (int r = 0; r < 16; r++) {
               int Y = Y0 + r;
@@ -702,10 +776,15 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
               for (int i = 0; i < 16; i++) {
                 int X = X0 + i;
                 if (X >= W) break;
-                int32_t a = acc[r][i];
-                if (a < 0) a = -a;
-                if (a > 65536) a = 65536;
-                uint32_t mcov = ((uint32_t)a * 255u + 32768u) >> 16;
+                uint32_t mcov;
+                if (sampled) {
+                  mcov = smask[r][i];
+                } else {
+                  int32_t a = acc[r][i];
+                  if (a < 0) a = -a;
+                  if (a > 65536) a = 65536;
+                  mcov = ((uint32_t)a * 255u + 32768u) >> 16;
+                }
                 if (!mcov) continue;
                 uint32_t src = eval_paint(&paint, X, Y);
                 fb[(size_t)Y * W + X] = over_masked(fb[(size_t)Y * W + X], src, mcov);

@@ -47,6 +47,7 @@ class Paint(C.Structure):
         ("matrix", C.c_double * 6),
         ("focal", C.c_double),
         ("lut", C.POINTER(C.c_uint32)),
+        ("sampled", C.c_int32),
     ]
 
 
@@ -383,7 +384,9 @@ def add_shape_def(b: _Builder, compiled):
                 width_state = float(line["width"])
             contours = stroker.stroke_path(_stroke_cmds(path["commands"]), width_state, False)
             segs = [(k, [x0, y0, cx, cy, x1, y1], [x0, y0, cx, cy, x1, y1]) for (k, x0, y0, cx, cy, x1, y1) in stroker.contours_to_segments(contours)]
-            paths.append((b.paint_from_fill(line["fill"]), segs))
+            paint = b.paint_from_fill(line["fill"])
+            paint.sampled = 1  # a stroke outline overlaps itself: non-zero rule per sub-scanline (raster.c: sampled_coverage)
+            paths.append((paint, segs))
     return b.add_def(paths, False)
 
 
@@ -419,6 +422,7 @@ def add_morph_shape_item(b: _Builder, compiled, matrix, ratio_u16, ratio_f=None)
                         )
                     )
             paint = b.paint_from_fill(line["fill"], morph=True)
+            paint.sampled = 1
             a = _lerp(paint.color0[3] / 255.0, paint.color1[3] / 255.0, r)
             if a <= 0:
                 continue  # invisible stroke: composites nothing

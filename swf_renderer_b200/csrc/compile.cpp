@@ -351,6 +351,7 @@ int compile_definition(const swfr_define_shape *tag, bool morph, CompiledDef &ou
       stroke_commands(cp.commands, width_state, false, ss);
       uint32_t path = (uint32_t)out.paints.size();
       out.paints.push_back(paint_from_fill(cp.line.fill, false, out));
+      out.paints.back().flags |= PF_SAMPLED;
       for (const StrokeSeg &s : ss) {
         SegMorph g{};
         for (int i = 0; i < 6; i++) g.s[i] = g.e[i] = s.p[i];

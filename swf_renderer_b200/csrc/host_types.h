@@ -25,7 +25,11 @@ struct SegMorph {
 };
 
 enum PaintType : uint32_t { PAINT_SOLID = 0, PAINT_LINEAR = 1, PAINT_FOCAL = 2, PAINT_BITMAP = 3 };
-enum PaintFlags : uint32_t { PF_COLOR_MORPH = 1u, PF_OPAQUE_RAMP = 2u };
+enum PaintFlags : uint32_t {
+  PF_COLOR_MORPH = 1u,
+  PF_OPAQUE_RAMP = 2u,
+  PF_SAMPLED = 4u  // stroke outline (overlaps itself): coverage by the non-zero rule per sub-scanline
+};
 
 // Per-path paint of a definition ("style table" entry).
 struct DefPaint {

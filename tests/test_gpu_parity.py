@@ -277,3 +277,24 @@ def test_gather_frames_between_renderers_in_one_process(built_library):
         ra.gather_frames([ra.export_frames(), rb.export_frames()])
     ra.close()
     rb.close()
+
+
+@pytest.mark.parametrize("ratio_f", [-0.5, 1.4, 2.0])
+def test_morph_ratio_outside_unit_interval_extrapolates(built_library, ratio_f):
+    """The reference lerps with any number (canvas-renderer.ts:24-26: end * r + start * (1 - r)); a float ratio outside
+    [0, 1] extrapolates the geometry past both morph states, and the tile bbox (built from the two states' bounds) grows
+    with it instead of cutting the shape off."""
+    tag = corpus.load_ast(corpus.MORPH_SAMPLE)
+    w, h, m = corpus.fixture_canvas(tag)
+    sc = corpus.Scene(3 * w, 3 * h)
+    m = [1.0, 1.0, 0.0, 0.0, m[4] + w * 20.0, m[5] + h * 20.0]
+    sc.draw_morph(sc.add_morph(tag), m, 0, ratio_f=ratio_f)
+    ref, info = corpus.render_oracle(sc, want_debug=True)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    edges, _ = r.debug_edges(0)
+    np.testing.assert_array_equal(edges, info["edges"])
+    np.testing.assert_array_equal(r.debug_tile_counts(0), info["tile_counts"])
+    r.close()
+    assert np.array_equal(out, ref) and out[..., 3].any()

@@ -388,8 +388,8 @@ def _oracle_frame(frame_index, n_shapes, w, h, rs=1.0):
     "w,h,rs,n_frames,fpp,check",
     [
         # bench.py's headline configuration: 10 000 shapes per frame at 1080p, ONE batch, library defaults (4 depth
-        # chunks, 16 frames per pass, passes alternating over two arenas / streams); one frame of passes 0, 1 and 2
-        (1920, 1080, 1.0, 33, 0, (0, 17, 32)),
+        # chunks, 32 frames per pass, passes alternating over two arenas / streams); one frame of passes 0, 1 and 2
+        (1920, 1080, 1.0, 65, 0, (0, 40, 64)),
         # bench.py's 4K line: radii x2, 8 frames per pass; one frame of passes 0 and 1
         (3840, 2160, 2.0, 9, 8, (3, 8)),
     ],
@@ -440,4 +440,52 @@ def test_benchmarked_configuration_matches_oracle(built_library, w, h, rs, n_fra
         frames = host[i].numpy().reshape(n_frames, h, w, 4)
         for f in check:
             assert np.array_equal(frames[f], want[f]), "streamed render %d, frame %d differs from the oracle" % (i, f)
+    r.close()
+
+
+def test_slot_memory_scales_with_area_times_count(built_library):
+    """1000 translucent full-screen paths at 3840x2160: slot memory is one slot per (path, tile of its bbox) - 32.4 M
+    slots, far beyond the start-up heuristics.  The render must come out right after at most a few grow-and-re-run
+    rounds (every overflowing counter reports the size it needs), not thrash the retry limit."""
+    import swf_renderer_b200 as sw
+
+    W, H, N = 3840, 2160, 1000
+    big = 20 * 4200
+    tag = {
+        "id": 1,
+        "bounds": {"x_min": -200, "x_max": big, "y_min": -200, "y_max": big},
+        "shape": {
+            "initial_styles": {"fill": [{"type": "solid", "color": {"r": 200, "g": 40, "b": 90, "a": 64}}], "line": []},
+            "records": [
+                {"type": "style-change", "move_to": {"x": -200, "y": -200}, "right_fill": 1},
+                {"type": "edge", "delta": {"x": big + 200, "y": 0}},
+                {"type": "edge", "delta": {"x": 0, "y": big + 200}},
+                {"type": "edge", "delta": {"x": -big - 200, "y": 0}},
+                {"type": "edge", "delta": {"x": 0, "y": -big - 200}},
+            ],
+        },
+    }
+    r = sw.HeadlessRenderer(W, H)
+    sid = r.register_shape(tag)
+    st = sw.Stage([sw.StoredShape(sid, sw.Matrix2D([1.0, 1.0, 0.0, 0.0, 0.0, 0.0])) for _ in range(N)])
+    r.render(st)
+    out = r.get_image(premultiplied=True).data
+    stats = r.stats()
+    assert stats["retries"] <= 3, stats
+    assert stats["n_slots"] == N * ((W + 15) // 16) * ((H + 15) // 16)
+
+    def mul_un8(a, b):
+        t = a * b + 0x80
+        return ((t >> 8) + t) >> 8
+
+    # the solid colour goes through Cairo's 16-bit premultiplied path (DESIGN.md section 5), then N times source-over
+    af = float(np.float32(64 / 255.0))
+    a16 = int(af * 65535.0 + 0.5)
+    src = [int(((c / 255.0) * af) * 65535.0 + 0.5) >> 8 for c in (200, 40, 90)] + [a16 >> 8]
+    px = [0, 0, 0, 0]
+    for _ in range(N):
+        px = [s + mul_un8(d, 255 - src[3]) for s, d in zip(src, px)]
+    assert (out == np.array(px, dtype=np.uint8)).all(), (out[0, 0].tolist(), px)
+    r.render(st)  # working memory is large enough now
+    assert r.stats()["retries"] == 0
     r.close()

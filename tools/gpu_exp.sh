@@ -37,7 +37,8 @@ for l in open(sys.argv[1]):
 PY
 done
 [ "$NCU" = "0" ] && exit 0
-PCMD="python bench.py --frames 16 --frames-per-pass 16 --steps 1 --warmup 3 --no-cpu-baseline --uhd-frames 0 --quick"
+# one pass of the default size (32 frames): every kernel of a render once, k_fine twice (slices of 16 frames)
+PCMD="python bench.py --frames 32 --steps 1 --warmup 3 --no-cpu-baseline --uhd-frames 0 --quick"
 timeout 300 $PCMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain_$TAG.log; exit 1; }
 L=$(python -c "import json,sys; print(json.loads(open('gpurun_out/plain_$TAG.log').read().strip().splitlines()[-1])['launches_per_render'])")
 echo "launches per render: $L"
