@@ -682,14 +682,43 @@ def run_ours(a):
     e2e_value = world * px_per_step * a.steps / e2e_s / 1e6
     checksum = int(host_out[(a.steps - 1) & 1][:: 4096].to(torch.int64).sum().item())
     e2e_frame0 = host_out[(a.steps - 1) & 1][: a.width * a.height * 4].numpy().reshape(a.height, a.width, 4).copy()
-    # the same call sequence without overlap between steps (sync after every step), for reference
-    t0 = time.perf_counter()
-    n_serial = 0 if a.quick else min(a.steps, 5)
-    for i in range(n_serial):
-        r.render_stage_array(stage_arr, a.frames)
-        r.read_frames_async(0, a.frames, host_out[i & 1].data_ptr())
-        r.sync()
-    e2e_serial_ms = (time.perf_counter() - t0) / max(n_serial, 1) * 1e3 if n_serial else None
+    # the same call sequence without overlap between steps (sync after every step), for reference: max over ranks
+    # between barriers, like every other multi-GPU number
+    n_serial = 0 if a.quick else min(a.steps, 8)
+    e2e_serial_ms = None
+    if n_serial:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_serial):
+            r.render_stage_array(stage_arr, a.frames)
+            r.read_frames_async(0, a.frames, host_out[i & 1].data_ptr())
+            r.sync()
+        e2e_serial_ms = max_over_ranks(time.perf_counter() - t0) / n_serial * 1e3
+    # what the box can move: every rank copies its finished frames (the same bytes, nothing else running) from HBM to
+    # its pinned host buffer, all ranks at once; device-timed between barriers, max over ranks
+    d2h_ceiling = None
+    if not a.quick:
+        frames_dev = r.device_frames().reshape(-1)
+        dst = host_out[0]
+        cs = torch.cuda.Stream()
+        n_copy = 6
+        barrier()
+        with torch.cuda.stream(cs):
+            dst.copy_(frames_dev, non_blocking=True)  # warm-up
+            cs.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            c0.record(cs)
+            for _ in range(n_copy):
+                dst.copy_(frames_dev, non_blocking=True)
+            c1.record(cs)
+            cs.synchronize()
+        barrier()
+        cms = max_over_ranks(c0.elapsed_time(c1)) / n_copy
+        d2h_ceiling = {"GB/s_aggregate": world * d2h_bytes / (cms / 1e3) / 1e9, "GB/s_per_gpu": d2h_bytes / (cms / 1e3) / 1e9,
+                       "ms_per_step_equivalent": cms, "value_equivalent": world * px_per_step / (cms / 1e3) / 1e6,
+                       "how": "all %d rank(s) copy %d MB HBM -> pinned host concurrently, nothing else running; CUDA events, max "
+                              "over ranks" % (world, d2h_bytes // 1000000)}
 
     # ---- optional: gather the finished frames of all ranks onto rank 0, device to device (not part of `value` / `e2e`) ----
     gather = None
@@ -823,6 +852,7 @@ def run_ours(a):
                 "mode": "streaming: render_batch(host stages) + read_frames_async(pinned) per step, 2 output buffers, "
                         "sync at the end",
                 "ms_per_step_sync_every_step": e2e_serial_ms,
+                "d2h_ceiling": d2h_ceiling,
                 "numa": numa,
                 "checksum": checksum,
             },

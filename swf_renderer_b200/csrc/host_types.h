@@ -80,7 +80,7 @@ struct DefEntry {
   uint32_t seg_first, seg_count;  // into the static or morph segment store
   uint32_t paint_first, path_count;
   uint32_t is_morph;
-  uint32_t pad;
+  uint32_t has_sampled;  // a path of the definition is a stroke outline (PF_SAMPLED)
 };
 
 // ---- host-only ---------------------------------------------------------------------------------------

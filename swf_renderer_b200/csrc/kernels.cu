@@ -1580,7 +1580,41 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
     int jj = rep ? floormod(j0, p.bh, p.inv_bh) : j0;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     const int ncol = (int)ceilf(hix) - i0;  // texel columns i0 .. i0 + ncol - 1 are those with (float)i < hix
-    if (ncol <= 3) {
+    const int nrow = (int)ceilf(hiy) - j0;  // texel rows likewise
+    if (ncol <= 2 && nrow <= 2) {
+      // bilinear footprint (no minification: a 1 x 1 texel box): at most 2 x 2 taps, straight-line code.  Same taps, same
+      // weights, same order (rows outer, columns inner) as the general loops below.
+      float wx[2], wy[2], xs[2], ys[2];
+      bool vx[2], vy[2];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int i = i0 + c;
+        int t = ii0 + c;
+        if (rep && t >= p.bw) t -= p.bw;
+        xs[c] = (float)t + 0.5f;
+        vx[c] = c < ncol && (rep || (i >= 0 && i < p.bw));
+        wx[c] = fmaxf(fminf(hix, (float)(i + 1)) - fmaxf(lox, (float)i), 0.0f) * irx;
+        const int j = j0 + c;
+        int u = jj + c;
+        if (rep && u >= p.bh) u -= p.bh;
+        ys[c] = (float)u + 0.5f;
+        vy[c] = c < nrow && (rep || (j >= 0 && j < p.bh));
+        wy[c] = fmaxf(fminf(hiy, (float)(j + 1)) - fmaxf(loy, (float)j), 0.0f) * iry;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          if (!(vy[rr] && vx[c])) continue;
+          const uchar4 t = tex2D<uchar4>(tex, xs[c], ys[rr]);
+          const float wgt = wx[c] * wy[rr];
+          acc0 = fmaf(wgt, (float)t.x, acc0);
+          acc1 = fmaf(wgt, (float)t.y, acc1);
+          acc2 = fmaf(wgt, (float)t.z, acc2);
+          acc3 = fmaf(wgt, (float)t.w, acc3);
+        }
+      }
+    } else if (ncol <= 3) {
       // the usual footprints (bilinear, 2x minification): column weights, wrapped column indices and validity are
       // computed once per pixel instead of once per tap; the taps are visited in the same order (rows outer, columns
       // inner) with the same operands, so the sums are the oracle's
@@ -1888,6 +1922,9 @@ __device__ __noinline__ uint2 slot_coverage_sampled(const unsigned long long *__
 
 // Four resident blocks per SM (64 registers per thread): measured best - 3 blocks at 80 registers 0.75 ms per launch,
 // 4 at 64 0.54, 5 at 48 and 6 at 40 0.56 (1080p / 10 k shapes, 16 frames per launch).
+// SAMPLED: the pass draws stroke outlines (RenderArgs.has_sampled).  The variant without them does not carry the call to
+// slot_coverage_sampled (measured: its stack frame and register pressure cost the hot path 5 %).
+template <bool SAMPLED>
 __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
   pdl_wait();  // (no launch_dependents: the successor's blocks would only squat in the slots the tail frees)
   if (a.totals->overflow | a.totals->overflow_stage) {
@@ -1897,7 +1934,7 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
   __shared__ int acc_sh[kFineWarps][16 * kAccStride];
   __shared__ int cross_sh[kFineWarps][20];
   __shared__ uint4 paint_sh[kFineWarps][sizeof(PaintInst) / 16];  // the paint instance the warp is compositing
-  __shared__ int4 samp_sh[kFineWarps][kMaxSampled];               // decoded records of a slot of a stroke outline
+  __shared__ int4 samp_sh[SAMPLED ? kFineWarps : 1][SAMPLED ? kMaxSampled : 1];  // decoded records of a slot of a stroke outline
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t n_hits = 0, n_recs = 0;  // statistics (swfr_stats.fine_*): per warp, posted once at the end
   int *acc = acc_sh[warp];
@@ -1967,9 +2004,9 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
         if (o1 == o0) {
 #pragma unroll
           for (int i = 0; i < 8; i++) m[i] = 255u;
-        } else if (((info >> 9) & 1u) && o1 - o0 <= (uint32_t)kMaxSampled) {
+        } else if (SAMPLED && ((info >> 9) & 1u) && o1 - o0 <= (uint32_t)kMaxSampled) {
           // a stroke outline: non-zero rule per sub-scanline (masks come back packed, four per word)
-          const uint2 mp = slot_coverage_sampled(a.records + o0, o1 - o0, bd, acc, samp_sh[warp], lane);
+          const uint2 mp = slot_coverage_sampled(a.records + o0, o1 - o0, bd, acc, samp_sh[SAMPLED ? warp : 0], lane);
 #pragma unroll
           for (int i = 0; i < 8; i++) m[i] = ((i < 4 ? mp.x : mp.y) >> (8 * (i & 3))) & 255u;
         } else {
@@ -2228,7 +2265,10 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   {
     const uint32_t fs = fine_slice_frames(a.n_frames), ns = fine_slices(a.n_frames);
     for (uint32_t k = 0; k < ns; k++) {
-      launch_k(k_fine, dim3(kNumSM * fine_blocks), dim3(kFineWarps * 32), st, a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
+      if (a.has_sampled)
+        launch_k(k_fine<true>, dim3(kNumSM * fine_blocks), dim3(kFineWarps * 32), st, a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
+      else
+        launch_k(k_fine<false>, dim3(kNumSM * fine_blocks), dim3(kFineWarps * 32), st, a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
       launches++;
       if (slice_done) cudaEventRecord(slice_done[k], st);
     }

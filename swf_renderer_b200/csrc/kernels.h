@@ -123,6 +123,7 @@ struct RenderArgs {
   // occlusion culling by depth chunks: the items of every frame are split into n_chunks ranges
   // in paint order; chunks are binned from the top one down, and what a chunk finds completely covered by an opaque
   // path hides the geometry of the chunks below it
+  uint32_t has_sampled;         // host-known: the pass draws stroke outlines (k_fine<true>: coverage by sub-scanlines for them)
   uint32_t n_chunks;            // host-known
   const uint32_t *chunk_items;  // (n_chunks + 1) * n_frames: first item of chunk c in frame f at [c * n_frames + f]
   uint32_t *tile_cover;         // n_frames * tiles: 1 + the highest path instance that covers the tile opaquely, 0 = none

@@ -90,6 +90,7 @@ struct Pass {
   // offsets into the batch-wide host/device arrays
   size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0, chunk_at = 0;
   uint32_t n_chunks = 1;  // depth chunks for occlusion culling
+  bool has_sampled = false;  // a frame of the pass draws a stroke outline: k_fine with the sub-scanline coverage routine
 };
 
 struct BitmapRes {
@@ -371,6 +372,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   };
   struct FrameSum {
     uint64_t seg = 0, path = 0, items = 0;
+    bool sampled = false;  // the frame draws a stroke outline
     int err = SWFR_OK;
     uint32_t bad_id = 0;
     std::vector<DynItem> dyn;
@@ -430,6 +432,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         s.seg += de->seg_count;
         s.path += de->path_count;
         s.items += 1;
+        s.sampled |= de->has_sampled != 0;
         if (pr.kind == SWFR_PRIM_MORPH_SHAPE && r->morph_strokes[pr.id]) {
           DynItem d;
           d.prim = i;
@@ -439,6 +442,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
           d.seg_count = (uint32_t)s.dyn_segs.size() - d.seg_at;
           d.paint_count = (uint32_t)s.dyn_paints.size() - d.paint_at;
           if (d.paint_count) {
+            s.sampled = true;
             s.dyn.push_back(d);
             s.seg += d.seg_count;
             s.path += d.paint_count;
@@ -479,6 +483,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
       seg_run += sums[f].seg;
       path_run += sums[f].path;
       it_run += sums[f].items;
+      p.has_sampled |= sums[f].sampled;
       dyn_seg_at += sums[f].dyn_segs.size();
       dyn_paint_at += sums[f].dyn_paints.size();
     }
@@ -750,6 +755,7 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.def_paints = r->d_paints.as<DefPaint>();
   a.frame_bg = b.d_frame_bg.as<uint32_t>() + p.f0;
   a.n_chunks = p.n_chunks;
+  a.has_sampled = p.has_sampled ? 1u : 0u;
   a.chunk_items = b.d_chunk_items.as<uint32_t>() + p.chunk_at;
   a.tile_cover = A.tile_cover.as<uint32_t>();
   a.path_alive = A.path_alive.as<uint32_t>();
@@ -1061,6 +1067,8 @@ int register_def(swfr_renderer *r, const swfr_define_shape *tag, bool morph, uin
   de.paint_first = (uint32_t)r->h_paints.size();
   de.path_count = (uint32_t)def->paints.size();
   de.seg_count = (uint32_t)def->segs.size();
+  for (const DefPaint &p : def->paints)
+    if (p.flags & PF_SAMPLED) de.has_sampled = 1;
   size_t ramp_base = r->h_ramps.size() / kRampSize;
   for (auto &l : def->luts) r->h_ramps.insert(r->h_ramps.end(), l.begin(), l.end());
   for (DefPaint p : def->paints) {

@@ -41,10 +41,15 @@ def test_library_holds_sm_100a_code_only(built_library):
 
 def test_k_fine_fits_four_blocks_per_sm_without_spills(built_library):
     res = _usage()
-    for name, (reg, stack, shared, local) in _one(res, "6k_fineE").items():
+    # k_fine<false>: passes without stroke outlines (the benchmarked stream): 64 registers, no stack at all
+    for name, (reg, stack, shared, local) in _one(res, "6k_fineILb0").items():
         assert reg <= 64, (name, reg)
-        # the only stack is the frame of the call to the out-of-line coverage routine of stroke outlines
-        # (slot_coverage_sampled): registers saved around it, on that path only; the hot path spills nothing
+        assert stack == 0 and local == 0, (name, stack, local)
+        assert shared <= 227 * 1024 // 4
+    # k_fine<true>: the only stack is the frame of the call to the out-of-line coverage routine of stroke outlines
+    # (slot_coverage_sampled): registers saved around it, on that path only
+    for name, (reg, stack, shared, local) in _one(res, "6k_fineILb1").items():
+        assert reg <= 64, (name, reg)
         assert stack <= 32 and local == 0, (name, stack, local)
         assert shared <= 227 * 1024 // 4
 
