@@ -284,6 +284,12 @@ int swfr_read_frames_async(swfr_renderer *r, uint32_t first, uint32_t count, uin
 /* Device pointer of frame 0 of the last render (premultiplied RGBA8, frames width*height*4 bytes apart). */
 int swfr_device_frames(swfr_renderer *r, void **out_ptr, uint32_t *out_n_frames);
 
+/* The outline the device stroker generates for one draw of a morph shape's strokes at `ratio` (lerped path and width,
+ * round caps and joins: canvas-renderer.ts:252-266), computed by the same code on the host - no renderer, no CUDA: 8
+ * doubles per segment (curve flag, line path index, x0, y0, cx, cy, x1, y1 in twips). */
+int swfr_debug_morph_stroke(const swfr_define_shape *tag, double ratio, double *out, uint64_t cap, uint64_t *n_segs,
+                            uint32_t *n_paths);
+
 /* ---- optional gather of finished frames onto one GPU (off the hot path) --------------------
  * Frames shard over renderers (one per GPU, frame f -> renderer f mod N) with no collective; a caller that wants all
  * of them on one GPU afterwards moves them GPU to GPU over NVLink / NVSwitch with plain asynchronous peer copies:

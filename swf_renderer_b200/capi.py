@@ -278,6 +278,11 @@ PROTOTYPES["swfr_gather_frames"] = (
 )
 PROTOTYPES["swfr_gather_last_ms"] = (C.c_int, [C.c_void_p, C.POINTER(C.c_float)])
 
+PROTOTYPES["swfr_debug_morph_stroke"] = (
+    C.c_int,
+    [C.POINTER(DefineShape), C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)],
+)
+
 _LIB = None
 
 

@@ -240,6 +240,11 @@ __device__ __forceinline__ uint32_t chunk_first(const RenderArgs &a, uint32_t c,
   return __ldg(a.chunk_items + c * a.n_frames + frame);
 }
 
+// Unused entries of a stroke outline's reserved room in the dynamic segment store (k_stroke) are no segments at all.
+__device__ __forceinline__ bool segment_is_null(const RenderArgs &a, const ItemRegs &item, uint32_t local) {
+  return item.kind == ITEM_DYNAMIC && __ldg(&a.segs_dynamic[item.seg_first + local].path_flags) == kNullSegment;
+}
+
 // Path instance of segment `local` of a draw item (without transforming the segment).
 __device__ __forceinline__ uint32_t segment_pid(const RenderArgs &a, const ItemRegs &item, uint32_t local) {
   uint32_t pf;
@@ -294,8 +299,12 @@ __global__ void k_flatten_count(RenderArgs a) {
       int p[6];
       bool curve;
       uint32_t pid;
-      load_segment(a, item, j - s0, p, curve, pid);
-      a.seg_edge_off[j] = (uint32_t)piece_count(curve, p);
+      uint32_t n = 0;
+      if (!segment_is_null(a, item, j - s0)) {
+        load_segment(a, item, j - s0, p, curve, pid);
+        n = (uint32_t)piece_count(curve, p);
+      }
+      a.seg_edge_off[j] = n;
       a.seg_item[j] = it;
     }
   }
@@ -465,7 +474,7 @@ __device__ __forceinline__ void emit_segments(const RenderArgs &a, int (*sh_p)[6
         head.seg_first = __ldg(&a.items[it].seg_first);
         head.path_off = __ldg(&a.items[it].path_off);
         head.kind = __ldg(&a.items[it].kind) & ITEM_KIND_MASK;
-        visible = __ldg(a.path_alive + segment_pid(a, head, local)) != 0;
+        visible = !segment_is_null(a, head, local) && __ldg(a.path_alive + segment_pid(a, head, local)) != 0;
       }
       if (visible) {  // hidden paths emit nothing (their edges stay marked ~0)
         const ItemRegs item = load_item(a, it);
@@ -567,6 +576,42 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_flatten_emit(RenderArgs a, 
       for (uint32_t base = s0; base < s1; base += 32) emit_segments<false>(a, sh_p[w], sh_inv[w], sh_pid[w], lane, base + lane, base + lane < s1, it);
     }
   }
+}
+
+// ======================================================================================================
+// Device stroker: the outlines of morph-shape strokes, per draw, at the draw's ratio
+// (canvas-renderer.ts:252-266: lerped path and width, round caps and joins).  One thread per draw runs the streaming
+// generator of stroke_core.h - FP64 + - * / sqrt in the host stroker's order, so the float32 segments are the oracle's
+// bit for bit - over the morph shape's lines, writes the segments into the room reserved for the draw in the dynamic
+// segment store, the bounds of every visible line path into its dynamic paint, and marks the unused room empty.  An
+// outline that outgrows its room raises overflow bit 6: the host lays the batch out again with exact counts.
+// ======================================================================================================
+__global__ void __launch_bounds__(64) k_stroke(RenderArgs a) {
+  pdl_enter();
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n_jobs) return;
+  const StrokeJob job = a.jobs[j];
+  SegStatic *out = a.segs_dynamic + job.seg_first;
+  double width_state = 1.0;  // Canvas default lineWidth; a zero width is ignored and the previous one stays
+  uint32_t used = 0, need = 0, path = 0;
+  for (uint32_t l = 0; l < job.line_count; l++) {
+    const stroke::LineDev ln = a.mlines[job.line_first + l];
+    const double w = stroke::lerp(ln.w0, ln.w1, job.ratio);
+    if (w > 0) width_state = w;
+    const double al = stroke::lerp(ln.color0[3] / 255.0, ln.color1[3] / 255.0, job.ratio);
+    if (al <= 0) continue;  // composites nothing (the host left it out of the draw's paths the same way)
+    stroke::Sink sink{out + used, job.seg_cap - used, 0, path, {1.f, 1.f, 0.f, 0.f}, false, 0.f, 0.f, 0.f, 0.f};
+    stroke::stroke_line(a.mcmds + ln.cmd_first, ln.cmd_count, job.ratio, width_state, sink);
+    need += sink.n;
+    used += min(sink.n, job.seg_cap - used);
+    if (path < job.path_count) {
+      float *b = a.paints_dynamic[job.paint_first + path].bounds;
+      b[0] = sink.bounds[0], b[1] = sink.bounds[1], b[2] = sink.bounds[2], b[3] = sink.bounds[3];
+    }
+    path++;
+  }
+  for (uint32_t k = used; k < job.seg_cap; k++) out[k].path_flags = kNullSegment;
+  if (need > job.seg_cap) atomicOr(&a.totals->overflow, 64u);
 }
 
 // ======================================================================================================
@@ -2206,6 +2251,10 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   // One depth chunk: every path is flattened, edges in segment order (the taps' mode).  More: only what is visible is
   // flattened, unordered, chunk by chunk.
   const bool ordered = a.n_chunks == 1;
+  if (a.n_jobs) {  // outlines of morph-shape strokes, generated on the device for this pass' draws
+    launch_k(k_stroke, dim3((a.n_jobs + 63) / 64), dim3(64), st, a);
+    launches++;
+  }
   if (a.n_seginst) {
     if (ordered) {
       launch_k(k_flatten_count, dim3(grid_for((uint64_t)a.n_items * 32)), dim3(T), st, a);

@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "host_types.h"
+#include "stroke_core.h"
 
 namespace swfr {
 
@@ -59,6 +60,18 @@ struct PaintInst {
 };
 static_assert(sizeof(PaintInst) == 80, "PaintInst is staged as five uint4");
 
+// One draw of a morph shape's strokes: the device stroker (k_stroke) writes its outline into the batch's dynamic
+// segment store, seg_cap entries from seg_first on (unused ones are marked empty), and the bounds of every visible line
+// path into the batch's dynamic paints.
+struct StrokeJob {
+  uint32_t line_first, line_count;  // the morph shape's lines (stroke::LineDev)
+  uint32_t seg_first, seg_cap;      // into the dynamic segment store
+  uint32_t paint_first, path_count; // into the dynamic paints: the lines visible at this ratio, in order
+  uint32_t item, morph_id;          // host bookkeeping: the draw item of the outline, the morph shape
+  double ratio;
+};
+constexpr uint32_t kNullSegment = 0xffffffffu;  // path_flags of an unused entry of the dynamic segment store
+
 struct BitmapDev {
   unsigned long long tex;
   int32_t w, h;
@@ -71,7 +84,8 @@ constexpr int kMaxFineSlices = 16;    // leave for the host while the rest of th
 
 struct Totals {
   uint32_t n_edges, n_slots, n_records;
-  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists, bit4 row lists, bit5 arena dirty (see k_init)
+  uint32_t overflow;  // bit0 edges, bit1 slots, bit2 records, bit3 candidate lists, bit4 row lists, bit5 arena dirty (see k_init),
+                      // bit6 a stroke outline outgrew the segments reserved for it (k_stroke)
   uint32_t error;     // bit0: unknown bitmap id
   uint32_t work[kMaxFineSlices];  // fine-kernel tile queues, one per slice of frames
   uint32_t n_list;    // candidate-list entries
@@ -101,8 +115,12 @@ struct RenderArgs {
   const SegStatic *segs_static;
   const SegMorph *segs_morph;
   const DefPaint *def_paints;
-  const SegStatic *segs_dynamic;   // per batch (ITEM_DYNAMIC)
-  const DefPaint *paints_dynamic;  // per batch (ITEM_DYNAMIC)
+  SegStatic *segs_dynamic;         // per batch (ITEM_DYNAMIC): written by k_stroke
+  DefPaint *paints_dynamic;        // per batch (ITEM_DYNAMIC): bounds written by k_stroke
+  const StrokeJob *jobs;           // stroke jobs of the pass
+  uint32_t n_jobs;                 // host-known
+  const stroke::LineDev *mlines;   // morph lines and their commands (asset store)
+  const stroke::CmdDev *mcmds;
   const uint32_t *ramps;  // kRampSize premultiplied RGBA8 entries per gradient
   const BitmapDev *bitmaps;
   uint32_t *seg_edge_off;   // n_seginst + 1 (piece counts, then exclusive scan)

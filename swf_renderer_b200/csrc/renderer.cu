@@ -24,6 +24,7 @@
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
 
 #include "kernels.h"
+#include "stroke_core.h"
 
 using namespace swfr;
 
@@ -90,6 +91,7 @@ struct Pass {
   // offsets into the batch-wide host/device arrays
   size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0, chunk_at = 0;
   uint32_t n_chunks = 1;  // depth chunks for occlusion culling
+  uint32_t job_first = 0, n_jobs = 0;  // stroke jobs of the pass' frames
   bool has_sampled = false;  // a frame of the pass draws a stroke outline: k_fine with the sub-scanline coverage routine
 };
 
@@ -122,9 +124,12 @@ struct swfr_batch {
   PinnedArr<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
   PinnedArr<uint32_t> chunk_items;                   // per pass: (n_chunks + 1) x n_frames first items of the depth chunks
   PinnedArr<uint32_t> frame_bg;                      // per frame: premultiplied RGBA8 the frame starts from
-  PinnedArr<SegStatic> dyn_segs;                     // outlines of morph-shape strokes expanded for this batch's draws
+  // Strokes of morph shapes: every such draw is a job for the device stroker (k_stroke), which writes the outline's
+  // segments into the batch's dynamic segment store (device only: dyn_seg_count entries) and the bounds into its paints
   PinnedArr<DefPaint> dyn_paints;
-  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints, d_frame_bg, d_chunk_items;
+  PinnedArr<StrokeJob> jobs;  // in frame order: the jobs of a pass are contiguous
+  size_t dyn_seg_count = 0;
+  DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints, d_frame_bg, d_chunk_items, d_jobs;
   bool resident = false;
   uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
   cudaEvent_t uploaded = nullptr;  // recorded on the upload stream after the H2D copies
@@ -148,7 +153,19 @@ struct swfr_renderer {
   std::vector<DefPaint> h_paints;
   std::vector<uint32_t> h_ramps;
   std::vector<DefEntry> shape_defs, morph_defs;
-  std::vector<std::shared_ptr<std::vector<MorphLine>>> morph_strokes;  // non-null: the morph shape has visible strokes
+  // Morph shapes with visible strokes: their line paths live on the device (lines + commands, both morph states); the
+  // outline of every draw is generated there (k_stroke).  seg_cap = segments reserved per draw: the largest outline
+  // found at five ratios at registration plus a margin; an outline that outgrows it is found by the device and the
+  // batch is laid out again with exact counts (relayout_strokes).
+  struct MorphStroke {
+    uint32_t line_first = 0, line_count = 0;  // into h_mlines; line_count == 0: no visible stroke
+    uint32_t seg_cap = 0;
+  };
+  std::vector<MorphStroke> morph_strokes;  // by morph shape id
+  std::vector<stroke::LineDev> h_mlines;
+  std::vector<stroke::CmdDev> h_mcmds;
+  DevBuf d_mlines, d_mcmds;
+  size_t up_mlines = 0, up_mcmds = 0;
   std::vector<std::unique_ptr<CompiledDef>> shape_dbg, morph_dbg;
   DevBuf d_static, d_morph, d_paints, d_ramps, d_bitmaps;
   size_t up_static = 0, up_morph = 0, up_paints = 0, up_ramps = 0;  // elements already uploaded
@@ -283,6 +300,10 @@ int flush_store(swfr_renderer *r) {
   CK(up(r->d_morph, r->h_morph.data(), sizeof(SegMorph), r->h_morph.size(), r->up_morph));
   CK(up(r->d_paints, r->h_paints.data(), sizeof(DefPaint), r->h_paints.size(), r->up_paints));
   CK(up(r->d_ramps, r->h_ramps.data(), sizeof(uint32_t), r->h_ramps.size(), r->up_ramps));
+  CK(up(r->d_mlines, r->h_mlines.data(), sizeof(stroke::LineDev), r->h_mlines.size(), r->up_mlines));
+  CK(up(r->d_mcmds, r->h_mcmds.data(), sizeof(stroke::CmdDev), r->h_mcmds.size(), r->up_mcmds));
+  CK(r->d_mlines.reserve(256));
+  CK(r->d_mcmds.reserve(256));
   CK(r->d_static.reserve(256));
   CK(r->d_morph.reserve(256));
   CK(r->d_paints.reserve(256));
@@ -294,54 +315,47 @@ int flush_store(swfr_renderer *r) {
   return SWFR_OK;
 }
 
-static inline double lerp_host(double start, double end, double r) {  // canvas-renderer.ts:24-26
-  double a = end * r;
-  double b = 1.0 - r;
-  double c = start * b;
-  return a + c;
+// Morph lines as the device stroker reads them: lines + commands, both morph states, appended to the two stores.
+static void morph_lines_to_device(const std::vector<MorphLine> &src, std::vector<stroke::LineDev> &lines, std::vector<stroke::CmdDev> &cmds) {
+  for (const MorphLine &ml : src) {
+    stroke::LineDev ln{};
+    ln.cmd_first = (uint32_t)cmds.size();
+    ln.cmd_count = (uint32_t)ml.commands.size();
+    ln.w0 = ml.w0;
+    ln.w1 = ml.w1;
+    memcpy(ln.color0, ml.color0, 4);
+    memcpy(ln.color1, ml.color1, 4);
+    for (const Command &c : ml.commands) {
+      stroke::CmdDev cd{};
+      cd.type = c.type;
+      for (int k = 0; k < 4; k++) cd.s[k] = c.s[k], cd.e[k] = c.e[k];
+      cmds.push_back(cd);
+    }
+    lines.push_back(ln);
+  }
 }
 
-// Outlines of the line paths of a morph shape at ratio r (canvas-renderer.ts:252-266: lerped path and width, round
-// caps and joins, a zero width keeps the previous one), as a transient static definition: one solid paint (its
-// colour still morphs on the device) and its fill segments per visible line.
-static void expand_morph_strokes(const std::vector<MorphLine> &lines, double r, std::vector<SegStatic> &segs,
-                                 std::vector<DefPaint> &paints) {
+// Visible line paths and outline segments of one draw of a morph shape's strokes at ratio r (host run of the
+// generator the device runs per draw: registration-time estimate and the exact counts of a relayout).
+static void count_morph_strokes(const swfr_renderer *r, const swfr_renderer::MorphStroke &ms, double ratio, uint32_t *n_paths,
+                                uint32_t *n_segs) {
   double width_state = 1.0;
-  std::vector<Command> cmds;
-  std::vector<StrokeSeg> ss;
-  const size_t paint0 = paints.size(), seg0 = segs.size();  // path indices are local to this draw
-  for (const MorphLine &ml : lines) {
-    double w = lerp_host(ml.w0, ml.w1, r);
+  uint32_t paths = 0, segs = 0;
+  for (uint32_t l = 0; l < ms.line_count; l++) {
+    const stroke::LineDev &ln = r->h_mlines[ms.line_first + l];
+    const double w = stroke::lerp(ln.w0, ln.w1, ratio);
     if (w > 0) width_state = w;
-    double al = lerp_host(ml.color0[3] / 255.0, ml.color1[3] / 255.0, r);
+    const double al = stroke::lerp(ln.color0[3] / 255.0, ln.color1[3] / 255.0, ratio);
     if (al <= 0) continue;  // composites nothing
-    cmds.clear();
-    for (const Command &c : ml.commands) {
-      Command o;
-      o.type = c.type;
-      for (int k = 0; k < 4; k++) o.s[k] = o.e[k] = lerp_host(c.s[k], c.e[k], r);
-      cmds.push_back(o);
+    if (n_segs) {
+      stroke::Sink sink{nullptr, 0, 0, paths, {1.f, 1.f, 0.f, 0.f}, false, 0.f, 0.f, 0.f, 0.f};
+      stroke::stroke_line(r->h_mcmds.data() + ln.cmd_first, ln.cmd_count, ratio, width_state, sink);
+      segs += sink.n;
     }
-    ss.clear();
-    stroke_commands(cmds, width_state, true, ss);
-    uint32_t path = (uint32_t)(paints.size() - paint0);
-    DefPaint p{};
-    p.type = PAINT_SOLID;
-    p.lut = -1;
-    memcpy(p.color0, ml.color0, 4);
-    memcpy(p.color1, ml.color1, 4);
-    p.flags |= PF_COLOR_MORPH | PF_SAMPLED;
-    paints.push_back(p);
-    for (const StrokeSeg &sg : ss) {
-      SegStatic g;
-      memcpy(g.p, sg.p, sizeof g.p);
-      g.path_flags = path | (sg.curve ? 0x80000000u : 0u);
-      segs.push_back(g);
-    }
+    paths++;
   }
-  if (paints.size() > paint0)
-    set_paint_bounds(paints.data() + paint0, paints.size() - paint0, segs.size() > seg0 ? segs[seg0].p : nullptr, segs.size() - seg0,
-                     sizeof(SegStatic) / sizeof(float), 3, segs.size() > seg0 ? &segs[seg0].path_flags : nullptr, sizeof(SegStatic));
+  if (n_paths) *n_paths = paths;
+  if (n_segs) *n_segs = segs;
 }
 
 // Flattens stages into draw items (reference: CanvasRenderer.renderStage / drawDisplayObject,
@@ -367,8 +381,9 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   nt = std::max<uint32_t>(1, std::min<uint32_t>(nt, n));
   if (total_prims < 20000) nt = 1;
 
-  struct DynItem {  // stroke outlines of one morph primitive
-    uint32_t prim, seg_at, seg_count, paint_at, paint_count;
+  struct DynItem {  // stroke outlines of one morph primitive (a job of the device stroker)
+    uint32_t prim, seg_at, seg_count, paint_at, paint_count, morph_id;
+    double ratio;
   };
   struct FrameSum {
     uint64_t seg = 0, path = 0, items = 0;
@@ -376,7 +391,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     int err = SWFR_OK;
     uint32_t bad_id = 0;
     std::vector<DynItem> dyn;
-    std::vector<SegStatic> dyn_segs;
+    uint64_t dyn_segs = 0;  // segments reserved for the frame's stroke outlines
     std::vector<DefPaint> dyn_paints;
   };
   std::vector<FrameSum> sums(n);
@@ -433,16 +448,34 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         s.path += de->path_count;
         s.items += 1;
         s.sampled |= de->has_sampled != 0;
-        if (pr.kind == SWFR_PRIM_MORPH_SHAPE && r->morph_strokes[pr.id]) {
+        if (pr.kind == SWFR_PRIM_MORPH_SHAPE && r->morph_strokes[pr.id].line_count) {
+          // the lines that are visible at this ratio (lerped alpha > 0) become the paths of one more draw item; their
+          // geometry is left to the device (no per-draw host geometry), `seg_cap` segments are reserved for it
+          const swfr_renderer::MorphStroke &ms = r->morph_strokes[pr.id];
           DynItem d;
           d.prim = i;
-          d.seg_at = (uint32_t)s.dyn_segs.size();
+          d.morph_id = pr.id;
+          d.ratio = prim_ratio(pr);
+          d.seg_at = (uint32_t)s.dyn_segs;
           d.paint_at = (uint32_t)s.dyn_paints.size();
-          expand_morph_strokes(*r->morph_strokes[pr.id], prim_ratio(pr), s.dyn_segs, s.dyn_paints);
-          d.seg_count = (uint32_t)s.dyn_segs.size() - d.seg_at;
+          for (uint32_t l = 0; l < ms.line_count; l++) {
+            const stroke::LineDev &ln = r->h_mlines[ms.line_first + l];
+            if (stroke::lerp(ln.color0[3] / 255.0, ln.color1[3] / 255.0, d.ratio) <= 0) continue;  // composites nothing
+            DefPaint p{};
+            p.type = PAINT_SOLID;
+            p.lut = -1;
+            memcpy(p.color0, ln.color0, 4);
+            memcpy(p.color1, ln.color1, 4);
+            p.flags |= PF_COLOR_MORPH | PF_SAMPLED;
+            p.bounds[0] = p.bounds[1] = 1.0f;  // empty until the device stroker has written the outline's bounds
+            s.dyn_paints.push_back(p);
+          }
+          // (SWFR_OPT_DEBUG_TINY_ARENA: far too little room, so that the relayout after an outgrown outline is exercised)
+          d.seg_count = r->tiny_arena ? std::min<uint32_t>(ms.seg_cap, 8u) : ms.seg_cap;
           d.paint_count = (uint32_t)s.dyn_paints.size() - d.paint_at;
           if (d.paint_count) {
             s.sampled = true;
+            s.dyn_segs += d.seg_count;
             s.dyn.push_back(d);
             s.seg += d.seg_count;
             s.path += d.paint_count;
@@ -462,11 +495,11 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
 
   // pass layout + per-frame bases
   struct FrameBase {
-    size_t item_at, seg_off_at, path_off_at, frame_off_at, dyn_seg_at, dyn_paint_at;
+    size_t item_at, seg_off_at, path_off_at, frame_off_at, dyn_seg_at, dyn_paint_at, job_at;
     uint32_t seg0, path0;
   };
   std::vector<FrameBase> base(n);
-  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0, dyn_seg_at = 0, dyn_paint_at = 0;
+  size_t items_at = 0, seg_off_at = 0, path_off_at = 0, frame_off_at = 0, dyn_seg_at = 0, dyn_paint_at = 0, job_at = 0;
   for (uint32_t f0 = 0; f0 < n; f0 += fpp) {
     Pass p;
     p.f0 = f0;
@@ -477,16 +510,19 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     p.frame_off_at = frame_off_at;
     uint64_t seg_run = 0, path_run = 0;
     size_t it_run = 0;
+    p.job_first = (uint32_t)job_at;
     for (uint32_t f = f0; f < f0 + p.n_frames; f++) {
       base[f] = FrameBase{items_at + it_run, seg_off_at + it_run, path_off_at + it_run, frame_off_at + (f - f0),
-                          dyn_seg_at,        dyn_paint_at,        (uint32_t)seg_run,    (uint32_t)path_run};
+                          dyn_seg_at,        dyn_paint_at,        job_at,               (uint32_t)seg_run,    (uint32_t)path_run};
       seg_run += sums[f].seg;
       path_run += sums[f].path;
       it_run += sums[f].items;
       p.has_sampled |= sums[f].sampled;
-      dyn_seg_at += sums[f].dyn_segs.size();
+      dyn_seg_at += sums[f].dyn_segs;
       dyn_paint_at += sums[f].dyn_paints.size();
+      job_at += sums[f].dyn.size();
     }
+    p.n_jobs = (uint32_t)job_at - p.job_first;
     if (seg_run > 0xfffffff0ull || path_run > 0xfffffff0ull || it_run > 0xfffffff0ull)
       return fail(r, SWFR_ERR_INVALID_ARGUMENT, "a pass exceeds 2^32 segment instances; lower SWFR_OPT_FRAMES_PER_PASS");
     p.n_items = (uint32_t)it_run;
@@ -531,7 +567,8 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   CK(b.seg_off.resize(seg_off_at));
   CK(b.path_off.resize(path_off_at));
   CK(b.frame_off.resize(frame_off_at));
-  CK(b.dyn_segs.resize(dyn_seg_at));
+  b.dyn_seg_count = dyn_seg_at;
+  CK(b.jobs.resize(job_at));
   CK(b.dyn_paints.resize(dyn_paint_at));
   CK(b.frame_bg.resize(n));
   for (uint32_t f = 0; f < n; f++) {
@@ -554,7 +591,6 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
       uint32_t seg_run = fb.seg0, path_run = fb.path0;
       b.frame_off[fb.frame_off_at] = path_run;
       const uint32_t local_frame = f % fpp;
-      if (!fs.dyn_segs.empty()) memcpy(b.dyn_segs.data() + fb.dyn_seg_at, fs.dyn_segs.data(), fs.dyn_segs.size() * sizeof(SegStatic));
       if (!fs.dyn_paints.empty())
         memcpy(b.dyn_paints.data() + fb.dyn_paint_at, fs.dyn_paints.data(), fs.dyn_paints.size() * sizeof(DefPaint));
       size_t k = 0, next_dyn = 0;
@@ -578,12 +614,25 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         seg_run += de->seg_count;
         path_run += de->path_count;
         if (next_dyn < fs.dyn.size() && fs.dyn[next_dyn].prim == i) {  // the primitive's strokes, painted after its fills
-          const DynItem &d = fs.dyn[next_dyn++];
+          const DynItem &d = fs.dyn[next_dyn];
           it.seg_first = (uint32_t)(fb.dyn_seg_at + d.seg_at);
           it.paint_first = (uint32_t)(fb.dyn_paint_at + d.paint_at);
           it.path_off = path_run;
           it.kind = (uint16_t)(ITEM_DYNAMIC | ((pr.flags & SWFR_PRIM_RATIO_F32) ? ITEM_RATIO_F32 : 0));
           items[k] = it;
+          const swfr_renderer::MorphStroke &ms = r->morph_strokes[d.morph_id];
+          StrokeJob job{};
+          job.line_first = ms.line_first;
+          job.line_count = ms.line_count;
+          job.seg_first = it.seg_first;
+          job.seg_cap = d.seg_count;
+          job.paint_first = it.paint_first;
+          job.path_count = d.paint_count;
+          job.item = (uint32_t)(fb.item_at + k);  // index into the batch's items
+          job.morph_id = d.morph_id;
+          job.ratio = d.ratio;
+          b.jobs[fb.job_at + next_dyn] = job;
+          next_dyn++;
           so[k] = seg_run;
           po[k] = path_run;
           k++;
@@ -617,9 +666,10 @@ int upload_batch(swfr_renderer *r, swfr_batch &b) {
     CK(cudaMemcpyAsync(b.d_chunk_items.p, b.chunk_items.data(), b.chunk_items.bytes(), cudaMemcpyHostToDevice, st));
   CK(b.d_frame_bg.reserve(std::max<size_t>(b.frame_bg.bytes(), 256)));
   if (b.frame_bg.bytes()) CK(cudaMemcpyAsync(b.d_frame_bg.p, b.frame_bg.data(), b.frame_bg.bytes(), cudaMemcpyHostToDevice, st));
-  CK(b.d_dyn_segs.reserve(std::max<size_t>(b.dyn_segs.bytes(), 256)));
+  CK(b.d_dyn_segs.reserve(std::max<size_t>(b.dyn_seg_count * sizeof(SegStatic), 256)));  // written by the device stroker
   CK(b.d_dyn_paints.reserve(std::max<size_t>(b.dyn_paints.bytes(), 256)));
-  if (b.dyn_segs.bytes()) CK(cudaMemcpyAsync(b.d_dyn_segs.p, b.dyn_segs.data(), b.dyn_segs.bytes(), cudaMemcpyHostToDevice, st));
+  CK(b.d_jobs.reserve(std::max<size_t>(b.jobs.bytes(), 256)));
+  if (b.jobs.bytes()) CK(cudaMemcpyAsync(b.d_jobs.p, b.jobs.data(), b.jobs.bytes(), cudaMemcpyHostToDevice, st));
   if (b.dyn_paints.bytes())
     CK(cudaMemcpyAsync(b.d_dyn_paints.p, b.dyn_paints.data(), b.dyn_paints.bytes(), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(b.uploaded, st));
@@ -765,6 +815,10 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.arena_dirty = A.dirty.as<uint32_t>();
   a.segs_dynamic = b.d_dyn_segs.as<SegStatic>();
   a.paints_dynamic = b.d_dyn_paints.as<DefPaint>();
+  a.jobs = b.d_jobs.as<StrokeJob>() + p.job_first;
+  a.n_jobs = p.n_jobs;
+  a.mlines = r->d_mlines.as<stroke::LineDev>();
+  a.mcmds = r->d_mcmds.as<stroke::CmdDev>();
   a.ramps = r->d_ramps.as<uint32_t>();
   a.bitmaps = r->d_bitmaps.as<BitmapDev>();
   a.seg_edge_off = A.seg_edge_off.as<uint32_t>();
@@ -933,6 +987,53 @@ bool any_overflow(const Totals *t, size_t n) {
   return false;
 }
 
+// A stroke outline outgrew the segments reserved for it (overflow bit 6, found by k_stroke): the exact size of every
+// outline of the batch is counted on the host (the same generator, count only), the dynamic segment store and the
+// per-item segment offsets of every pass are laid out again, and the estimate of the morph shapes is raised so that
+// the next batch reserves enough.  Everything is synchronised when this runs (recover).
+int relayout_strokes(swfr_renderer *r, swfr_batch &b) {
+  Range range("swfr: relayout stroke outlines");
+  std::vector<uint32_t> exact(b.jobs.size());
+  for (size_t j = 0; j < b.jobs.size(); j++) {
+    swfr_renderer::MorphStroke &ms = r->morph_strokes[b.jobs[j].morph_id];
+    count_morph_strokes(r, ms, b.jobs[j].ratio, nullptr, &exact[j]);
+    ms.seg_cap = std::max(ms.seg_cap, exact[j] + exact[j] / 4 + 16);
+  }
+  size_t ji = 0, dyn_at = 0;
+  b.n_seginst = 0;
+  for (Pass &p : b.passes) {
+    uint32_t *so = b.seg_off.data() + p.seg_off_at;
+    DrawItem *items = b.items.data() + p.items_at;
+    uint64_t seg_run = 0;
+    uint32_t prev_old = so[0];
+    for (uint32_t k = 0; k < p.n_items; k++) {
+      const uint32_t next_old = so[k + 1];
+      uint32_t cnt = next_old - prev_old;
+      prev_old = next_old;
+      if ((items[k].kind & ITEM_KIND_MASK) == ITEM_DYNAMIC) {
+        if (ji >= b.jobs.size() || b.jobs[ji].item != p.items_at + k) return fail(r, SWFR_ERR_INVALID_ARGUMENT, "stroke jobs out of step");
+        cnt = exact[ji];
+        items[k].seg_first = (uint32_t)dyn_at;
+        b.jobs[ji].seg_first = (uint32_t)dyn_at;
+        b.jobs[ji].seg_cap = cnt;
+        dyn_at += cnt;
+        ji++;
+      }
+      so[k] = (uint32_t)seg_run;
+      seg_run += cnt;
+    }
+    if (seg_run > 0xfffffff0ull) return fail(r, SWFR_ERR_OOM, "a pass exceeds 2^32 segment instances");
+    so[p.n_items] = (uint32_t)seg_run;
+    p.n_seginst = (uint32_t)seg_run;
+    b.n_seginst += seg_run;
+  }
+  b.dyn_seg_count = dyn_at;
+  int rc = upload_batch(r, b);
+  if (rc != SWFR_OK) return rc;
+  CK(cudaStreamSynchronize(r->up_stream));
+  return SWFR_OK;
+}
+
 // Working memory overflowed in the oldest render in flight (the later ones ran with the same arrays and have
 // overwritten its frames): everything is synchronised, then every render in flight is run again, in order and alone,
 // growing the arrays until it fits, and its read-back requests are served again.
@@ -956,6 +1057,7 @@ int recover(swfr_renderer *r) {
           return fail(r, SWFR_ERR_OOM, "working memory kept overflowing");
         }
         Caps want = r->caps;
+        bool strokes_outgrown = false;
         auto grow = [](uint32_t need) { return (uint32_t)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0xfffffff0ull); };
         for (size_t i = 0; i < np; i++) {
           const Totals &t = pt[i];
@@ -969,6 +1071,21 @@ int recover(swfr_renderer *r) {
             uint64_t need = ((uint64_t)t.n_stage_blocks + t.n_stage_blocks / 8 + 64) * 256;
             want.stage = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want.stage, need), 0xffffff00ull);
           }
+          strokes_outgrown |= (t.overflow & 64u) != 0;
+        }
+        if (strokes_outgrown) {
+          int rc = relayout_strokes(r, b);
+          if (rc != SWFR_OK) {
+            r->inflight.clear();
+            return rc;
+          }
+          uint32_t max_seg = 0;
+          for (const Pass &p : b.passes) max_seg = std::max(max_seg, p.n_seginst);
+          for (int k = 0; k < (int)std::min<size_t>(np, (size_t)r->n_arenas); k++) {
+            CK(r->arena[k].seg_edge_off.reserve(((size_t)max_seg + 1) * 4 + 256));
+            CK(r->arena[k].seg_item.reserve((size_t)max_seg * 4 + 256));
+          }
+          want.edges = std::max<uint32_t>(want.edges, std::max<uint32_t>(1u << 16, max_seg * 4));
         }
         if (!r->tiny_arena)
           want.stage = std::max<uint32_t>(want.stage, (uint32_t)std::min<uint64_t>(((uint64_t)want.records + want.records / 4 + 65535u) & ~255ull, 0xffffff00ull));
@@ -1080,9 +1197,21 @@ int register_def(swfr_renderer *r, const swfr_define_shape *tag, bool morph, uin
     r->h_morph.insert(r->h_morph.end(), def->segs.begin(), def->segs.end());
     *out_id = (uint32_t)r->morph_defs.size();
     r->morph_defs.push_back(de);
-    r->morph_strokes.push_back(def->has_visible_morph_stroke
-                                   ? std::make_shared<std::vector<MorphLine>>(std::move(def->morph_lines))
-                                   : nullptr);
+    swfr_renderer::MorphStroke ms;
+    if (def->has_visible_morph_stroke) {
+      ms.line_first = (uint32_t)r->h_mlines.size();
+      ms.line_count = (uint32_t)def->morph_lines.size();
+      morph_lines_to_device(def->morph_lines, r->h_mlines, r->h_mcmds);
+      // room reserved per draw: the largest outline at five ratios plus a quarter
+      uint32_t most = 0;
+      for (int q = 0; q <= 4; q++) {
+        uint32_t n_segs = 0;
+        count_morph_strokes(r, ms, q / 4.0, nullptr, &n_segs);
+        most = std::max(most, n_segs);
+      }
+      ms.seg_cap = most + most / 4 + 16;
+    }
+    r->morph_strokes.push_back(ms);
     r->morph_dbg.push_back(r->retain_compiled ? std::move(def) : nullptr);
   } else {
     de.seg_first = (uint32_t)r->h_static.size();
@@ -1716,6 +1845,46 @@ int swfr_debug_segments(swfr_renderer *r, uint32_t kind, uint32_t id, double *se
   }
   if (n) *n = d.segs.size();
   return SWFR_OK;
+}
+
+// Host run of the device stroker's generator (stroke_core.h) for one morph-shape tag at one ratio: what k_stroke writes
+// for a draw.  Host only (no renderer, no CUDA).  out: 8 doubles per segment (curve, path, x0, y0, cx, cy, x1, y1).
+int swfr_debug_morph_stroke(const swfr_define_shape *tag, double ratio, double *out, uint64_t cap, uint64_t *n_segs,
+                            uint32_t *n_paths) {
+  if (!tag) return SWFR_ERR_INVALID_ARGUMENT;
+  return guarded(nullptr, [&]() -> int {
+    CompiledDef def;
+    std::string err;
+    int rc = compile_definition(tag, true, def, err);
+    if (rc != SWFR_OK) return rc;
+    std::vector<stroke::LineDev> lines;
+    std::vector<stroke::CmdDev> cmds;
+    morph_lines_to_device(def.morph_lines, lines, cmds);
+    std::vector<SegStatic> segs;
+    double width_state = 1.0;
+    uint32_t path = 0;
+    for (const stroke::LineDev &ln : lines) {
+      const double w = stroke::lerp(ln.w0, ln.w1, ratio);
+      if (w > 0) width_state = w;
+      if (stroke::lerp(ln.color0[3] / 255.0, ln.color1[3] / 255.0, ratio) <= 0) continue;
+      stroke::Sink count{nullptr, 0, 0, path, {1.f, 1.f, 0.f, 0.f}, false, 0.f, 0.f, 0.f, 0.f};
+      stroke::stroke_line(cmds.data() + ln.cmd_first, ln.cmd_count, ratio, width_state, count);
+      const size_t at = segs.size();
+      segs.resize(at + count.n);
+      stroke::Sink sink{segs.data() + at, count.n, 0, path, {1.f, 1.f, 0.f, 0.f}, false, 0.f, 0.f, 0.f, 0.f};
+      stroke::stroke_line(cmds.data() + ln.cmd_first, ln.cmd_count, ratio, width_state, sink);
+      path++;
+    }
+    for (size_t i = 0; i < segs.size() && out && i < cap; i++) {
+      double *o = out + 8 * i;
+      o[0] = segs[i].path_flags >> 31;
+      o[1] = segs[i].path_flags & 0x7fffffffu;
+      for (int k = 0; k < 6; k++) o[2 + k] = segs[i].p[k];
+    }
+    if (n_segs) *n_segs = segs.size();
+    if (n_paths) *n_paths = path;
+    return SWFR_OK;
+  });
 }
 
 static int debug_pass(swfr_renderer *r, uint32_t frame, const Pass **pass, size_t *index) {

@@ -378,3 +378,22 @@ def compile_tag(tag: dict, morph: bool = False):
     if rc != capi.OK:
         raise SwfrError(rc, lib.swfr_status_string(rc).decode())
     return cmds[: nc.value], info[: npth.value], segs[: ns.value]
+
+
+def debug_morph_stroke(tag: dict, ratio: float):
+    """Host run of the device stroker's generator (swfr_debug_morph_stroke) for one DefineMorphShape tag at `ratio`.
+
+    Returns (segments[n, 8] = curve flag, line path index, x0, y0, cx, cy, x1, y1 in twips; number of visible line paths)."""
+    import numpy as _np
+
+    lib = capi.load()
+    cv = convert_define_shape(tag)
+    n, paths = C.c_uint64(), C.c_uint32()
+    rc = lib.swfr_debug_morph_stroke(C.byref(cv.tag), float(ratio), None, 0, C.byref(n), C.byref(paths))
+    if rc != capi.OK:
+        raise SwfrError(rc, lib.swfr_status_string(rc).decode())
+    segs = _np.zeros((max(1, n.value), 8), dtype=_np.float64)
+    rc = lib.swfr_debug_morph_stroke(C.byref(cv.tag), float(ratio), segs.ctypes.data, n.value, C.byref(n), C.byref(paths))
+    if rc != capi.OK:
+        raise SwfrError(rc, lib.swfr_status_string(rc).decode())
+    return segs[: n.value], int(paths.value)

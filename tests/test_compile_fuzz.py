@@ -125,3 +125,56 @@ def test_random_morph_shapes_compile_like_the_oracle(built_library, seed):
         assert len(cmds) == 0
     assert [(int(i[0]), bool(i[1]), bool(i[2])) for i in info] == [
         (len(p["commands"]), "fill" in p, "line" in p) for p in comp["paths"]]
+
+
+def _oracle_morph_stroke_segments(tag, ratio):
+    """The oracle's expansion of a morph shape's visible strokes at `ratio` (oracle/raster.py: add_morph_shape_item +
+    oracle/stroker.py): [(is_curve, line path, x0, y0, cx, cy, x1, y1)]."""
+    from oracle import compile_shape as cs
+    from oracle import raster
+
+    b = raster._Builder({})
+    raster.add_morph_shape_item(b, cs.compile_morph_shape(tag), [1, 1, 0, 0, 0, 0], 0, ratio)
+    if not b.defs or b.defs[-1][4]:  # no visible stroke: nothing, or only the fills' (morph) definition, was added
+        return [], 0
+    first_seg, n_seg, _, n_path, is_morph = b.defs[-1]
+    return [(k, lp) + tuple(s6) for (s6, e6, k, lp) in b.segs[first_seg:first_seg + n_seg]], n_path
+
+
+@pytest.mark.parametrize("ratio", [0.0, 0.25, 0.5, 0.7001953125, 1.0])
+def test_device_stroker_generator_matches_the_oracle_stroker(built_library, ratio):
+    """the streaming generator the GPU runs per morph draw (csrc/stroke_core.h, compiled for the host here
+    through swfr_debug_morph_stroke) yields the oracle stroker's float32 segments bit for bit, in the same order - for
+    the corpus morph shape with a visible lerped stroke and for random morph tags with line styles."""
+    import copy
+
+    import corpus
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200.renderer import debug_morph_stroke
+
+    tags = []
+    base = copy.deepcopy(corpus.load_ast(corpus.MORPH_SAMPLE))
+    for ls in base["shape"]["initial_styles"]["line"]:
+        ls["width"], ls["morph_width"] = 60, 140
+        ls["fill"] = {"type": "solid", "color": dict(zip("rgba", (0, 0, 0, 255))), "morph_color": dict(zip("rgba", (200, 30, 30, 128)))}
+    tags.append(base)
+    seed = int(ratio * 1000) * 100 + 5
+    while len(tags) < 25:
+        t = _random_tag(seed, morph=True)
+        seed += 1
+        if t["shape"]["initial_styles"]["line"]:
+            tags.append(t)
+    checked = 0
+    for tag in tags:
+        try:
+            want, want_paths = _oracle_morph_stroke_segments(tag, ratio)
+        except NotImplementedError:
+            continue
+        got, got_paths = debug_morph_stroke(tag, float(np.float32(ratio)))
+        assert got_paths == want_paths
+        assert len(got) == len(want), (len(got), len(want))
+        if len(want):
+            np.testing.assert_array_equal(got, np.array(want, dtype=np.float64))
+            checked += 1
+    assert checked >= 5
+    del sw

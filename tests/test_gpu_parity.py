@@ -298,3 +298,32 @@ def test_morph_ratio_outside_unit_interval_extrapolates(built_library, ratio_f):
     np.testing.assert_array_equal(r.debug_tile_counts(0), info["tile_counts"])
     r.close()
     assert np.array_equal(out, ref) and out[..., 3].any()
+
+
+def test_device_stroker_outgrown_room_is_laid_out_again(built_library):
+    """the outline of a morph stroke is generated on the device into room reserved at registration; with
+    SWFR_OPT_DEBUG_TINY_ARENA the room is far too small, k_stroke reports it, the host lays the batch out again with
+    exact counts and the render still equals the oracle - also for several draws and frames in one batch."""
+    from swf_renderer_b200 import capi
+
+    tag = _morph_with_visible_strokes(40, 100, (10, 20, 30, 255), (250, 240, 0, 255))
+    w, h, m = corpus.fixture_canvas(tag)
+    sc = corpus.Scene(w, h)
+    idx = sc.add_morph(tag)
+    for f, rt in enumerate([0, 21845, 43690, 65535]):
+        sc.draw_morph(idx, m, rt, frame=f)
+        sc.draw_morph(idx, [0.5, 0.5, 0.0, 0.0, m[4] * 0.5 + 200.0, m[5] * 0.5 + 100.0], 65535 - rt, frame=f)
+    r, stages = corpus.make_product(sc)
+    r.set_option(capi.OPT_FRAMES_PER_PASS, 2)
+    r.set_option(capi.OPT_DEBUG_TINY_ARENA, 1)
+    r.render_batch(stages)
+    assert r.stats()["retries"] >= 1
+    for f in range(4):
+        ref = corpus.render_oracle(sc, frame=f)
+        assert np.array_equal(r.get_image(frame=f, premultiplied=True).data, ref), "frame %d" % f
+    r.set_option(capi.OPT_DEBUG_TINY_ARENA, 0)
+    r.render_batch(stages)  # the estimate was raised: no retry now
+    assert r.stats()["retries"] == 0
+    for f in range(4):
+        assert np.array_equal(r.get_image(frame=f, premultiplied=True).data, corpus.render_oracle(sc, frame=f))
+    r.close()
