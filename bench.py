@@ -101,6 +101,7 @@ def parse():
     ap.add_argument("--config", default="stream", choices=["stream"] + list(EXTRA_CONFIGS),
                     help="workload of the line: stream = BASELINE configs[4] (the headline, with the other configs as extra "
                          "objects under `configs`); gradients1080 / morphsweep / textured4k = BASELINE configs[1] / [2] / [3] alone")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the gradients1080 / morphsweep / textured4k objects")
     ap.add_argument("--uhd-frames", type=int, default=16,
                     help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
     return ap.parse_args()
@@ -643,6 +644,9 @@ def run_ours(a):
         "traffic_source": ncu_src,
         "kernels_sha": kernels_sha(),
         "warp_instructions_per_launch": winst,
+        # the bound the kernel actually runs against: warp instructions issued per second against 148 SMs x 4 schedulers
+        # x one warp instruction per clock at the SM clock sampled during the run (filled in below, with the clocks)
+        "instruction_roofline": None,
         "algorithmic_bytes_per_launch": fine_bytes_per_launch,
         "launch_ms": fine_ms_per_launch,
         "launches_per_step": fine_launches,
@@ -813,7 +817,7 @@ def run_ours(a):
 
     # ---- BASELINE configs[1..3] as extra objects of the line ----
     extra = {}
-    if not a.quick:
+    if not a.quick and not a.no_extra_configs:
         if batch is not None:
             batch.close()
             batch = None
@@ -825,6 +829,12 @@ def run_ours(a):
             except Exception as e:  # an extra object must never cost the headline
                 extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    if rank == 0 and winst and clocks and clocks.get("sm_mhz"):
+        peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+        ach = winst / (fine_ms_per_launch / 1e3)
+        roofline["instruction_roofline"] = {"bound": "issue", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-inst/s",
+                                            "frac": ach / peak_issue, "sm_mhz": clocks["sm_mhz"],
+                                            "note": "k_fine issues on this share of all scheduler cycles; HBM is at `frac` above"}
     if rank == 0:
         line = {
             "metric": METRIC,

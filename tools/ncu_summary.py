@@ -74,7 +74,7 @@ def main():
         })
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     total = sum(k["duration_us"] for k in out) or 1
-    md = ["# ncu --set full, one render pass (16 frames of the 1080p / 10 k shapes stream), " + tag, "",
+    md = ["# ncu --set full, one render pass (32 frames of the 1080p / 10 k shapes stream; k_fine per slice of 16 frames), " + tag, "",
           "Source: `%s` (cold-cache, serialised launches: compare shares, not absolutes).  "
           "lanes = average active threads per warp instruction; stalls = warps stalled per issue slot." % os.path.basename(rep), "",
           "| kernel | us | share | DRAM rd MB | DRAM wr MB | DRAM GB/s | issue % | occupancy % | regs | Minst | lanes | top stalls |",
@@ -90,13 +90,25 @@ def main():
     if os.path.exists(launches):
         shutil.copy(launches, os.path.join(ROOT, "profiles", tag + "_launches.csv"))
     fine = [k for k in out if k["kernel"].startswith("k_fine")]
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ("kernels.cu", "kernels.h"):
+        with open(os.path.join(ROOT, "swf_renderer_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
     summary = {
         "source": os.path.basename(rep),
         "tag": tag,
-        "workload": "bench.py --frames 16 --frames-per-pass 16 (one pass = one launch of every kernel)",
+        # bench.py quotes the k_fine figures only when its own kernel sources hash to this value
+        "kernels_sha": h.hexdigest()[:16],
+        "workload": "bench.py --frames 32 (one pass of the default size = one launch of every kernel, k_fine once per slice of 16 frames)",
         "k_fine_dram_bytes_per_launch": (fine[0]["dram_read_bytes"] + fine[0]["dram_write_bytes"]) if fine else None,
+        "k_fine_warp_instructions_per_launch": fine[0]["warp_instructions"] if fine else None,
+        "k_fine_issue_active_pct": fine[0]["issue_active_pct"] if fine else None,
+        "k_fine_lanes_per_instruction": fine[0]["lanes_per_instruction"] if fine else None,
         "k_fine_duration_us_under_ncu": fine[0]["duration_us"] if fine else None,
-        "kernels": out,
+        "kernels": [{k: v for k, v in kk.items() if k in ("kernel", "duration_us", "warp_instructions", "issue_active_pct",
+                                                            "lanes_per_instruction", "dram_read_bytes", "dram_write_bytes")} for kk in out],
     }
     with open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
