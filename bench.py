@@ -101,6 +101,8 @@ def parse():
     ap.add_argument("--config", default="stream", choices=["stream"] + list(EXTRA_CONFIGS),
                     help="workload of the line: stream = BASELINE configs[4] (the headline, with the other configs as extra "
                          "objects under `configs`); gradients1080 / morphsweep / textured4k = BASELINE configs[1] / [2] / [3] alone")
+    ap.add_argument("--stroke-fraction", type=float, default=0.0,
+                    help="fraction of the stream's shapes that carry a 2 px stroke (SURVEY 8d config 5, 'separate variant': 0.25)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the gradients1080 / morphsweep / textured4k objects")
     ap.add_argument("--uhd-frames", type=int, default=16,
                     help="frames of the secondary 3840x2160 measurement (same generator, radii x2); 0 = skip")
@@ -109,8 +111,9 @@ def parse():
 
 def workload_config(a, n_gpus):
     return {
-        "workload": "synthetic stream, %d random SWF shapes/frame at %dx%d (SURVEY 8d config 5, BASELINE configs[4])"
-        % (a.shapes, a.width, a.height),
+        "workload": "synthetic stream, %d random SWF shapes/frame at %dx%d (SURVEY 8d config 5, BASELINE configs[4])%s"
+        % (a.shapes, a.width, a.height,
+           ", %.0f %% of the shapes with a 2 px stroke" % (100 * a.stroke_fraction) if getattr(a, "stroke_fraction", 0) else ""),
         "frames_per_step_per_gpu": a.frames,
         "shapes_per_frame": a.shapes,
         "resolution": [a.width, a.height],
@@ -179,7 +182,7 @@ def _oracle_scene(frame_index, a):
     from oracle import compile_shape as cs
     from oracle import raster
 
-    fr = synth.SynthFrame(frame_index, a.shapes, a.width, a.height)
+    fr = synth.SynthFrame(frame_index, a.shapes, a.width, a.height, stroke_fraction=getattr(a, "stroke_fraction", 0.0))
     b = raster._Builder({i: t for i, t in enumerate(synth.textures())})
     for i in range(fr.n):
         b.add_item(raster.add_shape_def(b, cs.compile_shape(fr.ast(i))), fr.matrix(i))
@@ -471,6 +474,60 @@ def run_extra_config(name, a, local, stream, rank, world, barrier, max_over_rank
     return out
 
 
+def run_stroked_variant(a, local, stream, rank, world, barrier, max_over_ranks, with_cpu, n_frames=16, fraction=0.25):
+    """SURVEY 8d config 5, 'separate variant': the same stream with a 2 px stroke on a quarter of the shapes (butt caps,
+    miter joins: outlines made at registration, composited with the per-sub-scanline coverage routine).  16 frames,
+    stages resident; frame 0 is checked against the oracle at N = 1."""
+    import torch
+
+    import synth
+    import swf_renderer_b200 as sw
+    from swf_renderer_b200 import capi
+    from swf_renderer_b200.renderer import stage_array_from_numpy, stages_from_prims
+
+    r = sw.HeadlessRenderer(a.width, a.height, device=local, cuda_stream=stream.cuda_stream)
+    r.set_option(capi.OPT_RETAIN_COMPILED, 0)
+    for i, t in enumerate(synth.textures()):
+        r.register_bitmap(i, t)
+    prims = []
+    for f in range(n_frames):
+        fr = synth.SynthFrame(rank * n_frames + f, a.shapes, a.width, a.height, stroke_fraction=fraction)
+        prims.append(stage_array_from_numpy(fr.register(r), fr.matrices()))
+    batch = r.create_batch(stages_from_prims(prims))
+    for _ in range(3):
+        batch.render()
+    r.sync()
+    barrier()
+    steps = 60
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        batch.render()
+    e1.record(stream)
+    r.sync()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    st = r.stats()
+    frame0 = r.get_image(frame=0, premultiplied=True).data.copy()
+    batch.close()
+    r.close()
+    out = {"workload": "the synthetic stream with a 2 px stroke on %.0f %% of the shapes (SURVEY 8d config 5, separate variant)" % (100 * fraction),
+           "resolution": [a.width, a.height], "frames_per_step_per_gpu": n_frames, "shapes_per_frame": a.shapes, "steps": steps,
+           "ms_per_step": ms, "value": world * n_frames * a.width * a.height / (ms / 1e3) / 1e6, "unit": UNIT,
+           "shapes_per_s": world * n_frames * a.shapes / (ms / 1e3),
+           "per_step": {k: st[k] for k in ("n_primitives", "n_path_instances", "n_segments", "n_edges", "n_records", "fine_slots")}}
+    if with_cpu:
+        import argparse as _ap
+
+        _, sc = _oracle_scene(0, _ap.Namespace(shapes=a.shapes, width=a.width, height=a.height, stroke_fraction=fraction))
+        from oracle import raster
+
+        want = raster.render_scene(sc)
+        d = int((frame0 != want).any(axis=2).sum())
+        out["parity"] = {"frame": 0, "equal": d == 0, "px_diff": d, "against": "oracle/raster.c, premultiplied RGBA8, bit-exact"}
+    return out
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -547,7 +604,7 @@ def run_ours(a):
         r.register_bitmap(i, t)
     prim_arrays = []
     for f in range(a.frames):
-        fr = synth.SynthFrame(rank * a.frames + f, a.shapes, a.width, a.height)
+        fr = synth.SynthFrame(rank * a.frames + f, a.shapes, a.width, a.height, stroke_fraction=a.stroke_fraction)
         ids = fr.register(r)
         prim_arrays.append(stage_array_from_numpy(ids, fr.matrices()))
     stage_arr, keep = stages_from_prims(prim_arrays)
@@ -828,6 +885,11 @@ def run_ours(a):
                 extra[name] = run_extra_config(name, a, local, stream, rank, world, barrier, max_over_ranks, with_cpu)
             except Exception as e:  # an extra object must never cost the headline
                 extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if a.stroke_fraction == 0.0:
+            try:
+                extra["stream_stroked25"] = run_stroked_variant(a, local, stream, rank, world, barrier, max_over_ranks, with_cpu)
+            except Exception as e:
+                extra["stream_stroked25"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0 and winst and clocks and clocks.get("sm_mhz"):
         peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6

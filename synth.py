@@ -59,7 +59,7 @@ def textures(seed: int = 0x7E87) -> list:
 
 class SynthFrame:
     def __init__(self, frame_index: int, n_shapes: int, width: int, height: int, radius_scale: float = 1.0,
-                 solid_only: bool = False):
+                 solid_only: bool = False, stroke_fraction: float = 0.0):
         self.seed = 0x5EED0000 + frame_index
         self.n, self.width, self.height = n_shapes, width, height
         s = np.arange(n_shapes)
@@ -89,6 +89,8 @@ class SynthFrame:
         self.rotated = u(24) < 0.2
         self.rot = u(25) * 2 * math.pi
         self.scale = 0.5 + 1.5 * u(26)
+        # SURVEY 8d config 5, "separate variant": 2 px strokes (opaque, the second colour) on this fraction of the shapes
+        self.stroked = u(27) < stroke_fraction
         self.stop_colors = np.stack(
             [np.stack([np.floor(u(32 + 4 * k + c) * 256) for c in range(4)], axis=1) for k in range(4)], axis=1
         ).astype(np.int64)  # (n, 4 stops, rgba)
@@ -182,11 +184,19 @@ class SynthFrame:
             out["focal_point"] = int(self.focal[i])
         return out
 
+    def _line_ast(self, i: int):
+        c = self.color2[i]
+        return {"width": 40, "fill": {"type": "solid", "color": {"r": int(c[0]), "g": int(c[1]), "b": int(c[2]), "a": 255}}}
+
     def ast(self, i: int) -> dict:
         """swf-tree JSON form of shape i (define-shape)."""
         n = int(self.nv[i])
         fills = [self._fill_ast(i, False)]
         recs = [{"type": "style-change", "move_to": {"x": int(self.vx[i, 0]), "y": int(self.vy[i, 0])}, "left_fill": 1}]
+        lines = []
+        if self.stroked[i]:
+            lines.append(self._line_ast(i))
+            recs[0]["line_style"] = 1
         for k in range(n):
             e = {"type": "edge", "delta": {"x": int(self.dx[i, k]), "y": int(self.dy[i, k])}}
             if self.curved[i, k]:
@@ -206,7 +216,7 @@ class SynthFrame:
             "type": "define-shape",
             "id": i & 0xFFFF,
             "bounds": {"x_min": -r, "x_max": r, "y_min": -r, "y_max": r},
-            "shape": {"initial_styles": {"fill": fills, "line": []}, "records": recs},
+            "shape": {"initial_styles": {"fill": fills, "line": lines}, "records": recs},
         }
 
     # ---- fast path into the C ABI -----------------------------------------------------------------------
@@ -222,7 +232,8 @@ class SynthFrame:
         recs = (capi.ShapeRecord * total)()
         R = capi.ShapeRecord
         fields = ["type", "delta_x", "delta_y", "control_delta_x", "control_delta_y", "has_control_delta", "has_move_to",
-                  "has_left_fill", "has_right_fill", "move_to_x", "move_to_y", "left_fill", "right_fill"]
+                  "has_left_fill", "has_right_fill", "has_line_style", "move_to_x", "move_to_y", "left_fill", "right_fill",
+                  "line_style"]
         np_t = {1: np.uint8, 4: np.int32}
         dt = np.dtype({
             "names": fields,
@@ -239,6 +250,8 @@ class SynthFrame:
         v["move_to_y"][b0] = self.vy[:, 0]
         v["has_left_fill"][b0] = 1
         v["left_fill"][b0] = 1
+        v["has_line_style"][b0] = self.stroked
+        v["line_style"][b0] = self.stroked.astype(np.int32)
         k = np.arange(MAXV)[None, :]
         dest = (b0[:, None] + 1 + k)[self.mask]
         v["type"][dest] = capi.RECORD_EDGE
@@ -283,6 +296,15 @@ class SynthFrame:
             tag.initial_styles.n_fill = nf
             tag.initial_styles.fill = C.cast(fills, C.POINTER(capi.FillStyle))
             tag.initial_styles.n_line = 0
+            if self.stroked[i]:
+                line = (capi.LineStyle * 1)()
+                la = self._line_ast(i)
+                line[0].width = la["width"]
+                line[0].morph_width = la["width"]
+                line[0].fill = _fill(la["fill"], keep)
+                keep.append(line)
+                tag.initial_styles.n_line = 1
+                tag.initial_styles.line = C.cast(line, C.POINTER(capi.LineStyle))
             tag.n_records = int(per[i])
             tag.records = C.cast(C.addressof(rec_ptr.contents) + int(base[i]) * C.sizeof(R), C.POINTER(capi.ShapeRecord))
             rc = lib.swfr_register_shape(renderer._h, C.byref(tag), C.byref(out))

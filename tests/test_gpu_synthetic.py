@@ -489,3 +489,36 @@ def test_slot_memory_scales_with_area_times_count(built_library):
     r.render(st)  # working memory is large enough now
     assert r.stats()["retries"] == 0
     r.close()
+
+
+@pytest.mark.parametrize("n_shapes,w,h,rs", [(300, 640, 360, 0.5), (1500, 1920, 1080, 1.0)])
+def test_stroked_stream_variant_bit_exact(built_library, n_shapes, w, h, rs):
+    """SURVEY 8d config 5, separate variant: a 2 px stroke on a quarter of the shapes.  Static strokes become outlines
+    at registration (butt caps, miter joins) and are composited with the non-zero rule per sub-scanline (stroke outlines
+    overlap themselves); frames of 1024 or more items also go through occlusion culling."""
+    fr = synth.SynthFrame(50 + n_shapes, n_shapes, w, h, rs, stroke_fraction=0.25)
+    sc = corpus.Scene(w, h)
+    for i, t in enumerate(synth.textures()):
+        sc.bitmaps[i] = t
+    for i in range(fr.n):
+        sc.draw_shape(sc.add_shape(fr.ast(i)), fr.matrix(i))
+    assert fr.stroked.sum() > n_shapes // 8
+    ref = corpus.render_oracle(sc)
+    r, stages = corpus.make_product(sc)
+    r.render(stages[0])
+    out = r.get_image(premultiplied=True).data
+    st = r.stats()
+    assert st["n_path_instances"] > n_shapes  # the strokes are paths of their own
+    bad = (out != ref).any(axis=2)
+    assert not bad.any(), "%d px differ, first %s" % (bad.sum(), np.argwhere(bad)[:5].tolist())
+    # the fast registration path of the benchmark builds the same definitions
+    r2 = type(r)(w, h)
+    for j, t in enumerate(synth.textures()):
+        r2.register_bitmap(j, t)
+    from swf_renderer_b200.renderer import stage_array_from_numpy, stages_from_prims
+
+    arr, keep = stages_from_prims([stage_array_from_numpy(fr.register(r2), fr.matrices())])
+    r2.render_stage_array(arr, 1)
+    assert np.array_equal(r2.get_image(premultiplied=True).data, ref)
+    r.close()
+    r2.close()
