@@ -597,7 +597,10 @@ def run_ours(a):
     # stage-flattening threads: the box's cores are shared by the ranks of the node
     cores = max(1, len(os.sched_getaffinity(0)))
     ranks_sharing = max(world, 1) if numa is None else max(1, (world + 1) // 2)  # ranks on this rank's cores
-    r.set_option(capi.OPT_HOST_THREADS, max(1, min(8, cores // ranks_sharing)))
+    host_threads = max(1, min(8, cores // ranks_sharing))
+    if os.environ.get("SWFR_BENCH_HOST_THREADS"):
+        host_threads = int(os.environ["SWFR_BENCH_HOST_THREADS"])
+    r.set_option(capi.OPT_HOST_THREADS, host_threads)
 
     # ---- inputs: textures, definitions, stages (host arrays) ----
     for i, t in enumerate(synth.textures()):
@@ -733,8 +736,11 @@ def run_ours(a):
     r.sync()
     barrier()
     t0 = time.perf_counter()
-    for i in range(a.steps):
+    host_call_s = 0.0  # time the caller spends inside swfr_render_batch (stage flattening, upload and enqueue; it also
+    for i in range(a.steps):  # waits there for the render before the previous one, which is long done)
+        c0 = time.perf_counter()
         r.render_stage_array(stage_arr, a.frames)
+        host_call_s += time.perf_counter() - c0
         r.read_frames_async(0, a.frames, host_out[i & 1].data_ptr())
     r.sync()
     torch.cuda.synchronize()
@@ -923,6 +929,8 @@ def run_ours(a):
                 "ms_per_step": e2e_s / a.steps * 1e3,
                 "mode": "streaming: render_batch(host stages) + read_frames_async(pinned) per step, 2 output buffers, "
                         "sync at the end",
+                "host_ms_per_step_in_render_call": host_call_s / a.steps * 1e3,
+                "host_threads": host_threads,
                 "ms_per_step_sync_every_step": e2e_serial_ms,
                 "d2h_ceiling": d2h_ceiling,
                 "numa": numa,

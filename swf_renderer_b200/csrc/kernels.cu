@@ -1543,13 +1543,10 @@ __device__ __forceinline__ uint32_t mul_un8x4(uint32_t p, uint32_t m) {
   return rb | ag;
 }
 
-__device__ __forceinline__ uint32_t over_masked(uint32_t dst, uint32_t src, uint32_t m) {
-  uint32_t s = (m == 255u) ? src : mul_un8x4(src, m);
-  uint32_t sa = s >> 24;
-  if (sa == 255u) return s;
-  if (s == 0u) return dst;
-  return s + mul_un8x4(dst, 255u - sa);
-}
+// over_masked(dst, src, m) of the oracle - s = (m == 255) ? src : MUL_UN8x4(src, m); s.a == 255 -> s; s == 0 -> dst;
+// else s + MUL_UN8x4(dst, 255 - s.a) - is computed in k_fine without the case analysis: the shortcuts are identities of
+// the general form (MUL_UN8(x, 255) = x, MUL_UN8(x, 0) = 0), so s + MUL_UN8x4(dst, 255 - s.a) with s = MUL_UN8x4(src, m)
+// is the same value in every case.
 
 // Adds one record's signed-area contribution for pixel row `r` into acc_row[0..15] as prefix differences.
 __device__ __forceinline__ void accumulate_row(int xa, int ya, int xb, int yb, int r, int *acc_row) {
@@ -2069,9 +2066,15 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
             for (int i = 0; i < 8; i++) px[i] = color + mul_un8x4(px[i], 255u - ca);
           }
         } else if (type == PAINT_SOLID) {
+          // partly covered tile of a solid path: over_masked without its case analysis.  The three shortcuts of
+          // over_masked are identities of the general form (MUL_UN8(x, 255) = x, MUL_UN8(x, 0) = 0), and in an edge tile
+          // some lane takes the general form at nearly every pixel anyway, so the branch-free form issues fewer
+          // instructions than the divergent one (18 of 32 lanes were active in the blend arithmetic).
 #pragma unroll
-          for (int i = 0; i < 8; i++)
-            if (m[i]) px[i] = over_masked(px[i], color, m[i]);
+          for (int i = 0; i < 8; i++) {
+            const uint32_t sm = mul_un8x4(color, m[i]);
+            px[i] = sm + mul_un8x4(px[i], 255u - (sm >> 24));
+          }
         } else {
           // One copy of the paint code, eight trips.  px[] and the masks are only ever indexed statically (the pixels
           // rotate through px[0], the masks are packed into two words), so both stay in registers: a dynamic index
@@ -2083,11 +2086,23 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
           const PaintInst &pi = *reinterpret_cast<const PaintInst *>(paint_sh[warp]);
           uint32_t mlo = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
           uint32_t mhi = m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
+          // warp-uniform cases of the blend (the general form below is exact for all of them, see the solid paint):
+          // every pixel of the tile fully covered, and an opaque paint on top of that
+          // (kept in the spare bits of the paint type: bit 8 = fully covered, bit 9 = and opaque -> the source replaces)
+          const uint32_t tf = type | (o1 == o0 ? (0x100u | ((info & 0x100u) << 1)) : 0u);
 #pragma unroll 1
           for (int i = 0; i < 8; i++) {
             const uint32_t mm = mlo & 255u;
             uint32_t v = px[0];
-            if (mm) v = over_masked(v, eval_paint(type, pi, X0 + i, Y), mm);
+            if (mm) {
+              const uint32_t src = eval_paint(tf & 0xffu, pi, X0 + i, Y);
+              if (tf & 0x200u) {
+                v = src;
+              } else {
+                const uint32_t sm = (tf & 0x100u) ? src : mul_un8x4(src, mm);
+                v = sm + mul_un8x4(v, 255u - (sm >> 24));
+              }
+            }
 #pragma unroll
             for (int k = 0; k < 7; k++) px[k] = px[k + 1];
             px[7] = v;

@@ -41,10 +41,11 @@ def test_library_holds_sm_100a_code_only(built_library):
 
 def test_k_fine_fits_four_blocks_per_sm_without_spills(built_library):
     res = _usage()
-    # k_fine<false>: passes without stroke outlines (the benchmarked stream): 64 registers, no stack at all
+    # k_fine<false>: passes without stroke outlines (the benchmarked stream): 64 registers; the only stack is the pair of
+    # per-warp statistics counters (swfr_stats.fine_*), touched once per composited slot - no pixel or mask ever spills
     for name, (reg, stack, shared, local) in _one(res, "6k_fineILb0").items():
         assert reg <= 64, (name, reg)
-        assert stack == 0 and local == 0, (name, stack, local)
+        assert stack <= 8 and local == 0, (name, stack, local)
         assert shared <= 227 * 1024 // 4
     # k_fine<true>: the only stack is the frame of the call to the out-of-line coverage routine of stroke outlines
     # (slot_coverage_sampled): registers saved around it, on that path only
