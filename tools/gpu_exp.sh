@@ -50,6 +50,8 @@ if [ "$NCU" = "fine" ]; then
     -o gpurun_out/prof_${TAG}_fine -f $PCMD > gpurun_out/ncu_fine_$TAG.log 2>&1
   echo "ncu fine rc=$?"
 elif [ "$NCU" = "full" ]; then
+  # the hash of the kernel sources this capture is taken on (bench.py quotes the figures only for matching sources)
+  python -c "import bench; print(bench.kernels_sha())" > gpurun_out/prof_$TAG.sha
   timeout 1200 ncu --set full --clock-control none --import-source on -s $((3 * L)) -c $L \
     -o gpurun_out/prof_$TAG -f $PCMD > gpurun_out/ncu_full_$TAG.log 2>&1
   echo "ncu full rc=$?"

@@ -96,11 +96,16 @@ def main():
     for name in ("kernels.cu", "kernels.h"):
         with open(os.path.join(ROOT, "swf_renderer_b200", "csrc", name), "rb") as f:
             h.update(f.read())
+    sha = h.hexdigest()[:16]
+    sha_file = os.path.splitext(rep)[0] + ".sha"  # written on the GPU box next to the capture (tools/gpu_exp.sh)
+    if os.path.exists(sha_file):
+        with open(sha_file) as f:
+            sha = f.read().strip()
     summary = {
         "source": os.path.basename(rep),
         "tag": tag,
         # bench.py quotes the k_fine figures only when its own kernel sources hash to this value
-        "kernels_sha": h.hexdigest()[:16],
+        "kernels_sha": sha,
         "workload": "bench.py --frames 32 (one pass of the default size = one launch of every kernel, k_fine once per slice of 16 frames)",
         "k_fine_dram_bytes_per_launch": (fine[0]["dram_read_bytes"] + fine[0]["dram_write_bytes"]) if fine else None,
         "k_fine_warp_instructions_per_launch": fine[0]["warp_instructions"] if fine else None,
