@@ -211,7 +211,10 @@ int swfr_flatten_display_stage(const swfr_display_stage *stage, swfr_display_pri
 
 /* Creates a renderer with a width x height RGBA8 viewport on CUDA device `device`, with its own stream. */
 int swfr_create(int device, uint32_t width, uint32_t height, swfr_renderer **out);
-/* Same, but all work is enqueued on an existing CUDA stream (a cudaStream_t passed as void*). */
+/* Same, with an existing CUDA stream (a cudaStream_t passed as void*) as the renderer's stream: every render is
+ * ordered INTO it - the stream waits for the render's last kernel, so work the caller enqueues on it after swfr_render
+ * sees finished frames, and events recorded on it time the renders.  The kernels themselves run on the renderer's own
+ * pass streams (two passes of a batch overlap, and a render starts while the tail of its predecessor still runs). */
 int swfr_create_on_stream(int device, uint32_t width, uint32_t height, void *cuda_stream, swfr_renderer **out);
 void swfr_destroy(swfr_renderer *r);
 const char *swfr_last_error(const swfr_renderer *r);
@@ -259,9 +262,11 @@ int swfr_decode_xswfbmp(const uint8_t *data, size_t len, uint8_t *rgba, uint64_t
 /* Renders one stage into frame 0.  Asynchronous on the renderer's stream. */
 int swfr_render(swfr_renderer *r, const swfr_stage *stage);
 /* Renders n stages into frames 0..n-1 with one set of launches per SWFR_OPT_FRAMES_PER_PASS frames.  Asynchronous:
- * the call flattens the stages on the host and uploads them while the PREVIOUS render (if still in flight) runs,
- * then waits for that render and enqueues this one - so a caller that streams batches (render k, read k async,
- * render k+1, ...) keeps the host flattening, both PCIe directions and the GPU busy at the same time. */
+ * the call flattens the stages on the host and uploads them while up to two earlier renders are still in flight,
+ * waits for all but the newest of those and enqueues this one behind it - so a caller that streams batches (render k,
+ * read k async, render k+1, ...) keeps the host flattening, both PCIe directions and the GPU busy at the same time.
+ * A render is settled lazily (device counters: working memory that overflowed -> grown and the render re-run,
+ * BitmapNotFound, statistics): such results surface at the next swfr_sync / swfr_read_image / swfr_get_stats. */
 int swfr_render_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n);
 
 /* Stages kept resident in HBM, for repeated rendering without host traffic. */
