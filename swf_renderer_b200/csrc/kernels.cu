@@ -349,28 +349,37 @@ __global__ void __launch_bounds__(256) k_path_alive(RenderArgs a, uint32_t c) {
       // without culling (one chunk) every path is emitted, also those outside the viewport: the edge tap lists them all
       alive = bw > 0 || a.n_chunks == 1;
       if (alive && !top) {
-        scan_small = bh <= 8 && (bx0 >> 5) == ((bx0 + bw - 1) >> 5);  // up to eight rows inside one 32-tile word
+        scan_small = bh <= 32 && ((bx0 + bw - 1) >> 5) - (bx0 >> 5) <= 1;  // up to 32 rows inside two 32-tile words
         scan_big = !scan_small;
       }
     }
-    if (scan_small) {  // the usual case: all eight loads in flight at once
+    // The usual case, one thread per path: its rows one after the other, the two words of a row in flight together.  All
+    // lanes run the trip count of the tallest grid of the warp (a grid of more than 32 rows, or wider than two words,
+    // would keep the others waiting: those go to the warp-cooperative scan below).
+    {
+      const int hmax = __reduce_max_sync(0xffffffffu, scan_small ? bh : 0);
       const int w0 = bx0 >> 5;
-      const uint32_t in = (0xffffffffu << (bx0 & 31)) & (0xffffffffu >> (31 - ((bx0 + bw - 1) & 31)));
-      uint32_t open[8];
-#pragma unroll
-      for (int y = 0; y < 8; y++) open[y] = y < bh ? (~__ldg(bits + (size_t)(by0 + y) * a.cover_words + w0) & in) : 0u;
-      uint32_t all = 0;
-#pragma unroll
-      for (int y = 0; y < 8; y++) {
-        all |= open[y];
-        if (open[y]) {
-          rmin = min(rmin, by0 + y);
-          rmax = by0 + y;
+      const bool two = ((bx0 + bw - 1) >> 5) != w0;
+      const uint32_t in0 = scan_small ? ((0xffffffffu << (bx0 & 31)) & (two ? 0xffffffffu : (0xffffffffu >> (31 - ((bx0 + bw - 1) & 31))))) : 0u;
+      const uint32_t in1 = (scan_small && two) ? (0xffffffffu >> (31 - ((bx0 + bw - 1) & 31))) : 0u;
+      const uint32_t *row = bits + (size_t)by0 * a.cover_words + w0;
+      uint32_t all0 = 0, all1 = 0;
+      for (int y = 0; y < hmax; y++) {
+        if (scan_small && y < bh) {
+          const uint32_t o0 = ~__ldg(row) & in0;
+          const uint32_t o1 = two ? (~__ldg(row + 1) & in1) : 0u;
+          if (o0 | o1) {
+            rmin = min(rmin, by0 + y);
+            rmax = by0 + y;
+          }
+          all0 |= o0;
+          all1 |= o1;
+          row += a.cover_words;
         }
       }
-      if (all) {
-        cmin = w0 * 32 + __ffs(all) - 1;
-        cmax = w0 * 32 + 31 - __clz(all);
+      if (all0 | all1) {
+        cmin = all0 ? w0 * 32 + __ffs(all0) - 1 : (w0 + 1) * 32 + __ffs(all1) - 1;
+        cmax = all1 ? (w0 + 1) * 32 + 31 - __clz(all1) : w0 * 32 + 31 - __clz(all0);
       }
     }
     // large grids, one at a time with the whole warp: lanes over the rows (a 68-row grid scanned by its own thread
@@ -1610,7 +1619,8 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
   const float gy = fmaf(p.inv[1], xc, fmaf(p.inv[3], yc, p.inv[5]));
   if (type == PAINT_BITMAP) {
     // box(rx) x box(ry) footprint around the sample point, texel by texel, rows outer / columns inner (the oracle's
-    // summation order).  Wrapped texel indices are carried along instead of taking a modulo per tap; 1 / rx and
+    // summation order).  The texture holds the premultiplied 8-bit texels as four floats (0..255, exact): a fetch
+    // returns the operands of the FMAs directly instead of four bytes to convert per tap.  Wrapped texel indices are carried along instead of taking a modulo per tap; 1 / rx and
     // 1 / ry come from path setup (p.focal / p.omf are reused for them: same IEEE division, done once per path).
     cudaTextureObject_t tex = (cudaTextureObject_t)p.ptr;
     const float hrx = p.rx * 0.5f, hry = p.ry * 0.5f;
@@ -1648,12 +1658,12 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           if (!(vy[rr] && vx[c])) continue;
-          const uchar4 t = tex2D<uchar4>(tex, xs[c], ys[rr]);
+          const float4 t = tex2D<float4>(tex, xs[c], ys[rr]);
           const float wgt = wx[c] * wy[rr];
-          acc0 = fmaf(wgt, (float)t.x, acc0);
-          acc1 = fmaf(wgt, (float)t.y, acc1);
-          acc2 = fmaf(wgt, (float)t.z, acc2);
-          acc3 = fmaf(wgt, (float)t.w, acc3);
+          acc0 = fmaf(wgt, t.x, acc0);
+          acc1 = fmaf(wgt, t.y, acc1);
+          acc2 = fmaf(wgt, t.z, acc2);
+          acc3 = fmaf(wgt, t.w, acc3);
         }
       }
     } else if (ncol <= 3) {
@@ -1685,12 +1695,12 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           if (!vc[c]) continue;
-          const uchar4 t = tex2D<uchar4>(tex, xcs[c], ycs);
+          const float4 t = tex2D<float4>(tex, xcs[c], ycs);
           const float wgt = wxc[c] * wy;
-          acc0 = fmaf(wgt, (float)t.x, acc0);
-          acc1 = fmaf(wgt, (float)t.y, acc1);
-          acc2 = fmaf(wgt, (float)t.z, acc2);
-          acc3 = fmaf(wgt, (float)t.w, acc3);
+          acc0 = fmaf(wgt, t.x, acc0);
+          acc1 = fmaf(wgt, t.y, acc1);
+          acc2 = fmaf(wgt, t.z, acc2);
+          acc3 = fmaf(wgt, t.w, acc3);
         }
       }
     } else {
@@ -1709,12 +1719,12 @@ __device__ uint32_t eval_paint(uint32_t type, const PaintInst &p, int X, int Y) 
           if (!rep && (i < 0 || i >= p.bw)) continue;
           const float vl = fmaxf(lox, (float)i), vh = fminf(hix, (float)(i + 1));
           const float wx = fmaxf(vh - vl, 0.0f) * irx;
-          const uchar4 t = tex2D<uchar4>(tex, (float)icur + 0.5f, (float)jcur + 0.5f);
+          const float4 t = tex2D<float4>(tex, (float)icur + 0.5f, (float)jcur + 0.5f);
           const float wgt = wx * wy;
-          acc0 = fmaf(wgt, (float)t.x, acc0);
-          acc1 = fmaf(wgt, (float)t.y, acc1);
-          acc2 = fmaf(wgt, (float)t.z, acc2);
-          acc3 = fmaf(wgt, (float)t.w, acc3);
+          acc0 = fmaf(wgt, t.x, acc0);
+          acc1 = fmaf(wgt, t.y, acc1);
+          acc2 = fmaf(wgt, t.z, acc2);
+          acc3 = fmaf(wgt, t.w, acc3);
         }
       }
     }
@@ -2167,6 +2177,15 @@ __global__ void k_premultiply(const uint8_t *__restrict__ src, size_t stride, ui
   if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(translucent, 1u);
 }
 
+// Tight premultiplied RGBA8 -> one float4 per texel holding the four 8-bit values (what the bitmap textures store).
+__global__ void k_texels_to_float(const uint32_t *__restrict__ src, float4 *__restrict__ dst, uint64_t n) {
+  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const uint32_t p = src[i];
+    dst[i] = make_float4((float)(p & 255u), (float)((p >> 8) & 255u), (float)((p >> 16) & 255u), (float)(p >> 24));
+  }
+}
+
 // image/x-swf-bmp format 3 after inflate (decode-x-swf-bmp.ts:17-39): `colors` RGB triplets, then rows of 8-bit
 // colour indices padded to a multiple of 4 bytes -> tight opaque RGBA8 (premultiplied == straight at alpha 255); an
 // index past the table is opaque black (decode-x-swf-bmp.ts:35-36).
@@ -2343,6 +2362,9 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
 
 void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t st) {
   k_unpremultiply<<<kNumSM * 8, 256, 0, st>>>(src, dst, n_px);
+}
+void launch_texels_to_float(const uint32_t *src, void *dst, uint64_t n_px, cudaStream_t st) {
+  k_texels_to_float<<<kNumSM * 8, 256, 0, st>>>(src, reinterpret_cast<float4 *>(dst), n_px);
 }
 void launch_premultiply(const uint8_t *src, size_t stride, uint32_t w, uint32_t h, uint32_t *dst, uint32_t *translucent,
                         cudaStream_t st) {
