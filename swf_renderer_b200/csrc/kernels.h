@@ -194,7 +194,6 @@ inline uint32_t fine_slices(uint32_t n_frames) {
 }
 
 void launch_unpremultiply(const uint32_t *src, uint32_t *dst, uint64_t n_px, cudaStream_t stream);
-void launch_texels_to_float(const uint32_t *src, void *dst_float4, uint64_t n_px, cudaStream_t stream);
 void launch_premultiply(const uint8_t *src, size_t stride, uint32_t w, uint32_t h, uint32_t *dst, uint32_t *translucent,
                         cudaStream_t stream);
 void launch_xswfbmp_expand(const uint8_t *inflated, uint32_t colors, uint32_t w, uint32_t h, uint32_t padded, uint32_t *dst,

@@ -1359,13 +1359,9 @@ int install_bitmap(swfr_renderer *r, uint16_t id, uint32_t w, uint32_t h, bool o
   if (res.tex) cudaDestroyTextureObject(res.tex);
   if (res.arr) cudaFreeArray(res.arr);
   res = BitmapRes{};
-  // the texture stores every texel as four floats holding its premultiplied 8-bit values: the sampler's FMAs take them
-  // as they come (no byte -> float conversion per tap)
-  cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
+  cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
   CK(cudaMallocArray(&res.arr, &cd, w, h));
-  CK(r->scratch2.reserve((size_t)w * h * 16));
-  launch_texels_to_float(r->scratch.as<uint32_t>(), r->scratch2.p, (uint64_t)w * h, r->stream);
-  CK(cudaMemcpy2DToArrayAsync(res.arr, 0, 0, r->scratch2.p, (size_t)w * 16, (size_t)w * 16, h, cudaMemcpyDeviceToDevice, r->stream));
+  CK(cudaMemcpy2DToArrayAsync(res.arr, 0, 0, r->scratch.p, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, r->stream));
   cudaResourceDesc rd{};
   rd.resType = cudaResourceTypeArray;
   rd.res.array.array = res.arr;
