@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SWFR_ABI_VERSION 2
+#define SWFR_ABI_VERSION 3
 
 typedef enum swfr_status {
   SWFR_OK = 0,
@@ -152,6 +152,18 @@ typedef struct swfr_define_shape {
 
 typedef enum swfr_primitive_kind { SWFR_PRIM_SHAPE = 0, SWFR_PRIM_MORPH_SHAPE = 1 } swfr_primitive_kind;
 
+/* swf_tree::ColorTransformWithAlpha: per channel c' = clamp(((c * mult) >> 8) + add, 0, 255) on the straight (not
+ * premultiplied) 8-bit colour; mult is Sfixed8P8 (epsilons: 256 = 1.0), add is a signed 16-bit integer.  The reference
+ * renderer has no colour-transform input at all (its display list carries a matrix and a ratio); this is the SWF
+ * semantics, defined here by the oracle ("parity unpinned"):
+ *   solid fills      the fill colour is transformed before it is premultiplied;
+ *   gradients, bitmaps   the evaluated premultiplied pixel is un-premultiplied ((c * 255 + a / 2) / a), transformed and
+ *                    premultiplied again ((c' * a' + 127) / 255) - integer arithmetic throughout. */
+typedef struct swfr_color_transform {
+  int16_t red_mult, green_mult, blue_mult, alpha_mult;
+  int16_t red_add, green_add, blue_add, alpha_add;
+} swfr_color_transform;
+
 /* DisplayPrimitive::{Shape(StoredShape), MorphShape(StoredMorphShape)} */
 typedef struct swfr_display_primitive {
   uint32_t kind;   /* swfr_primitive_kind */
@@ -162,8 +174,10 @@ typedef struct swfr_display_primitive {
   uint16_t flags;  /* SWFR_PRIM_RATIO_F32: ratio_f replaces ratio */
   float ratio_f;   /* the TypeScript renderer's MorphShape.ratio, a number in 0..1 (ts/src/lib/display/morph-shape.ts:5-10,
                       canvas-renderer.ts:190-205); lets a caller ask for exactly 0.5 */
+  swfr_color_transform color_transform; /* read when flags has SWFR_PRIM_COLOR_TRANSFORM */
 } swfr_display_primitive;
 #define SWFR_PRIM_RATIO_F32 1u
+#define SWFR_PRIM_COLOR_TRANSFORM 2u
 
 typedef struct swfr_stage {
   swfr_rgba8 background_color; /* carried; the reference TS renderer ignores it (canvas-renderer.ts:70-72) */
@@ -188,6 +202,9 @@ typedef struct swfr_display_object {
   uint8_t has_matrix;      /* `matrix?: Matrix` */
   swfr_swf_matrix matrix;  /* swf-tree Matrix: Sfixed16P16 epsilons + twips */
   float ratio;             /* MorphShape.ratio, a number in 0..1 */
+  uint8_t has_color_transform; /* applies to everything below a container (concatenated down the tree: the child's
+                                  transform first, mult = (Pm * Cm) >> 8, add = ((Pm * Ca) >> 8) + Pa, clamped to int16) */
+  swfr_color_transform color_transform;
   uint32_t n_children;     /* containers */
   const struct swfr_display_object *children;
 } swfr_display_object;

@@ -68,6 +68,8 @@ typedef struct {
   uint16_t ratio; /* MorphRatio (rs/src/stage.rs:28-34) */
   uint16_t use_ratio_f; /* != 0: ratio_f (the TypeScript renderer's number in 0..1, display/morph-shape.ts) replaces ratio */
   float ratio_f;
+  int32_t has_cx; /* != 0: cx is a swf-tree ColorTransformWithAlpha for this draw (include/swfr.h swfr_color_transform) */
+  int16_t cx[8];  /* red, green, blue, alpha mult (Sfixed8P8 epsilons), then red, green, blue, alpha add */
 } swfo_item;
 
 typedef struct {
@@ -415,6 +417,7 @@ typedef struct {
   const uint32_t *lut;
   const swfo_bitmap *bmp;
   int valid;
+  const int16_t *cx; /* colour transform of the draw (NULL: none) */
 } paint_inst;
 
 static inline uint32_t mul_un8(uint32_t a, uint32_t b) { /* pixman MUL_UN8 */
@@ -447,8 +450,39 @@ static uint32_t solid_premul8(double r8, double g8, double b8, double alpha) {
   return (r16 >> 8) | ((g16 >> 8) << 8) | ((b16 >> 8) << 16) | ((a16 >> 8) << 24);
 }
 
+/* swf-tree ColorTransformWithAlpha on one straight 8-bit channel (the reference renderer has no colour-transform input;
+ * these are the SWF semantics, defined by this file: "parity unpinned") */
+static int cx_channel(int c, int mult, int add) {
+  int v = (int)(((int64_t)c * mult) >> 8) + add; /* floor, also for negative products */
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+/* ... on a premultiplied pixel (gradients, bitmaps): un-premultiply, transform, premultiply - integers throughout */
+static uint32_t cx_premul(uint32_t p, const int16_t *cx) {
+  int a = (int)(p >> 24);
+  int a2 = cx_channel(a, cx[3], cx[7]);
+  uint32_t out = (uint32_t)a2 << 24;
+  for (int k = 0; k < 3; k++) {
+    int c = (int)((p >> (8 * k)) & 255);
+    int s = a ? (c * 255 + a / 2) / a : 0;
+    if (s > 255) s = 255;
+    int c2 = cx_channel(s, cx[k], cx[4 + k]);
+    out |= (uint32_t)((c2 * a2 + 127) / 255) << (8 * k);
+  }
+  return out;
+}
+/* ... on a solid fill: the colour is transformed before it is premultiplied; alpha goes through 8 bits */
+static uint32_t cx_solid(double r8, double g8, double b8, double alpha, const int16_t *cx) {
+  double af = (double)(float)alpha;
+  if (af < 0) af = 0;
+  if (af > 1) af = 1;
+  int a8 = (int)(af * 255.0 + 0.5);
+  int r2 = cx_channel((int)r8, cx[0], cx[4]), g2 = cx_channel((int)g8, cx[1], cx[5]), b2 = cx_channel((int)b8, cx[2], cx[6]);
+  int a2 = cx_channel(a8, cx[3], cx[7]);
+  return solid_premul8((double)r2, (double)g2, (double)b2, a2 / 255.0);
+}
+
 /* css-color.ts:11-13 through node-canvas' rgba() parser, for a lerped normalised colour */
-static uint32_t morph_solid(const uint8_t c0[4], const uint8_t c1[4], double r) {
+static uint32_t morph_solid(const uint8_t c0[4], const uint8_t c1[4], double r, const int16_t *cx) {
   double ch[4];
   for (int i = 0; i < 4; i++) ch[i] = lerp_ref(c0[i] / 255.0, c1[i] / 255.0, r);
   /* red: (r * 0xff) & 0xff  (ToInt32 truncation) */
@@ -460,19 +494,23 @@ static uint32_t morph_solid(const uint8_t c0[4], const uint8_t c1[4], double r) 
   if (g > 255) g = 255;
   if (b < 0) b = 0;
   if (b > 255) b = 255;
-  return solid_premul8(red, g, b, ch[3]);
+  return cx ? cx_solid(red, g, b, ch[3], cx) : solid_premul8(red, g, b, ch[3]);
 }
 
-static void make_paint(const swfo_scene *sc, const swfo_paint *p, const double m[6], double ratio, paint_inst *out) {
+static void make_paint(const swfo_scene *sc, const swfo_paint *p, const double m[6], double ratio, const int16_t *cx,
+                       paint_inst *out) {
   int is_morph = p->color_is_morph;
   memset(out, 0, sizeof(*out));
   out->type = p->type;
   out->spread = p->spread;
   out->repeating = p->repeating;
   out->valid = 1;
+  out->cx = cx;
   if (p->type == SWFO_PAINT_SOLID) {
     if (is_morph)
-      out->solid = morph_solid(p->color0, p->color1, ratio);
+      out->solid = morph_solid(p->color0, p->color1, ratio, cx);
+    else if (cx)
+      out->solid = cx_solid(p->color0[0], p->color0[1], p->color0[2], p->color0[3] / 255.0, cx);
     else
       out->solid = solid_premul8(p->color0[0], p->color0[1], p->color0[2], p->color0[3] / 255.0);
     return;
@@ -668,6 +706,9 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
     for (int i = 0; i < 6; i++) m0[i] = (double)item->m[i];
     ctm_from_matrix(m0, m);
     double ratio = item->use_ratio_f ? (double)item->ratio_f : (double)item->ratio / 65535.0;
+    /* an identity transform is no transform (un-premultiplying and premultiplying a pixel again is lossy) */
+    static const int16_t cx_identity[8] = {256, 256, 256, 256, 0, 0, 0, 0};
+    const int16_t *item_cx = (item->has_cx && memcmp(item->cx, cx_identity, sizeof cx_identity) != 0) ? item->cx : NULL;
     for (int lp = 0; lp < def->n_path; lp++, path_inst++) {
       /* ---- flatten this path's segments ---- */
       size_t ne = 0;
@@ -720,7 +761,7 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
       if (ne == 0) continue;
       /* ---- paint ---- */
       paint_inst paint;
-      make_paint(sc, &sc->paints[def->first_path + lp], m0, ratio, &paint);
+      make_paint(sc, &sc->paints[def->first_path + lp], m0, ratio, item_cx, &paint);
       /* A path whose paint cannot be evaluated, or whose solid colour is premultiplied 0 (alpha 0: over() returns the
        * destination unchanged), composites nothing: it is flattened (the edge tap above lists it) but not binned. */
       if (!paint.valid || (paint.type == SWFO_PAINT_SOLID && paint.solid == 0)) continue;
@@ -787,6 +828,7 @@ int swfo_render(const swfo_scene *sc, uint8_t *out_premul_rgba, swfo_debug *dbg)
                 }
                 if (!mcov) continue;
                 uint32_t src = eval_paint(&paint, X, Y);
+                if (paint.cx && paint.type != SWFO_PAINT_SOLID) src = cx_premul(src, paint.cx);
                 fb[(size_t)Y * W + X] = over_masked(fb[(size_t)Y * W + X], src, mcov);
               }
             }

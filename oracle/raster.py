@@ -63,7 +63,7 @@ class Def(C.Structure):
 
 class Item(C.Structure):
     _fields_ = [("def_", C.c_int32), ("m", C.c_float * 6), ("ratio", C.c_uint16), ("use_ratio_f", C.c_uint16),
-                ("ratio_f", C.c_float)]
+                ("ratio_f", C.c_float), ("has_cx", C.c_int32), ("cx", C.c_int16 * 8)]
 
 
 class Bitmap(C.Structure):
@@ -253,8 +253,10 @@ class _Builder:
         self.defs.append((first_seg, len(self.segs) - first_seg, first_path, len(paths), 1 if is_morph else 0))
         return len(self.defs) - 1
 
-    def add_item(self, def_index, matrix, ratio=0, ratio_f=None):
-        self.items.append((def_index, matrix, ratio, ratio_f))
+    def add_item(self, def_index, matrix, ratio=0, ratio_f=None, cx=None):
+        """cx: a colour transform for this draw - eight integers, red/green/blue/alpha mult (256 = 1.0) then
+        red/green/blue/alpha add (include/swfr.h swfr_color_transform)."""
+        self.items.append((def_index, matrix, ratio, ratio_f, cx))
 
     def scene(self, width, height, background=None):
         """background: None = transparent clear (the TypeScript renderer), or (r, g, b) = opaque stage colour."""
@@ -269,13 +271,16 @@ class _Builder:
         for i, d in enumerate(self.defs):
             defs[i].first_seg, defs[i].n_seg, defs[i].first_path, defs[i].n_path, defs[i].is_morph = d
         items = (Item * max(1, len(self.items)))()
-        for i, (d, m, r, rf) in enumerate(self.items):
+        for i, (d, m, r, rf, cx) in enumerate(self.items):
             items[i].def_ = d
             items[i].m[:] = [float(np.float32(v)) for v in m]
             items[i].ratio = r
             if rf is not None:
                 items[i].use_ratio_f = 1
                 items[i].ratio_f = float(np.float32(rf))
+            if cx is not None:
+                items[i].has_cx = 1
+                items[i].cx[:] = [int(v) for v in cx]
         bitmaps = (Bitmap * max(1, len(self.bitmaps)))()
         for i, (w, h, pm) in enumerate(self.bitmaps):
             bitmaps[i].w, bitmaps[i].h = w, h
@@ -390,7 +395,7 @@ def add_shape_def(b: _Builder, compiled):
     return b.add_def(paths, False)
 
 
-def add_morph_shape_item(b: _Builder, compiled, matrix, ratio_u16, ratio_f=None):
+def add_morph_shape_item(b: _Builder, compiled, matrix, ratio_u16, ratio_f=None, cx=None):
     """Morph shape: fills as one morph definition; visible strokes as a transient static definition
     expanded at this ratio (stroke geometry depends on the lerped path and width).  ratio_f (float32, the
     TypeScript renderer's ratio in 0..1) replaces ratio_u16 / 65535 when given."""
@@ -430,9 +435,9 @@ def add_morph_shape_item(b: _Builder, compiled, matrix, ratio_u16, ratio_f=None)
             segs = [(k, [x0, y0, cx, cy, x1, y1], [x0, y0, cx, cy, x1, y1]) for (k, x0, y0, cx, cy, x1, y1) in stroker.contours_to_segments(contours)]
             lines.append((paint, segs))
     if fills:
-        b.add_item(b.add_def(fills, True), matrix, ratio_u16, ratio_f)
+        b.add_item(b.add_def(fills, True), matrix, ratio_u16, ratio_f, cx)
     if lines:
-        b.add_item(b.add_def(lines, False), matrix, ratio_u16, ratio_f)
+        b.add_item(b.add_def(lines, False), matrix, ratio_u16, ratio_f, cx)
 
 
 # ---------------------------------------------------------------------------------------------

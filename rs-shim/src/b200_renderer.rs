@@ -44,6 +44,7 @@ fn primitive(p: &DisplayPrimitive) -> swfr_display_primitive {
       ratio: 0,
       flags: 0,
       ratio_f: 0.0,
+      color_transform: swfr_color_transform::default(),
     },
     DisplayPrimitive::MorphShape(m) => swfr_display_primitive {
       kind: SWFR_PRIM_MORPH_SHAPE,
@@ -52,6 +53,7 @@ fn primitive(p: &DisplayPrimitive) -> swfr_display_primitive {
       ratio: m.ratio.0, // MorphRatio(u16): 0 = start, 65535 = end (rs/src/stage.rs:28-34)
       flags: 0,
       ratio_f: 0.0,
+      color_transform: swfr_color_transform::default(),
     },
   }
 }
@@ -209,6 +211,7 @@ impl Renderer for B200Renderer {
       ratio: 0,
       flags: 0,
       ratio_f: 0.0,
+      color_transform: swfr_color_transform::default(),
     };
     let stage = swfr_stage { background_color: swfr_rgba8::default(), n_primitives: 1, display_root: &prim };
     let rc = unsafe { swfr_render(self.handle, &stage) };

@@ -4,7 +4,7 @@
 
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const SWFR_ABI_VERSION: u32 = 2;
+pub const SWFR_ABI_VERSION: u32 = 3;
 
 pub const SWFR_OK: c_int = 0;
 pub const SWFR_ERR_INVALID_HANDLE: c_int = -1;
@@ -146,6 +146,21 @@ pub const SWFR_PRIM_SHAPE: u32 = 0;
 pub const SWFR_PRIM_MORPH_SHAPE: u32 = 1;
 pub const SWFR_PRIM_RATIO_F32: u16 = 1;
 
+/// swf-tree ColorTransformWithAlpha in raw units (mult: Sfixed8P8 epsilons, add: integers); not an input of the
+/// reference's Stage - left zeroed (flag clear) by this shim
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct swfr_color_transform {
+  pub red_mult: i16,
+  pub green_mult: i16,
+  pub blue_mult: i16,
+  pub alpha_mult: i16,
+  pub red_add: i16,
+  pub green_add: i16,
+  pub blue_add: i16,
+  pub alpha_add: i16,
+}
+
 /// DisplayPrimitive::{Shape(StoredShape), MorphShape(StoredMorphShape)} - rs/src/stage.rs:36-59
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -156,6 +171,7 @@ pub struct swfr_display_primitive {
   pub ratio: u16,
   pub flags: u16,
   pub ratio_f: f32,
+  pub color_transform: swfr_color_transform,
 }
 
 /// Stage - rs/src/stage.rs:4-9

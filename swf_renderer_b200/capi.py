@@ -21,6 +21,7 @@ COLOR_SRGB, COLOR_LINEAR_RGB = 0, 1
 RECORD_EDGE, RECORD_STYLE_CHANGE = 0, 1
 PRIM_SHAPE, PRIM_MORPH_SHAPE = 0, 1
 PRIM_RATIO_F32 = 1
+PRIM_COLOR_TRANSFORM = 2
 OPT_RETAIN_COMPILED, OPT_FRAMES_PER_PASS, OPT_PROFILE, OPT_HOST_THREADS, OPT_CLEAR_TO_BACKGROUND = 1, 2, 3, 4, 5
 OPT_DEBUG_TINY_ARENA = 6
 OPT_OCCLUSION_CHUNKS = 7
@@ -122,6 +123,19 @@ class DefineShape(C.Structure):
     ]
 
 
+class ColorTransform(C.Structure):  # swfr_color_transform: mult in Sfixed8P8 epsilons (256 = 1.0), add in integers
+    _fields_ = [
+        ("red_mult", C.c_int16),
+        ("green_mult", C.c_int16),
+        ("blue_mult", C.c_int16),
+        ("alpha_mult", C.c_int16),
+        ("red_add", C.c_int16),
+        ("green_add", C.c_int16),
+        ("blue_add", C.c_int16),
+        ("alpha_add", C.c_int16),
+    ]
+
+
 class DisplayPrimitive(C.Structure):
     _fields_ = [
         ("kind", C.c_uint32),
@@ -130,6 +144,7 @@ class DisplayPrimitive(C.Structure):
         ("ratio", C.c_uint16),
         ("flags", C.c_uint16),
         ("ratio_f", C.c_float),
+        ("color_transform", ColorTransform),
     ]
 
 
@@ -151,6 +166,8 @@ DisplayObject._fields_ = [
     ("has_matrix", C.c_uint8),
     ("matrix", SwfMatrix),
     ("ratio", C.c_float),
+    ("has_color_transform", C.c_uint8),
+    ("color_transform", ColorTransform),
     ("n_children", C.c_uint32),
     ("children", C.POINTER(DisplayObject)),
 ]

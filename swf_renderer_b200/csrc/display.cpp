@@ -44,16 +44,48 @@ Affine compose(const Affine &p, const Affine &c) {
   return r;
 }
 
-int walk(const swfr_display_object *objs, uint32_t n, const Affine &ctm, int depth, swfr_display_primitive *out, uint32_t cap,
-         uint32_t &count) {
+// SWF colour transforms concatenate down the tree like matrices: the child's applies to the colour first
+struct Cx {
+  bool on = false;
+  int32_t mult[4] = {256, 256, 256, 256}, add[4] = {0, 0, 0, 0};
+};
+
+int32_t clamp_i16(int32_t v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
+Cx from_swf(const swfr_color_transform &t) {
+  Cx r;
+  r.on = true;
+  const int16_t m[4] = {t.red_mult, t.green_mult, t.blue_mult, t.alpha_mult};
+  const int16_t a[4] = {t.red_add, t.green_add, t.blue_add, t.alpha_add};
+  for (int i = 0; i < 4; i++) {
+    r.mult[i] = m[i];
+    r.add[i] = a[i];
+  }
+  return r;
+}
+
+Cx compose(const Cx &p, const Cx &c) {
+  if (!p.on) return c;
+  Cx r;
+  r.on = true;
+  for (int i = 0; i < 4; i++) {
+    r.mult[i] = clamp_i16((p.mult[i] * c.mult[i]) >> 8);
+    r.add[i] = clamp_i16(((p.mult[i] * c.add[i]) >> 8) + p.add[i]);
+  }
+  return r;
+}
+
+int walk(const swfr_display_object *objs, uint32_t n, const Affine &ctm, const Cx &ccx, int depth, swfr_display_primitive *out,
+         uint32_t cap, uint32_t &count) {
   if (n && !objs) return SWFR_ERR_INVALID_ARGUMENT;
   if (depth > 256) return SWFR_ERR_INVALID_ARGUMENT;  // a display list is a tree of modest depth; refuse cycles
   for (uint32_t i = 0; i < n; i++) {
     const swfr_display_object &o = objs[i];
     const Affine m = o.has_matrix ? compose(ctm, from_swf(o.matrix)) : ctm;
+    const Cx cx = o.has_color_transform ? compose(ccx, from_swf(o.color_transform)) : ccx;
     switch (o.type) {
       case SWFR_DISPLAY_CONTAINER: {
-        int rc = walk(o.children, o.n_children, m, depth + 1, out, cap, count);
+        int rc = walk(o.children, o.n_children, m, cx, depth + 1, out, cap, count);
         if (rc != SWFR_OK) return rc;
         break;
       }
@@ -76,6 +108,11 @@ int walk(const swfr_display_object *objs, uint32_t n, const Affine &ctm, int dep
             p.ratio_f = o.ratio;
             double q = (double)o.ratio * 65535.0 + 0.5;
             p.ratio = (uint16_t)(q < 0 ? 0 : (q > 65535.0 ? 65535 : (int)q));
+          }
+          if (cx.on) {
+            p.flags |= SWFR_PRIM_COLOR_TRANSFORM;
+            p.color_transform = {(int16_t)cx.mult[0], (int16_t)cx.mult[1], (int16_t)cx.mult[2], (int16_t)cx.mult[3],
+                                 (int16_t)cx.add[0],  (int16_t)cx.add[1],  (int16_t)cx.add[2],  (int16_t)cx.add[3]};
           }
         }
         count++;
@@ -113,7 +150,7 @@ int swfr_flatten_display_stage(const swfr_display_stage *stage, swfr_display_pri
   uint32_t count = 0;
   int rc;
   try {
-    rc = walk(stage->children, stage->n_children, Affine{}, 0, out, cap, count);
+    rc = walk(stage->children, stage->n_children, Affine{}, Cx{}, 0, out, cap, count);
   } catch (...) {
     rc = SWFR_ERR_OOM;
   }

@@ -770,7 +770,36 @@ __device__ uint32_t solid_premul8(double r8, double g8, double b8, double alpha)
   return (r16 >> 8) | ((g16 >> 8) << 8) | ((b16 >> 8) << 16) | ((a16 >> 8) << 24);
 }
 
-__device__ uint32_t morph_solid(const uint8_t *c0, const uint8_t *c1, double r) {
+// swf-tree ColorTransformWithAlpha (include/swfr.h swfr_color_transform; oracle/raster.c cx_channel / cx_premul / cx_solid)
+__device__ __forceinline__ int cx_channel(int c, int mult, int add) {
+  const int v = ((c * mult) >> 8) + add;  // |c * mult| < 2^23: the arithmetic shift is the oracle's floor
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+__device__ uint32_t cx_premul(uint32_t p, const int16_t *cx) {
+  const int a = (int)(p >> 24);
+  const int a2 = cx_channel(a, cx[3], cx[7]);
+  uint32_t out = (uint32_t)a2 << 24;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int c = (int)((p >> (8 * k)) & 255u);
+    int s = a ? (c * 255 + a / 2) / a : 0;
+    if (s > 255) s = 255;
+    const int c2 = cx_channel(s, cx[k], cx[4 + k]);
+    out |= (uint32_t)((c2 * a2 + 127) / 255) << (8 * k);
+  }
+  return out;
+}
+__device__ uint32_t cx_solid(double r8, double g8, double b8, double alpha, const int16_t *cx) {
+  double af = (double)(float)alpha;
+  if (af < 0) af = 0;
+  if (af > 1) af = 1;
+  const int a8 = (int)(af * 255.0 + 0.5);
+  const int r2 = cx_channel((int)r8, cx[0], cx[4]), g2 = cx_channel((int)g8, cx[1], cx[5]), b2 = cx_channel((int)b8, cx[2], cx[6]);
+  const int a2 = cx_channel(a8, cx[3], cx[7]);
+  return solid_premul8((double)r2, (double)g2, (double)b2, a2 / 255.0);
+}
+
+__device__ uint32_t morph_solid(const uint8_t *c0, const uint8_t *c1, double r, const int16_t *cx) {
   double ch[4];
   for (int i = 0; i < 4; i++) ch[i] = lerp_ref(c0[i] / 255.0, c1[i] / 255.0, r);
   double red = (double)(((long long)(ch[0] * 255.0)) & 0xff);
@@ -780,7 +809,7 @@ __device__ uint32_t morph_solid(const uint8_t *c0, const uint8_t *c1, double r) 
   if (g > 255) g = 255;
   if (b < 0) b = 0;
   if (b > 255) b = 255;
-  return solid_premul8(red, g, b, ch[3]);
+  return cx ? cx_solid(red, g, b, ch[3], cx) : solid_premul8(red, g, b, ch[3]);
 }
 
 constexpr int kMaxTileRows = 1024;  // frames up to 16384 px high
@@ -849,9 +878,12 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
     uint32_t flags = 0;
     bool valid = true;
     double ratio = item_ratio(item);
+    const int16_t *cx = (item.kind & ITEM_CX) ? a.item_cx + (size_t)it * 8 : nullptr;
     if (dp.type == PAINT_SOLID) {
       if (dp.flags & PF_COLOR_MORPH)
-        rec.color = morph_solid(dp.color0, dp.color1, ratio);
+        rec.color = morph_solid(dp.color0, dp.color1, ratio, cx);
+      else if (cx)
+        rec.color = cx_solid(dp.color0[0], dp.color0[1], dp.color0[2], dp.color0[3] / 255.0, cx);
       else
         rec.color = solid_premul8(dp.color0[0], dp.color0[1], dp.color0[2], dp.color0[3] / 255.0);
       if ((rec.color >> 24) == 255) flags |= 1u;
@@ -914,6 +946,13 @@ __global__ void __launch_bounds__(256) k_path_setup(RenderArgs a) {
           pi.ptr = (unsigned long long)(a.ramps + (size_t)dp.lut * kRampSize);
           if (dp.flags & PF_OPAQUE_RAMP) flags |= 1u;
         }
+      }
+      if (cx) {
+        // every evaluated pixel goes through the transform; an opaque paint stays opaque only if alpha 255 maps to 255
+        pi.cx_on = 1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) pi.cx[k] = cx[k];
+        if (cx_channel(255, cx[3], cx[7]) != 255) flags &= ~1u;
       }
       a.paint_inst[pid] = pi;
     }
@@ -1975,8 +2014,9 @@ __device__ __noinline__ uint2 slot_coverage_sampled(const unsigned long long *__
 
 // Four resident blocks per SM (64 registers per thread): measured best - 3 blocks at 80 registers 0.75 ms per launch,
 // 4 at 64 0.54, 5 at 48 and 6 at 40 0.56 (1080p / 10 k shapes, 16 frames per launch).
-// SAMPLED: the pass draws stroke outlines (RenderArgs.has_sampled).  The variant without them does not carry the call to
-// slot_coverage_sampled (measured: its stack frame and register pressure cost the hot path 5 %).
+// SAMPLED: the pass draws stroke outlines (RenderArgs.has_sampled) or carries colour transforms (RenderArgs.has_cx): the
+// rare work.  The variant without them does not carry the call to slot_coverage_sampled (measured: its stack frame and
+// register pressure cost the hot path 5 %) nor the per-pixel colour transform of gradients and bitmaps.
 template <bool SAMPLED>
 __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint32_t slice, uint32_t frame_begin, uint32_t frame_end) {
   pdl_wait();  // (no launch_dependents: the successor's blocks would only squat in the slots the tail frees)
@@ -2106,7 +2146,8 @@ __global__ void __launch_bounds__(kFineWarps * 32, 4) k_fine(RenderArgs a, uint3
             const uint32_t mm = mlo & 255u;
             uint32_t v = px[0];
             if (mm) {
-              const uint32_t src = eval_paint(tf & 0xffu, pi, X0 + i, Y);
+              uint32_t src = eval_paint(tf & 0xffu, pi, X0 + i, Y);
+              if (SAMPLED && pi.cx_on) src = cx_premul(src, pi.cx);
               if (tf & 0x200u) {
                 v = src;
               } else {
@@ -2340,7 +2381,7 @@ int launch_render(const RenderArgs &a, cudaStream_t st, cudaEvent_t *ev, cudaEve
   {
     const uint32_t fs = fine_slice_frames(a.n_frames), ns = fine_slices(a.n_frames);
     for (uint32_t k = 0; k < ns; k++) {
-      if (a.has_sampled)
+      if (a.has_sampled | a.has_cx)
         launch_k(k_fine<true>, dim3(kNumSM * fine_blocks), dim3(kFineWarps * 32), st, a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));
       else
         launch_k(k_fine<false>, dim3(kNumSM * fine_blocks), dim3(kFineWarps * 32), st, a, k, k * fs, std::min(a.n_frames, (k + 1) * fs));

@@ -35,7 +35,8 @@ enum : uint16_t {
   ITEM_MORPH = 1,    // start/end segments in the morph store
   ITEM_DYNAMIC = 2,  // segments and paints in the batch's own stores (morph-shape strokes expanded for this draw)
   ITEM_KIND_MASK = 0xff,
-  ITEM_RATIO_F32 = 0x100
+  ITEM_RATIO_F32 = 0x100,
+  ITEM_CX = 0x200  // the draw carries a colour transform (RenderArgs.item_cx)
 };
 
 // Per path instance, read by binning and by the fine kernel: 16 bytes.
@@ -56,9 +57,10 @@ struct PaintInst {
   int32_t bw, bh;          // bitmap size
   uint32_t spread, repeating;
   float inv_bw, inv_bh;    // bitmaps: 1 / bw, 1 / bh (float division)
-  uint32_t pad[2];
+  uint32_t cx_on, pad;     // cx_on != 0: the draw's colour transform applies to every evaluated pixel (k_fine<true> only)
+  int16_t cx[8];           // swfr_color_transform: red, green, blue, alpha mult (8.8), then the four adds
 };
-static_assert(sizeof(PaintInst) == 80, "PaintInst is staged as five uint4");
+static_assert(sizeof(PaintInst) == 96, "PaintInst is staged as six uint4");
 
 // One draw of a morph shape's strokes: the device stroker (k_stroke) writes its outline into the batch's dynamic
 // segment store, seg_cap entries from seg_first on (unused ones are marked empty), and the bounds of every visible line
@@ -141,6 +143,8 @@ struct RenderArgs {
   // occlusion culling by depth chunks: the items of every frame are split into n_chunks ranges
   // in paint order; chunks are binned from the top one down, and what a chunk finds completely covered by an opaque
   // path hides the geometry of the chunks below it
+  uint32_t has_cx;              // host-known: a draw of the pass carries a colour transform (k_fine<true> as well)
+  const int16_t *item_cx;       // [n_items][8] colour transforms (swfr_color_transform), or null when has_cx == 0
   uint32_t has_sampled;         // host-known: the pass draws stroke outlines (k_fine<true>: coverage by sub-scanlines for them)
   uint32_t n_chunks;            // host-known
   const uint32_t *chunk_items;  // (n_chunks + 1) * n_frames: first item of chunk c in frame f at [c * n_frames + f]

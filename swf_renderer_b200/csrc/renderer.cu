@@ -93,6 +93,7 @@ struct Pass {
   uint32_t n_chunks = 1;  // depth chunks for occlusion culling
   uint32_t job_first = 0, n_jobs = 0;  // stroke jobs of the pass' frames
   bool has_sampled = false;  // a frame of the pass draws a stroke outline: k_fine with the sub-scanline coverage routine
+  bool has_cx = false;       // a draw of the pass carries a colour transform
 };
 
 struct BitmapRes {
@@ -121,6 +122,7 @@ struct swfr_batch {
   uint32_t n_frames = 0;
   std::vector<Pass> passes;
   PinnedArr<DrawItem> items;
+  PinnedArr<swfr_color_transform> item_cx;  // parallel to items; empty unless a draw of the batch carries a colour transform
   PinnedArr<uint32_t> seg_off, path_off, frame_off;  // concatenated per pass ([n+1] each)
   PinnedArr<uint32_t> chunk_items;                   // per pass: (n_chunks + 1) x n_frames first items of the depth chunks
   PinnedArr<uint32_t> frame_bg;                      // per frame: premultiplied RGBA8 the frame starts from
@@ -129,6 +131,7 @@ struct swfr_batch {
   PinnedArr<DefPaint> dyn_paints;
   PinnedArr<StrokeJob> jobs;  // in frame order: the jobs of a pass are contiguous
   size_t dyn_seg_count = 0;
+  DevBuf d_item_cx;
   DevBuf d_items, d_seg_off, d_path_off, d_frame_off, d_dyn_segs, d_dyn_paints, d_frame_bg, d_chunk_items, d_jobs;
   bool resident = false;
   uint64_t n_prims = 0, n_seginst = 0, n_paths = 0;
@@ -388,6 +391,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   struct FrameSum {
     uint64_t seg = 0, path = 0, items = 0;
     bool sampled = false;  // the frame draws a stroke outline
+    bool cx = false;       // a draw of the frame carries a colour transform
     int err = SWFR_OK;
     uint32_t bad_id = 0;
     std::vector<DynItem> dyn;
@@ -412,6 +416,13 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
     }
     err = SWFR_ERR_INVALID_ARGUMENT;
     return nullptr;
+  };
+  // an identity transform is no transform (un-premultiplying and premultiplying a gradient pixel again is lossy)
+  auto prim_cx = [](const swfr_display_primitive &pr) -> bool {
+    if (!(pr.flags & SWFR_PRIM_COLOR_TRANSFORM)) return false;
+    const swfr_color_transform &t = pr.color_transform;
+    return !(t.red_mult == 256 && t.green_mult == 256 && t.blue_mult == 256 && t.alpha_mult == 256 && t.red_add == 0 &&
+             t.green_add == 0 && t.blue_add == 0 && t.alpha_add == 0);
   };
   auto prim_ratio = [](const swfr_display_primitive &pr) -> double {
     return (pr.flags & SWFR_PRIM_RATIO_F32) ? (double)pr.ratio_f : (double)pr.ratio / 65535.0;
@@ -448,6 +459,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         s.path += de->path_count;
         s.items += 1;
         s.sampled |= de->has_sampled != 0;
+        s.cx |= prim_cx(pr);
         if (pr.kind == SWFR_PRIM_MORPH_SHAPE && r->morph_strokes[pr.id].line_count) {
           // the lines that are visible at this ratio (lerped alpha > 0) become the paths of one more draw item; their
           // geometry is left to the device (no per-draw host geometry), `seg_cap` segments are reserved for it
@@ -518,6 +530,7 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
       path_run += sums[f].path;
       it_run += sums[f].items;
       p.has_sampled |= sums[f].sampled;
+      p.has_cx |= sums[f].cx;
       dyn_seg_at += sums[f].dyn_segs;
       dyn_paint_at += sums[f].dyn_paints.size();
       job_at += sums[f].dyn.size();
@@ -564,6 +577,9 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
   }
   b.n_prims = total_prims;
   CK(b.items.resize(items_at));
+  bool any_cx = false;
+  for (const Pass &p : b.passes) any_cx |= p.has_cx;
+  CK(b.item_cx.resize(any_cx ? items_at : 0));
   CK(b.seg_off.resize(seg_off_at));
   CK(b.path_off.resize(path_off_at));
   CK(b.frame_off.resize(frame_off_at));
@@ -587,6 +603,8 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
       const FrameBase &fb = base[f];
       const FrameSum &fs = sums[f];
       DrawItem *items = b.items.data() + fb.item_at;
+      swfr_color_transform *cxs = b.item_cx.size() ? b.item_cx.data() + fb.item_at : nullptr;
+      const swfr_color_transform cx_identity = {256, 256, 256, 256, 0, 0, 0, 0};
       uint32_t *so = b.seg_off.data() + fb.seg_off_at, *po = b.path_off.data() + fb.path_off_at;
       uint32_t seg_run = fb.seg0, path_run = fb.path0;
       b.frame_off[fb.frame_off_at] = path_run;
@@ -605,9 +623,12 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
         it.path_off = path_run;
         it.frame = local_frame;
         it.ratio = pr.ratio;
-        it.kind = (uint16_t)((de->is_morph ? ITEM_MORPH : ITEM_STATIC) | ((pr.flags & SWFR_PRIM_RATIO_F32) ? ITEM_RATIO_F32 : 0));
+        const bool has_cx = prim_cx(pr);
+        const uint16_t item_flags = (uint16_t)(((pr.flags & SWFR_PRIM_RATIO_F32) ? ITEM_RATIO_F32 : 0) | (has_cx ? ITEM_CX : 0));
+        it.kind = (uint16_t)((de->is_morph ? ITEM_MORPH : ITEM_STATIC) | item_flags);
         it.ratio_f32 = pr.ratio_f;
         items[k] = it;
+        if (cxs) cxs[k] = has_cx ? pr.color_transform : cx_identity;
         so[k] = seg_run;
         po[k] = path_run;
         k++;
@@ -618,8 +639,9 @@ int build_batch(swfr_renderer *r, const swfr_stage *stages, uint32_t n, swfr_bat
           it.seg_first = (uint32_t)(fb.dyn_seg_at + d.seg_at);
           it.paint_first = (uint32_t)(fb.dyn_paint_at + d.paint_at);
           it.path_off = path_run;
-          it.kind = (uint16_t)(ITEM_DYNAMIC | ((pr.flags & SWFR_PRIM_RATIO_F32) ? ITEM_RATIO_F32 : 0));
+          it.kind = (uint16_t)(ITEM_DYNAMIC | item_flags);
           items[k] = it;
+          if (cxs) cxs[k] = has_cx ? pr.color_transform : cx_identity;
           const swfr_renderer::MorphStroke &ms = r->morph_strokes[d.morph_id];
           StrokeJob job{};
           job.line_first = ms.line_first;
@@ -657,6 +679,10 @@ int upload_batch(swfr_renderer *r, swfr_batch &b) {
   CK(b.d_path_off.reserve(std::max<size_t>(b.path_off.bytes(), 256)));
   CK(b.d_frame_off.reserve(std::max<size_t>(b.frame_off.bytes(), 256)));
   if (b.items.bytes()) CK(cudaMemcpyAsync(b.d_items.p, b.items.data(), b.items.bytes(), cudaMemcpyHostToDevice, st));
+  if (b.item_cx.bytes()) {
+    CK(b.d_item_cx.reserve(b.item_cx.bytes()));
+    CK(cudaMemcpyAsync(b.d_item_cx.p, b.item_cx.data(), b.item_cx.bytes(), cudaMemcpyHostToDevice, st));
+  }
   if (b.seg_off.bytes()) CK(cudaMemcpyAsync(b.d_seg_off.p, b.seg_off.data(), b.seg_off.bytes(), cudaMemcpyHostToDevice, st));
   if (b.path_off.bytes()) CK(cudaMemcpyAsync(b.d_path_off.p, b.path_off.data(), b.path_off.bytes(), cudaMemcpyHostToDevice, st));
   if (b.frame_off.bytes())
@@ -806,6 +832,8 @@ RenderArgs make_args(swfr_renderer *r, const swfr_batch &b, const Pass &p, size_
   a.frame_bg = b.d_frame_bg.as<uint32_t>() + p.f0;
   a.n_chunks = p.n_chunks;
   a.has_sampled = p.has_sampled ? 1u : 0u;
+  a.has_cx = p.has_cx ? 1u : 0u;
+  a.item_cx = p.has_cx ? b.d_item_cx.as<int16_t>() + p.items_at * 8 : nullptr;
   a.chunk_items = b.d_chunk_items.as<uint32_t>() + p.chunk_at;
   a.tile_cover = A.tile_cover.as<uint32_t>();
   a.path_alive = A.path_alive.as<uint32_t>();

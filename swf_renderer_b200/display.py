@@ -34,9 +34,24 @@ class Matrix:
 
 
 @dataclass
+class ColorTransform:
+    """swf-tree ColorTransformWithAlpha: mult in Sfixed8P8 epsilons (256 = 1.0), add in integers.  The reference's
+    display objects carry no colour transform; this is the SWF place-object field, concatenated down the tree."""
+    red_mult: int = 256
+    green_mult: int = 256
+    blue_mult: int = 256
+    alpha_mult: int = 256
+    red_add: int = 0
+    green_add: int = 0
+    blue_add: int = 0
+    alpha_add: int = 0
+
+
+@dataclass
 class Shape:
     definition: dict
     matrix: Optional[Matrix] = None
+    color_transform: Optional[ColorTransform] = None
 
 
 @dataclass
@@ -44,12 +59,14 @@ class MorphShape:
     definition: dict
     matrix: Optional[Matrix] = None
     ratio: float = 0.0  # 0..1
+    color_transform: Optional[ColorTransform] = None
 
 
 @dataclass
 class DisplayObjectContainer:
     children: List["DisplayObject"] = field(default_factory=list)
     matrix: Optional[Matrix] = None
+    color_transform: Optional[ColorTransform] = None
 
 
 DisplayObject = Union[DisplayObjectContainer, MorphShape, Shape]
@@ -129,6 +146,11 @@ class CanvasRenderer:
             if o.matrix is not None:
                 arr[i].has_matrix = 1
                 arr[i].matrix = _matrix(o.matrix)
+            if o.color_transform is not None:
+                t = o.color_transform
+                arr[i].has_color_transform = 1
+                arr[i].color_transform = capi.ColorTransform(t.red_mult, t.green_mult, t.blue_mult, t.alpha_mult, t.red_add,
+                                                             t.green_add, t.blue_add, t.alpha_add)
             if isinstance(o, DisplayObjectContainer):
                 arr[i].type = capi.DISPLAY_CONTAINER
                 kids = self._objects(o.children, keep)

@@ -45,6 +45,9 @@ class Matrix2D:
 class StoredShape:  # DisplayPrimitive::Shape
     id: int
     matrix: Matrix2D = field(default_factory=Matrix2D)
+    # swf-tree ColorTransformWithAlpha (not an input of the reference renderer): eight integers, red/green/blue/alpha
+    # mult in Sfixed8P8 epsilons (256 = 1.0) then red/green/blue/alpha add; None = identity
+    color_transform: Optional[Sequence[int]] = None
 
 
 @dataclass
@@ -53,6 +56,7 @@ class StoredMorphShape:  # DisplayPrimitive::MorphShape
     matrix: Matrix2D = field(default_factory=Matrix2D)
     ratio: int = 0  # MorphRatio(u16): 0 = start, 65535 = end
     ratio_f: Optional[float] = None  # the TypeScript renderer's ratio (0..1, float32); replaces `ratio` when set
+    color_transform: Optional[Sequence[int]] = None  # see StoredShape
 
 
 DisplayPrimitive = Union[StoredShape, StoredMorphShape]
@@ -94,6 +98,9 @@ def _stage_arrays(stages: Sequence[Stage]):
                     prims[j].ratio_f = float(p.ratio_f)
             else:
                 prims[j].kind = capi.PRIM_SHAPE
+            if p.color_transform is not None:
+                prims[j].flags |= capi.PRIM_COLOR_TRANSFORM
+                prims[j].color_transform = capi.ColorTransform(*[int(v) for v in p.color_transform])
         keep.append(prims)
         arr[i].background_color = capi.Rgba8(*[int(v) for v in st.background_color])
         arr[i].n_primitives = len(st.display_root)

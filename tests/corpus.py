@@ -79,16 +79,17 @@ class Scene:
         self.morphs.append(tag)
         return len(self.morphs) - 1
 
-    def draw_shape(self, idx, matrix, frame=0):
+    def draw_shape(self, idx, matrix, frame=0, cx=None):
+        """cx (optional): colour transform of the draw, eight integers (mult x 4 in 8.8, add x 4)."""
         while len(self.frames) <= frame:
             self.frames.append([])
-        self.frames[frame].append(("shape", idx, list(matrix), 0))
+        self.frames[frame].append(("shape", idx, list(matrix), 0, cx))
 
-    def draw_morph(self, idx, matrix, ratio, frame=0, ratio_f=None):
+    def draw_morph(self, idx, matrix, ratio, frame=0, ratio_f=None, cx=None):
         """ratio: MorphRatio(u16); ratio_f (optional): the TypeScript renderer's float ratio, replaces it."""
         while len(self.frames) <= frame:
             self.frames.append([])
-        self.frames[frame].append(("morph", idx, list(matrix), int(ratio) if ratio_f is None else (int(ratio), float(ratio_f))))
+        self.frames[frame].append(("morph", idx, list(matrix), int(ratio) if ratio_f is None else (int(ratio), float(ratio_f)), cx))
 
 
 def render_oracle(scene: Scene, frame=0, want_debug=False):
@@ -98,18 +99,18 @@ def render_oracle(scene: Scene, frame=0, want_debug=False):
     b = raster._Builder(scene.bitmaps)
     shape_defs = {}
     morph_compiled = {}
-    for kind, idx, m, ratio in scene.frames[frame]:
+    for kind, idx, m, ratio, cx in scene.frames[frame]:
         if kind == "shape":
             if idx not in shape_defs:
                 shape_defs[idx] = raster.add_shape_def(b, cs.compile_shape(scene.shapes[idx]))
-            b.add_item(shape_defs[idx], m)
+            b.add_item(shape_defs[idx], m, cx=cx)
         else:
             if idx not in morph_compiled:
                 morph_compiled[idx] = cs.compile_morph_shape(scene.morphs[idx])
             if isinstance(ratio, tuple):
-                raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio[0], ratio[1])
+                raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio[0], ratio[1], cx=cx)
             else:
-                raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio)
+                raster.add_morph_shape_item(b, morph_compiled[idx], m, ratio, cx=cx)
     return raster.render_scene(b.scene(scene.width, scene.height), want_debug)
 
 
@@ -125,13 +126,13 @@ def make_product(scene: Scene, device=0, cuda_stream=None):
     stages = []
     for items in scene.frames:
         st = sw.Stage()
-        for kind, idx, m, ratio in items:
+        for kind, idx, m, ratio, cx in items:
             if kind == "shape":
-                st.display_root.append(sw.StoredShape(shape_ids[idx], sw.Matrix2D(m)))
+                st.display_root.append(sw.StoredShape(shape_ids[idx], sw.Matrix2D(m), cx))
             elif isinstance(ratio, tuple):
-                st.display_root.append(sw.StoredMorphShape(morph_ids[idx], sw.Matrix2D(m), ratio[0], ratio[1]))
+                st.display_root.append(sw.StoredMorphShape(morph_ids[idx], sw.Matrix2D(m), ratio[0], ratio[1], cx))
             else:
-                st.display_root.append(sw.StoredMorphShape(morph_ids[idx], sw.Matrix2D(m), ratio))
+                st.display_root.append(sw.StoredMorphShape(morph_ids[idx], sw.Matrix2D(m), ratio, None, cx))
         stages.append(st)
     return r, stages
 

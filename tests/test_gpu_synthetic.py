@@ -264,7 +264,7 @@ def test_occlusion_chunks_do_not_change_pixels(built_library, chunks):
     r2, st2 = corpus.make_product(sc2)
     r2.close()
     sid = {id(t): r.register_shape(t) for t in sc2.shapes}
-    stage2 = sw.Stage([sw.StoredShape(sid[id(sc2.shapes[idx])], sw.Matrix2D(m)) for _, idx, m, _ in sc2.frames[0]])
+    stage2 = sw.Stage([sw.StoredShape(sid[id(sc2.shapes[idx])], sw.Matrix2D(m)) for _, idx, m, _, _ in sc2.frames[0]])
     empty = sw.Stage([])
     r.render_batch([stages[0], stage2, empty, stages[0]])
     np.testing.assert_array_equal(r.get_image(frame=0, premultiplied=True).data, ref)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built_library):
     from swf_renderer_b200 import capi
 
     assert set(capi.PROTOTYPES) == declared
-    assert built_library.swfr_abi_version() == 2
+    assert built_library.swfr_abi_version() == 3
 
 
 def test_no_cuda_device_is_a_loud_error_not_a_fallback(built_library):
