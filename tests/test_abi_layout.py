@@ -146,3 +146,12 @@ def test_rust_shim_structs_have_the_headers_layout(c_layout):
 def test_rust_shim_declares_the_current_abi_version(built_library):
     m = re.search(r"SWFR_ABI_VERSION:\s*u32\s*=\s*(\d+)", open(FFI_RS).read())
     assert int(m.group(1)) == built_library.swfr_abi_version()
+
+
+def test_ts_addon_type_checks_against_the_header():
+    """ts-shim/src/addon.cc (the N-API binding a maintainer adds to the reference's TypeScript package) cannot be built
+    here - no Node toolchain - but its use of include/swfr.h can be type-checked: g++ -fsyntax-only against a
+    declarations-only stand-in for <napi.h> (tests/mock_napi)."""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "tests", "mock_napi"), "-I",
+                        os.path.dirname(HEADER), os.path.join(ROOT, "ts-shim", "src", "addon.cc")], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
